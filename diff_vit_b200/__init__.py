@@ -1,0 +1,40 @@
+"""diff_vit_b200: B200-native integer inference path for P2-ViT quantized Vision Transformers.
+
+Drop-in for the reference's ``from models import *`` / ``from config import Config`` surface
+(reference: models/__init__.py:2-5): the ptq operators, the DeiT/ViT factories, ``Config`` and
+``str2model``.
+"""
+from .config import Config
+from .ptq import BIT_TYPE_DICT, BIT_TYPE_LIST, BitType, QAct, QConv2d, QIntLayerNorm, QIntSoftmax, QLinear
+from .vit_fquant import (Attention, Block, VisionTransformer, deit_base_patch16_224, deit_small_patch16_224,
+                         deit_tiny_patch16_224, vit_base_patch16_224, vit_large_patch16_224)
+from .layers_quant import Mlp, PatchEmbed
+
+_MODELS = {
+    'deit_tiny': deit_tiny_patch16_224,
+    'deit_small': deit_small_patch16_224,
+    'deit_base': deit_base_patch16_224,
+    'vit_base': vit_base_patch16_224,
+    'vit_large': vit_large_patch16_224,
+}
+
+
+def str2model(name):
+    """reference: test_quant.py:56-68 (Swin entries are an extension not built yet)."""
+    return _MODELS[name]
+
+
+def calibrate_model(model, batches):
+    """One calibration pass per batch, quantization parameters fixed on the last one, then
+    ``model_quant()`` (reference flow: test_quant.py:222-249, model_utility.py:121-175)."""
+    import torch
+    batches = list(batches)
+    model.model_open_calibrate()
+    with torch.no_grad():
+        for i, x in enumerate(batches):
+            if i == len(batches) - 1:
+                model.model_open_last_calibrate()
+            model(x, plot=False)
+    model.model_close_calibrate()
+    model.model_quant()
+    return model
