@@ -1,0 +1,117 @@
+"""ctypes binding of libp2vit_b200.so (C ABI declared in include/p2v.h).
+
+The library is built in-tree by ``python -m diff_vit_b200.build``.  Loading fails loudly when it is
+missing: quantized execution has no other implementation.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libp2vit_b200.so')
+
+EPI_GELU, EPI_RESIDUAL, EPI_OUT_POT, EPI_OUT_F32 = 1, 2, 4, 8
+
+_fp = C.POINTER(C.c_float)
+_i8p = C.POINTER(C.c_int8)
+_vp = C.c_void_p
+
+
+class Epilogue(C.Structure):
+    _fields_ = [('acc_scale', _vp), ('bias', _vp), ('out_scale', _vp), ('out_rscale', _vp), ('res_scale', _vp),
+                ('out2_scale', _vp), ('residual', _vp), ('aux_codes', _vp), ('out_f32', _vp),
+                ('out_zp', C.c_float), ('flags', C.c_uint32)]
+
+
+class LayerNorm(C.Structure):
+    _fields_ = [('in_mask', _vp), ('gamma', _vp), ('beta', _vp), ('ln_out_scale', _vp), ('ln_out_rscale', _vp),
+                ('post_mul', _vp), ('post_div1', _vp), ('post_div2', C.c_float), ('post_zp', C.c_float),
+                ('in_scale1', C.c_float), ('pot', C.c_int)]
+
+
+class Attention(C.Structure):
+    _fields_ = [('score_mul', C.c_float), ('score_zp', C.c_float), ('out_mul', C.c_double), ('out_zp', C.c_float),
+                ('softmax_levels', C.c_int), ('exp_lut', _vp), ('dump_scores', _vp), ('dump_softmax', _vp)]
+
+
+class LinearDesc(C.Structure):
+    _fields_ = [('w', _vp), ('n', C.c_int32), ('k', C.c_int32), ('epi', Epilogue)]
+
+
+class BlockDesc(C.Structure):
+    _fields_ = [('norm1', LayerNorm), ('norm2', LayerNorm), ('qkv', LinearDesc), ('proj', LinearDesc),
+                ('fc1', LinearDesc), ('fc2', LinearDesc), ('attn', Attention)]
+
+
+class VitDesc(C.Structure):
+    _fields_ = [('img_size', C.c_int32), ('patch_size', C.c_int32), ('in_chans', C.c_int32),
+                ('embed_dim', C.c_int32), ('depth', C.c_int32), ('num_heads', C.c_int32),
+                ('hidden_dim', C.c_int32), ('num_classes', C.c_int32),
+                ('input_scale', C.c_float), ('input_zp', C.c_float),
+                ('patch_embed', LinearDesc),
+                ('pe_scale', C.c_float), ('pe_zp', C.c_float), ('embed_scale', C.c_float), ('embed_zp', C.c_float),
+                ('cls_value', _vp), ('pos_value', _vp), ('embed_out_scale', _vp),
+                ('blocks', C.POINTER(BlockDesc)),
+                ('norm', LayerNorm), ('head', LinearDesc)]
+
+
+# name -> (restype, argtypes); every entry point include/p2v.h declares
+SYMBOLS = {
+    'p2v_last_error': (C.c_char_p, []),
+    'p2v_version': (C.c_int, []),
+    'p2v_check_device': (C.c_int, [C.c_int]),
+    'p2v_gemm_i8': (C.c_int, [_vp, C.c_int64, _vp, _vp, C.c_int64, C.c_int, C.c_int, C.c_int, C.POINTER(Epilogue), _vp]),
+    'p2v_gemm_i8_simt': (C.c_int, [_vp, C.c_int64, _vp, _vp, C.c_int64, C.c_int, C.c_int, C.c_int, C.POINTER(Epilogue), _vp]),
+    'p2v_gemm_i8_acc': (C.c_int, [_vp, C.c_int64, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp]),
+    'p2v_quant_patchify': (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, _vp]),
+    'p2v_embed_assemble': (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float,
+                                     _vp, _vp, _vp, _vp]),
+    'p2v_layernorm_int': (C.c_int, [_vp, C.c_int64, _vp, _vp, C.c_int, C.c_int, C.POINTER(LayerNorm), _vp]),
+    'p2v_attention_int': (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.POINTER(Attention), _vp]),
+    'p2v_fake_quant_f32': (C.c_int, [_vp, _vp, _vp, C.c_int64, C.c_int, C.c_int64, _vp, _vp, C.c_int, C.c_int, _vp]),
+    'p2v_vit_create': (C.c_int, [C.POINTER(VitDesc), C.c_int, C.POINTER(_vp)]),
+    'p2v_vit_destroy': (None, [_vp]),
+    'p2v_vit_workspace_bytes': (C.c_int64, [_vp, C.c_int]),
+    'p2v_vit_forward': (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, _vp, _vp, C.c_int, _vp]),
+    'p2v_vit_forward_host': (C.c_int, [_vp, _vp, _vp, C.c_int, _vp, _vp, _vp, _vp]),
+    'p2v_vit_launches_per_forward': (C.c_int, [_vp]),
+    'p2v_vit_dump_layout': (C.c_int, [_vp, C.c_int, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_int64),
+                                      C.POINTER(C.c_int64), C.POINTER(C.c_int32)]),
+    'p2v_vit_dump_bytes': (C.c_int64, [_vp, C.c_int]),
+}
+
+_lib = None
+
+
+class P2VError(RuntimeError):
+    pass
+
+
+def lib():
+    """The loaded library; raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise P2VError('%s is missing: run `python -m diff_vit_b200.build` (needs nvcc). Quantized '
+                           'execution has no fallback implementation.' % LIB_PATH)
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(handle, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise P2VError('libp2vit_b200 error %d: %s' % (rc, lib().p2v_last_error().decode()))
+
+
+def ptr(t):
+    """Device (or host) address of a tensor, None -> NULL."""
+    return None if t is None else t.data_ptr()
+
+
+def current_stream():
+    import torch
+    return torch.cuda.current_stream().cuda_stream

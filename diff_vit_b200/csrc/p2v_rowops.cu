@@ -1,0 +1,238 @@
+// p2v_rowops.cu - the HBM-bound element / row kernels of the integer forward:
+//   input QAct + im2col, token assembly, integer LayerNorm (+ consumer QAct), standalone fake-quant.
+// All fp32 steps follow the reference's op order through p2v_math.cuh.
+#include "p2v_common.cuh"
+#include "p2v_math.cuh"
+
+namespace p2v {
+
+__device__ __forceinline__ uint32_t pack4i(int q0, int q1, int q2, int q3) {
+  return (uint32_t)(q0 & 0xff) | ((uint32_t)(q1 & 0xff) << 8) | ((uint32_t)(q2 & 0xff) << 16) |
+         ((uint32_t)(q3 & 0xff) << 24);
+}
+
+// ---- input quantizer + patchify ------------------------------------------------------------------
+// One thread converts 16 consecutive pixels of one image row (64 B fp32 in, 16 B codes out).  With
+// p % 16 == 0 those 16 pixels are 16 consecutive K entries of one patch row: K = (c*p + kh)*p + kw.
+__global__ void quant_patchify_kernel(const float* __restrict__ x, int8_t* __restrict__ codes, int b, int c,
+                                      int h, int w, int p, float scale, float zp, int64_t total16) {
+  const int gw = w / p, gh = h / p;
+  const int k = c * p * p;
+  const int w16 = w / 16;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total16;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int xs = (int)(i % w16);
+    int64_t r = i / w16;
+    const int y = (int)(r % h);
+    r /= h;
+    const int ch = (int)(r % c);
+    const int img = (int)(r / c);
+    const float4* src = reinterpret_cast<const float4*>(x + (((int64_t)img * c + ch) * h + y) * w + xs * 16);
+    float4 v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = __ldg(src + j);
+    uint32_t o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      o[j] = pack4i(quant_div(v[j].x, scale, zp, -128, 127), quant_div(v[j].y, scale, zp, -128, 127),
+                    quant_div(v[j].z, scale, zp, -128, 127), quant_div(v[j].w, scale, zp, -128, 127));
+    }
+    const int px = xs * 16;
+    const int pw = px / p, kw = px % p, ph = y / p, kh = y % p;
+    const int64_t row = ((int64_t)img * gh + ph) * gw + pw;
+    *reinterpret_cast<uint4*>(codes + row * k + ((int64_t)ch * p + kh) * p + kw) = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+// ---- token assembly ------------------------------------------------------------------------------------
+// x = qact_embed(cat(cls, patches)) + qact_pos(pos_embed); out = qact1(x)   (models/vit_fquant.py:718-733)
+__global__ void embed_assemble_kernel(const int8_t* __restrict__ pe, int8_t* __restrict__ out, int b, int np,
+                                      int d, float pe_scale, float pe_zp, float embed_scale, float embed_zp,
+                                      const float* __restrict__ cls_value, const float* __restrict__ pos_value,
+                                      const float* __restrict__ out_scale, int64_t total4) {
+  const int d4 = d / 4;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total4;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int c0 = (int)(i % d4) * 4;
+    const int64_t tok = i / d4;
+    const int t = (int)(tok % (np + 1));
+    const int img = (int)(tok / (np + 1));
+    int q[4];
+    uint32_t word = 0;
+    if (t > 0) word = *reinterpret_cast<const uint32_t*>(pe + ((int64_t)img * np + (t - 1)) * d + c0);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float xe;
+      if (t == 0) {
+        xe = cls_value[c0 + j];
+      } else {
+        const float pv = fmul(fsub((float)(int8_t)((word >> (8 * j)) & 0xff), pe_zp), pe_scale);
+        const int qe = quant_div(pv, embed_scale, embed_zp, -128, 127);
+        xe = fmul(fsub((float)qe, embed_zp), embed_scale);
+      }
+      const float xv = fadd(xe, pos_value[(int64_t)t * d + c0 + j]);
+      q[j] = quant_div(xv, out_scale[c0 + j], 0.f, -128, 127);
+    }
+    *reinterpret_cast<uint32_t*>(out + tok * d + c0) = pack4i(q[0], q[1], q[2], q[3]);
+  }
+}
+
+// ---- integer LayerNorm ---------------------------------------------------------------------------------
+// One warp per row; each lane owns 4-channel groups (32-bit loads; rows are 4-byte aligned by contract).
+// kMaxGroups bounds d <= 32 * 4 * kMaxGroups.
+constexpr int kLnMaxGroups = 8;  // d <= 1024
+
+template <bool POT>
+__global__ void __launch_bounds__(256)
+layernorm_int_kernel(const int8_t* __restrict__ in, int64_t in_row_stride, int8_t* __restrict__ out,
+                     int32_t* __restrict__ ln_codes, int rows, int d, const p2v_layernorm p) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int groups = d >> 2;  // 4-channel groups in the row
+  const int8_t* src = in + (int64_t)row * in_row_stride;
+  float xq[kLnMaxGroups][4];
+  int sum = 0;
+  long long sumsq = 0;
+#pragma unroll
+  for (int g = 0; g < kLnMaxGroups; ++g) {
+    const int grp = g * 32 + lane;
+    if (grp < groups) {
+      const uint32_t word = *reinterpret_cast<const uint32_t*>(src + grp * 4);
+      const float4 mk = *reinterpret_cast<const float4*>(p.in_mask + grp * 4);
+      const float m[4] = {mk.x, mk.y, mk.z, mk.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int v = (int)(int8_t)((word >> (8 * j)) & 0xff) * (int)m[j];
+        xq[g][j] = (float)v;
+        sum += v;
+        sumsq += (long long)(v * v);
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    sumsq += __shfl_xor_sync(0xffffffffu, sumsq, o);
+  }
+  const LnRow st = ln_row_stats((long long)sum, sumsq, d, p.in_scale1);
+#pragma unroll
+  for (int g = 0; g < kLnMaxGroups; ++g) {
+    const int grp = g * 32 + lane;
+    if (grp < groups) {
+      const int c0 = grp * 4;
+      const float4 ga = *reinterpret_cast<const float4*>(p.gamma + c0);
+      const float4 be = *reinterpret_cast<const float4*>(p.beta + c0);
+      const float4 os = *reinterpret_cast<const float4*>(p.ln_out_scale + c0);
+      const float gam[4] = {ga.x, ga.y, ga.z, ga.w}, bet[4] = {be.x, be.y, be.z, be.w};
+      const float osc[4] = {os.x, os.y, os.z, os.w};
+      float ors[4] = {0.f, 0.f, 0.f, 0.f}, pm[4] = {1.f, 1.f, 1.f, 1.f}, pd[4] = {1.f, 1.f, 1.f, 1.f};
+      if (POT) {
+        const float4 r4 = *reinterpret_cast<const float4*>(p.ln_out_rscale + c0);
+        const float4 m4 = *reinterpret_cast<const float4*>(p.post_mul + c0);
+        ors[0] = r4.x; ors[1] = r4.y; ors[2] = r4.z; ors[3] = r4.w;
+        pm[0] = m4.x; pm[1] = m4.y; pm[2] = m4.z; pm[3] = m4.w;
+      } else {
+        const float4 d4 = *reinterpret_cast<const float4*>(p.post_div1 + c0);
+        pd[0] = d4.x; pd[1] = d4.y; pd[2] = d4.z; pd[3] = d4.w;
+      }
+      int q[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float code = ln_code<POT>(xq[g][j], st, gam[j], bet[j], osc[j], ors[j]);
+        if (ln_codes != nullptr) ln_codes[(int64_t)row * d + c0 + j] = (int)code;
+        float v;
+        if (POT) {
+          v = rne(fadd(fmul(code, pm[j]), p.post_zp));
+        } else {
+          // value on the LN grid, / SmoothQuant scale of the consumer, / its QAct scale (+ zp)
+          v = rne(fadd(fdiv(fdiv(fmul(code, osc[j]), pd[j]), p.post_div2), p.post_zp));
+        }
+        q[j] = clamp_i(v, -128, 127);
+      }
+      *reinterpret_cast<uint32_t*>(out + (int64_t)row * d + c0) = pack4i(q[0], q[1], q[2], q[3]);
+    }
+  }
+}
+
+// ---- standalone QAct on fp32 tensors -------------------------------------------------------------------
+__global__ void fake_quant_f32_kernel(const float* __restrict__ x, float* __restrict__ out, int8_t* __restrict__ codes,
+                                      int64_t total, int channels, int64_t inner, const float* __restrict__ scale,
+                                      const float* __restrict__ zero_point, int qmin, int qmax) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int ch = (int)((i / inner) % channels);
+    const float s = scale[ch], z = zero_point ? zero_point[ch] : 0.f;
+    const int q = quant_div(x[i], s, z, qmin, qmax);
+    if (codes != nullptr) codes[i] = (int8_t)q;
+    if (out != nullptr) out[i] = fmul(fsub((float)q, z), s);
+  }
+}
+
+static int grid_for(int64_t work, int block) {
+  int64_t g = (work + block - 1) / block;
+  const int64_t cap = (int64_t)kNumSMs * 16;
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace p2v
+
+using namespace p2v;
+
+extern "C" int p2v_quant_patchify(const float* x, int8_t* codes, int b, int c, int h, int w, int p, float scale,
+                                  float zero_point, void* stream) {
+  P2V_REQUIRE(x && codes, "p2v_quant_patchify: null pointer");
+  P2V_REQUIRE(b > 0 && c > 0 && p > 0 && h % p == 0 && w % p == 0, "p2v_quant_patchify: bad shape %dx%dx%dx%d p=%d", b,
+              c, h, w, p);
+  P2V_REQUIRE(p % 16 == 0 && w % 16 == 0, "p2v_quant_patchify: patch size and width must be multiples of 16");
+  const int64_t total16 = (int64_t)b * c * h * (w / 16);
+  quant_patchify_kernel<<<grid_for(total16, 256), 256, 0, (cudaStream_t)stream>>>(x, codes, b, c, h, w, p, scale,
+                                                                                  zero_point, total16);
+  P2V_CHECK_CUDA(cudaGetLastError());
+  return P2V_OK;
+}
+
+extern "C" int p2v_embed_assemble(const int8_t* pe, int8_t* out, int b, int np, int d, float pe_scale, float pe_zp,
+                                  float embed_scale, float embed_zp, const float* cls_value, const float* pos_value,
+                                  const float* out_scale, void* stream) {
+  P2V_REQUIRE(pe && out && cls_value && pos_value && out_scale, "p2v_embed_assemble: null pointer");
+  P2V_REQUIRE(b > 0 && np > 0 && d > 0 && d % 4 == 0, "p2v_embed_assemble: bad shape b=%d np=%d d=%d", b, np, d);
+  const int64_t total4 = (int64_t)b * (np + 1) * (d / 4);
+  embed_assemble_kernel<<<grid_for(total4, 256), 256, 0, (cudaStream_t)stream>>>(
+      pe, out, b, np, d, pe_scale, pe_zp, embed_scale, embed_zp, cls_value, pos_value, out_scale, total4);
+  P2V_CHECK_CUDA(cudaGetLastError());
+  return P2V_OK;
+}
+
+extern "C" int p2v_layernorm_int(const int8_t* in, int64_t in_row_stride, int8_t* out, int32_t* ln_codes, int rows,
+                                 int d, const p2v_layernorm* p, void* stream) {
+  P2V_REQUIRE(in && out && p, "p2v_layernorm_int: null pointer");
+  P2V_REQUIRE(rows > 0 && d > 0 && d % 4 == 0 && d <= 128 * kLnMaxGroups, "p2v_layernorm_int: bad shape rows=%d d=%d",
+              rows, d);
+  P2V_REQUIRE(in_row_stride % 4 == 0, "p2v_layernorm_int: row stride must be a multiple of 4 bytes");
+  P2V_REQUIRE(p->in_mask && p->gamma && p->beta && p->ln_out_scale, "p2v_layernorm_int: missing vectors");
+  const int warps = 8;
+  const int grid = (rows + warps - 1) / warps;
+  if (p->pot) {
+    P2V_REQUIRE(p->ln_out_rscale && p->post_mul, "p2v_layernorm_int: pot path needs ln_out_rscale and post_mul");
+    layernorm_int_kernel<true><<<grid, warps * 32, 0, (cudaStream_t)stream>>>(in, in_row_stride, out, ln_codes, rows,
+                                                                               d, *p);
+  } else {
+    P2V_REQUIRE(p->post_div1, "p2v_layernorm_int: non-pot path needs post_div1");
+    layernorm_int_kernel<false><<<grid, warps * 32, 0, (cudaStream_t)stream>>>(in, in_row_stride, out, ln_codes, rows,
+                                                                                d, *p);
+  }
+  P2V_CHECK_CUDA(cudaGetLastError());
+  return P2V_OK;
+}
+
+extern "C" int p2v_fake_quant_f32(const float* x, float* out, int8_t* codes, int64_t outer, int channels,
+                                  int64_t inner, const float* scale, const float* zero_point, int qmin, int qmax,
+                                  void* stream) {
+  P2V_REQUIRE(x && (out || codes) && scale, "p2v_fake_quant_f32: null pointer");
+  P2V_REQUIRE(outer > 0 && channels > 0 && inner > 0, "p2v_fake_quant_f32: bad shape");
+  const int64_t total = outer * channels * inner;
+  fake_quant_f32_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(x, out, codes, total, channels, inner,
+                                                                                 scale, zero_point, qmin, qmax);
+  P2V_CHECK_CUDA(cudaGetLastError());
+  return P2V_OK;
+}

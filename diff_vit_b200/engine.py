@@ -1,0 +1,206 @@
+"""The integer execution engine: a calibrated VisionTransformer -> libp2vit_b200.so.
+
+``IntegerEngine`` extracts the calibrated state once, builds one integer plan per ``bit_config``
+(plans are cached, so the mixed-precision sweeps of the reference re-use them), uploads the plan's
+tensors and binds them to a ``p2v_vit`` handle.  Torch owns every device buffer; the library only
+launches kernels on the caller's stream.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _cabi
+from .plan import build_plan, extract_state
+
+
+def _dev(t, device):
+    return t.to(device).contiguous()
+
+
+class _BoundPlan:
+    """A VitPlan uploaded to one device with its C descriptor and library handle."""
+
+    def __init__(self, plan, device):
+        self.plan = plan
+        self.device = device
+        self.keep = []          # device tensors referenced by raw pointers
+        lib = _cabi.lib()
+        a = plan.arch
+        desc = _cabi.VitDesc()
+        desc.img_size, desc.patch_size, desc.in_chans = a['img_size'], a['patch_size'], a['in_chans']
+        desc.embed_dim, desc.depth, desc.num_heads = a['embed_dim'], a['depth'], a['num_heads']
+        desc.hidden_dim, desc.num_classes = a['hidden_dim'], a['num_classes']
+        desc.input_scale, desc.input_zp = plan.input_scale, plan.input_zp
+        desc.patch_embed = self._linear(plan.patch_embed)
+        desc.pe_scale, desc.pe_zp = plan.pe_scale, plan.pe_zp
+        desc.embed_scale, desc.embed_zp = plan.embed_scale, plan.embed_zp
+        desc.cls_value = self._p(plan.cls_value)
+        desc.pos_value = self._p(plan.pos_value)
+        desc.embed_out_scale = self._p(plan.embed_out_scale)
+        self.blocks = (_cabi.BlockDesc * a['depth'])()
+        for i, b in enumerate(plan.blocks):
+            bd = self.blocks[i]
+            bd.norm1, bd.norm2 = self._ln(b.norm1), self._ln(b.norm2)
+            bd.qkv, bd.proj = self._linear(b.qkv), self._linear(b.proj)
+            bd.fc1, bd.fc2 = self._linear(b.fc1), self._linear(b.fc2)
+            bd.attn = self._attn(b.attn)
+        desc.blocks = C.cast(self.blocks, C.POINTER(_cabi.BlockDesc))
+        desc.norm = self._ln(plan.norm)
+        desc.head = self._linear(plan.head)
+        self.desc = desc
+        handle = C.c_void_p()
+        _cabi.check(lib.p2v_vit_create(C.byref(desc), device.index or 0, C.byref(handle)))
+        self.handle = handle
+        self.launches = lib.p2v_vit_launches_per_forward(handle)
+        self._buffers = {}
+
+    def _p(self, t):
+        if t is None:
+            return None
+        d = _dev(t, self.device)
+        self.keep.append(d)
+        return d.data_ptr()
+
+    def _linear(self, lp):
+        d = _cabi.LinearDesc()
+        d.w = self._p(lp.w)
+        d.n, d.k = lp.w.shape
+        e = d.epi
+        e.acc_scale, e.bias = self._p(lp.acc_scale), self._p(lp.bias)
+        e.out_scale, e.out_rscale = self._p(lp.out_scale), self._p(lp.out_rscale)
+        e.res_scale, e.out2_scale = self._p(lp.res_scale), self._p(lp.out2_scale)
+        e.out_zp, e.flags = lp.out_zp, lp.flags
+        return d
+
+    def _ln(self, p):
+        d = _cabi.LayerNorm()
+        d.in_mask, d.gamma, d.beta = self._p(p.in_mask), self._p(p.gamma), self._p(p.beta)
+        d.ln_out_scale, d.ln_out_rscale = self._p(p.ln_out_scale), self._p(p.ln_out_rscale)
+        d.post_mul, d.post_div1 = self._p(p.post_mul), self._p(p.post_div1)
+        d.post_div2, d.post_zp, d.in_scale1, d.pot = p.post_div2, p.post_zp, p.in_scale1, p.pot
+        return d
+
+    def _attn(self, p):
+        d = _cabi.Attention()
+        d.score_mul, d.score_zp, d.out_mul, d.out_zp = p.score_mul, p.score_zp, p.out_mul, p.out_zp
+        d.softmax_levels = p.levels
+        d.exp_lut = self._p(p.exp_lut)
+        return d
+
+    def buffers(self, batch):
+        """(workspace, logits, logit codes) for a batch size; allocated once so graph replays stay valid."""
+        if batch not in self._buffers:
+            nbytes = _cabi.lib().p2v_vit_workspace_bytes(self.handle, batch)
+            ws = torch.empty(nbytes + 1024, dtype=torch.uint8, device=self.device)
+            off = (-ws.data_ptr()) % 1024
+            logits = torch.empty(batch, self.plan.arch['num_classes'], dtype=torch.float32, device=self.device)
+            codes = torch.empty(batch, self.plan.arch['num_classes'], dtype=torch.int8, device=self.device)
+            self._buffers[batch] = (ws, ws.data_ptr() + off, logits, codes)
+        return self._buffers[batch]
+
+    def close(self):
+        if self.handle:
+            _cabi.lib().p2v_vit_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class IntegerEngine:
+    """Quantized forward of one calibrated model on one CUDA device."""
+
+    def __init__(self, model=None, state=None, device=None):
+        if state is None:
+            state = extract_state(model)
+        self.state = state
+        if device is None:
+            device = next(model.parameters()).device if model is not None else torch.device('cuda', 0)
+        self.device = torch.device(device)
+        if self.device.type != 'cuda':
+            if torch.cuda.is_available():
+                self.device = torch.device('cuda', torch.cuda.current_device())
+            else:
+                raise RuntimeError('the quantized forward runs only in the sm_100a kernels of libp2vit_b200.so; '
+                                   'no CUDA device is available and there is no CPU fallback')
+        if self.device.index is None:
+            self.device = torch.device('cuda', torch.cuda.current_device())
+        self._plans = {}
+
+    def bound(self, bit_config):
+        key = tuple(int(b) for b in bit_config)
+        if key not in self._plans:
+            self._plans[key] = _BoundPlan(build_plan(self.state, key), self.device)
+        return self._plans[key]
+
+    def _check_input(self, x, arch):
+        if x.dim() != 4 or x.shape[1] != arch['in_chans'] or x.shape[2] != arch['img_size'] or x.shape[3] != arch['img_size']:
+            raise AssertionError("Input image size (%d*%d) doesn't match model (%d*%d)." %
+                                 (x.shape[-2], x.shape[-1], arch['img_size'], arch['img_size']))
+
+    def forward_into(self, x, bit_config, use_graph=True):
+        """Launch the forward on the current stream; returns the engine-owned logits buffer."""
+        bp = self.bound(bit_config)
+        self._check_input(x, bp.plan.arch)
+        if not x.is_cuda:
+            raise RuntimeError('IntegerEngine.forward_into expects a CUDA tensor')
+        x = x.contiguous().float()
+        b = x.shape[0]
+        _, ws, logits, codes = bp.buffers(b)
+        _cabi.check(_cabi.lib().p2v_vit_forward(bp.handle, x.data_ptr(), logits.data_ptr(), codes.data_ptr(), b, ws,
+                                                None, 1 if use_graph else 0, _cabi.current_stream()))
+        self._last_input = x  # keep the (possibly re-laid-out) input alive until the stream consumed it
+        return logits
+
+    def forward(self, x, bit_config):
+        """Drop-in: fp32 logits [B, classes] on x's device (host inputs are copied to the GPU and back)."""
+        on_host = not x.is_cuda
+        xd = x.to(self.device, non_blocking=True) if on_host else x
+        out = self.forward_into(xd, bit_config).clone()
+        return out.cpu() if on_host else out
+
+    def forward_dump(self, x, bit_config):
+        """Forward that also returns every intermediate integer code tensor (parity tests, hooks)."""
+        bp = self.bound(bit_config)
+        self._check_input(x, bp.plan.arch)
+        lib = _cabi.lib()
+        x = x.to(self.device).contiguous().float()
+        b = x.shape[0]
+        _, ws, logits, codes = bp.buffers(b)
+        nbytes = lib.p2v_vit_dump_bytes(bp.handle, b)
+        dump = torch.zeros(nbytes, dtype=torch.uint8, device=self.device)
+        _cabi.check(lib.p2v_vit_forward(bp.handle, x.data_ptr(), logits.data_ptr(), codes.data_ptr(), b, ws,
+                                        dump.data_ptr(), 0, _cabi.current_stream()))
+        torch.cuda.synchronize(self.device)
+        host = dump.cpu().numpy()
+        out = {}
+        name, off, size, elem = C.c_char_p(), C.c_int64(), C.c_int64(), C.c_int32()
+        count = lib.p2v_vit_dump_layout(bp.handle, b, 0, C.byref(name), C.byref(off), C.byref(size), C.byref(elem))
+        for i in range(count):
+            lib.p2v_vit_dump_layout(bp.handle, b, i, C.byref(name), C.byref(off), C.byref(size), C.byref(elem))
+            raw = host[off.value:off.value + size.value]
+            key = name.value.decode()
+            if elem.value == 4:
+                out[key] = raw.view(np.int32).copy()
+            elif key.startswith('softmax/'):
+                out[key] = raw.view(np.uint8).copy()
+            else:
+                out[key] = raw.view(np.int8).copy()
+        return logits.clone(), out
+
+    def forward_host(self, x_host, logits_host, bit_config):
+        """End-to-end call on HOST buffers (pinned for async copies): H2D, forward, D2H, sync."""
+        bp = self.bound(bit_config)
+        b = x_host.shape[0]
+        _, ws, logits, _ = bp.buffers(b)
+        key = ('xdev', b)
+        if key not in bp._buffers:
+            bp._buffers[key] = torch.empty(x_host.shape, dtype=torch.float32, device=self.device)
+        xdev = bp._buffers[key]
+        _cabi.check(_cabi.lib().p2v_vit_forward_host(bp.handle, x_host.data_ptr(), logits_host.data_ptr(), b, ws,
+                                                     xdev.data_ptr(), logits.data_ptr(), _cabi.current_stream()))
+        return logits_host

@@ -1,0 +1,191 @@
+/* p2v.h - C ABI of libp2vit_b200.so: the B200 (sm_100a) integer inference path of P2-ViT.
+ *
+ * The reference (LeSN-Lab/diff-ViT) has no FFI: its boundary for this path is the Python nn.Module
+ * surface of models/ptq (QConv2d, QLinear, QAct, QIntLayerNorm, QIntSoftmax; models/ptq/layers.py) and
+ * VisionTransformer.forward (models/vit_fquant.py:780-799).  Each entry point below names the
+ * reference interface whose arithmetic it replaces.  INTEGRATION.md shows the ctypes binding.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative p2v_status; p2v_last_error() gives the message
+ *     of the calling thread's last failure;
+ *   - all pointers are DEVICE pointers unless the name says host; the caller owns every buffer;
+ *   - `stream` is a cudaStream_t passed as void*; calls are asynchronous on it;
+ *   - activation codes are int8 row-major [rows, channels]; weights are int8 [out, in] row-major
+ *     (int4 layers store their [-8,7] codes in int8);
+ *   - fp32 steps follow the reference's operation order (diff_vit_b200/csrc/p2v_math.cuh).
+ */
+#ifndef P2V_H_
+#define P2V_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  P2V_OK = 0,
+  P2V_ERR_INVALID = -1,     /* bad argument / unsupported shape */
+  P2V_ERR_CUDA = -2,        /* CUDA runtime or driver error */
+  P2V_ERR_UNSUPPORTED = -3, /* device is not compute capability 10.0 (kind::i8 tensor cores) */
+  P2V_ERR_STATE = -4        /* handle used before it was bound / wrong batch */
+} p2v_status;
+
+const char* p2v_last_error(void);
+int p2v_version(void);
+/* 0 when `device` is an sm_100 part (tcgen05 kind::i8 exists on B200, not on sm_103). */
+int p2v_check_device(int device);
+
+/* ---- epilogue flags (bit-or) ---------------------------------------------------------------- */
+#define P2V_EPI_GELU 1u     /* erf-GELU before re-quantization            (models/layers_quant.py:331) */
+#define P2V_EPI_RESIDUAL 2u /* + residual stream, block-level PTF re-quant (models/vit_fquant.py:431,468) */
+#define P2V_EPI_OUT_POT 4u  /* out scale is a power of two: use out_rscale (exact reciprocal) */
+#define P2V_EPI_OUT_F32 8u  /* also write dequantized fp32 (logits)        (models/vit_fquant.py:796) */
+
+/* Per-output-channel epilogue of an int8 GEMM: replaces F.linear/F.conv2d + the following QAct
+ * (models/ptq/layers.py:86-88,173-178 and :207-220).  All vectors have n entries. */
+typedef struct p2v_epilogue {
+  const float* acc_scale;   /* s_in * s_w[n]                                             */
+  const float* bias;        /* fp32 bias (never quantized, layers.py:178)                */
+  const float* out_scale;   /* s_out[n]                                                  */
+  const float* out_rscale;  /* 1/s_out[n] (exact for power-of-two scales)                */
+  const float* res_scale;   /* s_res[n], residual stream scale      (RESIDUAL only)      */
+  const float* out2_scale;  /* s_out2[n], block-level output scale  (RESIDUAL only)      */
+  const int8_t* residual;   /* [m, n] residual codes, row stride ld_out (RESIDUAL only)  */
+  int8_t* aux_codes;        /* optional [m, n]: branch codes before the residual add     */
+  float* out_f32;           /* optional [m, n] fp32 (OUT_F32)                            */
+  float out_zp;             /* zero point of the output quantizer (0 for minmax / ptf)   */
+  uint32_t flags;
+} p2v_epilogue;
+
+/* out[m, n] = epilogue( sum_k a[m, k] * w[n, k] ), int32 accumulation on tcgen05 kind::i8.
+ * a: [m, k] int8, row stride lda bytes (multiple of 16); w: [n, k] int8 contiguous; out: [m, n] int8,
+ * row stride ld_out.  k must be a multiple of 16.
+ * Replaces QLinear.forward / QConv2d.forward in quantized mode (models/ptq/layers.py:82-88,171-178). */
+int p2v_gemm_i8(const int8_t* a, int64_t lda, const int8_t* w, int8_t* out, int64_t ld_out, int m, int n,
+                int k, const p2v_epilogue* epi, void* stream);
+/* Same contract on CUDA cores (dp4a); a slow cross-check used by the tests. */
+int p2v_gemm_i8_simt(const int8_t* a, int64_t lda, const int8_t* w, int8_t* out, int64_t ld_out, int m,
+                     int n, int k, const p2v_epilogue* epi, void* stream);
+/* Raw int32 accumulators of the tensor-core kernel (test hook). */
+int p2v_gemm_i8_acc(const int8_t* a, int64_t lda, const int8_t* w, int32_t* acc, int m, int n, int k,
+                    void* stream);
+
+/* Input QAct + im2col for a stride-P patch convolution: x fp32 [b, c, h, w] ->
+ * codes int8 [b*(h/p)*(w/p), c*p*p], K order (c, kh, kw) = conv weight.reshape(out, -1).
+ * Replaces qact_input (models/vit_fquant.py:705-706) and the unfold inside F.conv2d. */
+int p2v_quant_patchify(const float* x, int8_t* codes, int b, int c, int h, int w, int p, float scale,
+                       float zero_point, void* stream);
+
+/* Token assembly: cls concat, qact_embed, + qact_pos(pos_embed), qact1 (PTF)
+ * (models/vit_fquant.py:718-733).  pe: patch-embed codes [b*np, d]; cls_value[d] / pos_value[(np+1)*d]
+ * are the dequantized cls token (after qact_embed) and position embedding (after qact_pos);
+ * out: [b*(np+1), d] codes on the per-channel grid out_scale[d]. */
+int p2v_embed_assemble(const int8_t* pe, int8_t* out, int b, int np, int d, float pe_scale, float pe_zp,
+                       float embed_scale, float embed_zp, const float* cls_value, const float* pos_value,
+                       const float* out_scale, void* stream);
+
+/* Integer LayerNorm fused with the QAct that consumes it.  Replaces QIntLayerNorm.forward mode 'int'
+ * (models/ptq/layers.py:255-289) + x / channel_scale + qact0 (models/vit_fquant.py:284-289,
+ * models/layers_quant.py:307-312).  Per channel c:
+ *   xq = in[r, c] * in_mask[c];  code = LN_dyadic(xq; gamma, beta, ln_out_scale[c])
+ *   out[r, c] = clamp(RNE(code * post_mul[c]))           post_mul = ln_out_scale / (cs_next * s_next)
+ * All of ln_out_scale, post_mul are powers of two under the minmax observer (pot != 0); with pot == 0
+ * the kernel divides by ln_out_scale and by post_div[c] = cs_next[c] * ... in fp32 instead.
+ * in_row_stride: bytes between consecutive rows (lets the final norm read only the CLS rows).
+ * ln_codes (optional, int32 [rows, d]): the unclamped LN codes. */
+typedef struct p2v_layernorm {
+  const float* in_mask;        /* [d] round(in_scale / min(in_scale)) in {1,2,4,8} */
+  const float* gamma;          /* [d] */
+  const float* beta;           /* [d] */
+  const float* ln_out_scale;   /* [d] */
+  const float* ln_out_rscale;  /* [d] exact reciprocal (pot) */
+  const float* post_mul;       /* [d] (pot) */
+  const float* post_div1;      /* [d] cs_next (non-pot) */
+  float post_div2;             /* s_next (non-pot) */
+  float post_zp;
+  float in_scale1;             /* min over channels of the input scale */
+  int pot;
+} p2v_layernorm;
+int p2v_layernorm_int(const int8_t* in, int64_t in_row_stride, int8_t* out, int32_t* ln_codes, int rows,
+                      int d, const p2v_layernorm* p, void* stream);
+
+/* Fused integer attention for one layer: per (image, head)
+ *   S = Q K^T (int32) -> qact_attn1 codes -> log-int-softmax 4-bit codes -> P V -> qact2 codes.
+ * Replaces models/vit_fquant.py:308-326 and QIntSoftmax.forward (models/ptq/layers.py:323-376).
+ * qkv: codes [b, n, 3, heads, 64]; out: [b, n, heads*64].  exp_lut[256]: integer exp of the row-max
+ * distance d = max - code, built on the host from the score scale exactly as layers.py:334-358 does.
+ * Optional dumps: score codes int8 [b, heads, n, n] and softmax codes uint8 [b, heads, n, n]. */
+typedef struct p2v_attention {
+  float score_mul;    /* s_qkv^2 * head_dim^-0.5 / s_score (power of two under minmax) */
+  float score_zp;
+  double out_mul;     /* 2^-15 * s_qkv / s_out */
+  float out_zp;
+  int softmax_levels; /* 2^bits = 16 */
+  const float* exp_lut; /* [256] fp32 view of the integer exp (exact: < 2^24 significant bits) */
+  int8_t* dump_scores;
+  uint8_t* dump_softmax;
+} p2v_attention;
+int p2v_attention_int(const int8_t* qkv, int8_t* out, int b, int n, int heads, const p2v_attention* p,
+                      void* stream);
+
+/* Standalone QAct on fp32 data (module-level use): out = (clamp(RNE(x/s + zp)) - zp) * s with a scale
+ * per channel of the innermost (inner == 1) or of an outer dimension.  models/ptq/layers.py:207-220. */
+int p2v_fake_quant_f32(const float* x, float* out, int8_t* codes, int64_t outer, int channels, int64_t inner,
+                       const float* scale, const float* zero_point, int qmin, int qmax, void* stream);
+
+/* ---- whole-model engine ------------------------------------------------------------------------ */
+typedef struct p2v_linear_desc {
+  const int8_t* w;          /* [n, k] codes */
+  int32_t n, k;
+  p2v_epilogue epi;         /* residual / aux / out pointers are filled by the engine */
+} p2v_linear_desc;
+
+typedef struct p2v_block_desc {
+  p2v_layernorm norm1, norm2;
+  p2v_linear_desc qkv, proj, fc1, fc2;
+  p2v_attention attn;
+} p2v_block_desc;
+
+typedef struct p2v_vit_desc {
+  int32_t img_size, patch_size, in_chans, embed_dim, depth, num_heads, hidden_dim, num_classes;
+  float input_scale, input_zp;             /* qact_input */
+  p2v_linear_desc patch_embed;             /* conv as GEMM, epilogue = patch_embed.qact */
+  float pe_scale, pe_zp, embed_scale, embed_zp;
+  const float* cls_value;                  /* [d] */
+  const float* pos_value;                  /* [(np+1) * d] */
+  const float* embed_out_scale;            /* [d] qact1 PTF scale */
+  const p2v_block_desc* blocks;            /* HOST array [depth] */
+  p2v_layernorm norm;                      /* final norm (CLS rows) -> qact2 */
+  p2v_linear_desc head;                    /* epilogue = act_out, OUT_F32 */
+} p2v_vit_desc;
+
+typedef struct p2v_vit p2v_vit;
+
+/* Replaces VisionTransformer.forward in quantized mode (models/vit_fquant.py:700-799).
+ * The descriptor (and the host block array) is copied; device buffers it points to stay owned by the
+ * caller and must outlive the handle. */
+int p2v_vit_create(const p2v_vit_desc* desc, int device, p2v_vit** out);
+void p2v_vit_destroy(p2v_vit* h);
+/* Bytes of device workspace the forward needs for a batch of b images. */
+int64_t p2v_vit_workspace_bytes(const p2v_vit* h, int b);
+/* x: fp32 [b, c, h, w] device; logits: fp32 [b, classes] device; workspace: device scratch.
+ * dump (optional, device): receives every intermediate code tensor at the offsets reported by
+ * p2v_vit_dump_layout.  The launch sequence for (b, workspace, logits, x) is captured into a CUDA graph
+ * on first use when use_graph != 0. */
+int p2v_vit_forward(p2v_vit* h, const float* x, float* logits, int8_t* logit_codes, int b, void* workspace,
+                    void* dump, int use_graph, void* stream);
+/* End-to-end call with HOST buffers (pinned or pageable): H2D copy, forward, D2H copy, stream sync. */
+int p2v_vit_forward_host(p2v_vit* h, const float* x_host, float* logits_host, int b, void* workspace,
+                         void* x_dev, void* logits_dev, void* stream);
+/* Number of kernels one forward launches (for bench accounting). */
+int p2v_vit_launches_per_forward(const p2v_vit* h);
+/* Dump layout: entry i -> name (static string), byte offset, byte size, element size. Returns count. */
+int p2v_vit_dump_layout(const p2v_vit* h, int b, int i, const char** name, int64_t* offset, int64_t* bytes,
+                        int32_t* elem_size);
+int64_t p2v_vit_dump_bytes(const p2v_vit* h, int b);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* P2V_H_ */

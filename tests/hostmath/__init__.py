@@ -1,0 +1,113 @@
+"""TEST INFRASTRUCTURE: runs a VitPlan on the CPU through the kernels' own scalar arithmetic
+(diff_vit_b200/csrc/p2v_math.cuh compiled for the host by g++), integer GEMMs done in numpy int64.
+Used by the CPU test-suite to pin the plan builder and the fp32 op order against the oracle; the
+product never imports it."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = os.path.join(_HERE, 'libp2v_hostmath.so')
+_SRC = os.path.join(_HERE, 'hostmath.cpp')
+_HDR = os.path.join(_HERE, '..', '..', 'diff_vit_b200', 'csrc', 'p2v_math.cuh')
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if (not os.path.exists(_LIB) or os.path.getmtime(_LIB) < max(os.path.getmtime(_SRC), os.path.getmtime(_HDR))):
+            subprocess.check_call(['g++', '-O2', '-ffp-contract=off', '-std=c++17', '-shared', '-fPIC', '-x', 'c++',
+                                   _SRC, '-o', _LIB])
+        _lib = C.CDLL(_LIB)
+    return _lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _f(t):
+    return np.ascontiguousarray(t.detach().cpu().numpy() if hasattr(t, 'detach') else t, dtype=np.float32)
+
+
+def gemm_epilogue(a, lp, residual=None, want_f32=False):
+    """a int8 [m,k]; lp LinearPlan -> (codes, aux, f32)"""
+    w = lp.w.numpy().astype(np.int64)
+    acc = (a.astype(np.int64) @ w.T).astype(np.int32)
+    m, n = acc.shape
+    out = np.empty((m, n), np.int8)
+    aux = np.empty((m, n), np.int8) if residual is not None else None
+    f32 = np.empty((m, n), np.float32) if want_f32 else None
+    flags = lp.flags | (2 if residual is not None else 0)
+    keep = [_f(lp.acc_scale), _f(lp.bias), _f(lp.out_scale), _f(lp.out_rscale),
+            _f(lp.res_scale) if residual is not None else None, _f(lp.out2_scale) if residual is not None else None]
+    res = np.ascontiguousarray(residual) if residual is not None else None
+    lib().hm_epilogue(_p(np.ascontiguousarray(acc)), m, n, _p(keep[0]), _p(keep[1]), _p(keep[2]), _p(keep[3]),
+                      C.c_float(lp.out_zp), C.c_uint32(flags), _p(res), _p(keep[4]), _p(keep[5]), _p(out), _p(aux), _p(f32))
+    return out, aux, f32
+
+
+def layernorm(x, row_stride, rows, d, p):
+    out = np.empty((rows, d), np.int8)
+    codes = np.empty((rows, d), np.int32)
+    keep = [_f(p.in_mask), _f(p.gamma), _f(p.beta), _f(p.ln_out_scale), _f(p.ln_out_rscale), _f(p.post_mul), _f(p.post_div1)]
+    lib().hm_layernorm(_p(x), C.c_int64(row_stride), _p(out), _p(codes), rows, d, *[_p(k) for k in keep],
+                       C.c_float(p.post_div2), C.c_float(p.post_zp), C.c_float(p.in_scale1), int(p.pot))
+    return out, codes
+
+
+def attention(qkv, b, n, heads, p):
+    out = np.empty((b * n, heads * 64), np.int8)
+    sc = np.empty((b, heads, n, n), np.int8)
+    sm = np.empty((b, heads, n, n), np.uint8)
+    lut = _f(p.exp_lut)
+    lib().hm_attention(_p(qkv), _p(out), b, n, heads, C.c_float(p.score_mul), C.c_float(p.score_zp),
+                       C.c_double(p.out_mul), C.c_float(p.out_zp), p.levels, _p(lut), _p(sc), _p(sm))
+    return out, sc, sm
+
+
+def run_plan(plan, x):
+    """x: float32 numpy [b, c, h, w].  Returns (logits fp32, {golden-style key: codes})."""
+    a = plan.arch
+    b, d, np_, heads = x.shape[0], a['embed_dim'], a['num_patches'], a['num_heads']
+    n = np_ + 1
+    P = a['patch_size']
+    g = a['img_size'] // P
+    codes = {}
+    xin = np.empty(x.shape, np.int8)
+    xc = np.ascontiguousarray(x, dtype=np.float32)
+    lib().hm_quant(_p(xc), _p(xin), C.c_int64(xc.size), C.c_float(plan.input_scale), C.c_float(plan.input_zp))
+    codes['act/qact_input'] = xin
+    patches = xin.reshape(b, a['in_chans'], g, P, g, P).transpose(0, 2, 4, 1, 3, 5).reshape(b * np_, -1)
+    pe, _, _ = gemm_epilogue(np.ascontiguousarray(patches), plan.patch_embed)
+    codes['act/patch_embed.qact'] = pe
+    xs = np.empty((b * n, d), np.int8)
+    keep = [_f(plan.cls_value), _f(plan.pos_value), _f(plan.embed_out_scale)]
+    lib().hm_embed(_p(pe), _p(xs), b, np_, d, C.c_float(plan.pe_scale), C.c_float(plan.pe_zp),
+                   C.c_float(plan.embed_scale), C.c_float(plan.embed_zp), _p(keep[0]), _p(keep[1]), _p(keep[2]))
+    codes['act/qact1'] = xs
+    for i, blk in enumerate(plan.blocks):
+        pre = 'blocks.%d' % i
+        a0, ln = layernorm(xs, d, b * n, d, blk.norm1)
+        codes['ln/' + pre + '.norm1'], codes['act/' + pre + '.attn.qact0'] = ln, a0
+        qkv, _, _ = gemm_epilogue(a0, blk.qkv)
+        codes['act/' + pre + '.attn.qact1'] = qkv
+        o, sc, sm = attention(qkv, b, n, heads, blk.attn)
+        codes['act/' + pre + '.attn.qact_attn1'], codes['softmax/' + pre + '.attn.log_int_softmax'] = sc, sm
+        codes['act/' + pre + '.attn.qact2'] = o
+        x1, aux, _ = gemm_epilogue(o, blk.proj, residual=xs)
+        codes['act/' + pre + '.attn.qact3'], codes['act/' + pre + '.qact2'] = aux, x1
+        m0, ln = layernorm(x1, d, b * n, d, blk.norm2)
+        codes['ln/' + pre + '.norm2'], codes['act/' + pre + '.mlp.qact0'] = ln, m0
+        hid, _, _ = gemm_epilogue(m0, blk.fc1)
+        codes['act/' + pre + '.mlp.qact1'] = hid
+        xs, aux, _ = gemm_epilogue(hid, blk.fc2, residual=x1)
+        codes['act/' + pre + '.mlp.qact2'], codes['act/' + pre + '.qact4'] = aux, xs
+    cls, ln = layernorm(xs, n * d, b, d, plan.norm)
+    codes['ln/norm'], codes['act/qact2'] = ln, cls
+    lc, _, logits = gemm_epilogue(cls, plan.head, want_f32=True)
+    codes['act/act_out'] = lc
+    return logits, codes
