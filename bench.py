@@ -1,0 +1,310 @@
+#!/usr/bin/env python
+"""Headline benchmark: images/s of the W8A8 PoT DeiT-S quantized forward at batch 256 per B200.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's sm_100a path
+    python bench.py --impl reference --steps K --warmup W    # the reference's CPU fake-quant path (port)
+
+One "step" = one quantized forward of one batch of 256 synthetic images (calibration excluded, as in
+BASELINE.md).  N > 1 is launched by torchrun, one rank per GPU; ranks process independent batches
+(weak scaling: 256 images per GPU per step, no data-path collective; NCCL only for the barrier and the
+max-over-ranks timing).  Rank 0 prints ONE JSON line.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+MODEL = 'deit_small'
+BATCH = 256
+GOP_PER_IMAGE = 9.198      # 2 * 4 598 882 304 MAC incl. QK^T / AV
+INT8_NOMINAL_TOPS = 4500.0
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--model', default=MODEL)
+    ap.add_argument('--batch', type=int, default=BATCH, help='images per GPU per step')
+    ap.add_argument('--calib-batch', type=int, default=32)
+    ap.add_argument('--e2e-steps', type=int, default=5)
+    ap.add_argument('--cpu-sample', type=int, default=32, help='images in the CPU-baseline sample')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get('hbm_gbs', 6650.0), d.get('bf16_tflops', 1590.0), 'measured'
+    return 6650.0, 1590.0, 'fallback'
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[4:8]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        sm.sort()
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'samples': len(sm), 'reasons': sorted(reasons)}
+
+
+def build_calibrated(args, device):
+    import torch
+    import diff_vit_b200 as dv
+    torch.manual_seed(0)
+    model = dv.str2model(args.model)(pretrained=False, cfg=dv.Config(True, True, 'minmax')).eval().to(device)
+    g = torch.Generator(device=device).manual_seed(0)
+    torch.backends.cudnn.allow_tf32 = False
+    calib = torch.randn(args.calib_batch, 3, 224, 224, device=device, generator=g)
+    t0 = time.time()
+    dv.calibrate_model(model, [calib])
+    return model, time.time() - t0
+
+
+def cpu_port_rate(state, nbits, sample, steps, warmup, threads):
+    """images/s of the oracle's fp32 fake-quant forward (the reference's CPU path, restated) on `sample` images."""
+    import torch
+    from oracle import fakequant_forward as orc
+    torch.set_num_threads(threads)
+    x = torch.randn(sample, 3, 224, 224, generator=torch.Generator().manual_seed(1))
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        orc.forward(state, x, nbits)
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    return sample * len(times) / sum(times), sum(times) / len(times)
+
+
+def run_reference(args):
+    """The reference arm: the reference's own CPU fake-quant implementation of the path (oracle port; the
+    reference is Python and /root/reference is not on the GPU box), all host threads, rank 0 only."""
+    if int(os.environ.get('RANK', '0')) != 0:
+        return
+    import torch
+    from diff_vit_b200.plan import extract_state
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    model, calib_s = build_calibrated(argparse.Namespace(**{**vars(args), 'calib_batch': 8}), torch.device('cpu'))
+    state = extract_state(model)
+    sample = 16
+    rate, per_step = cpu_port_rate(state, [8] * 50, sample, args.steps, args.warmup, threads)
+    print(json.dumps({
+        'impl': 'reference', 'metric': 'images/sec W8A8 PoT DeiT-S b256', 'value': round(rate, 3), 'unit': 'images/s',
+        'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': round(per_step * 1e3, 3),
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32 fake-quant (int8 grid)',
+        'data': 'synthetic',
+        'config': {'workload': '%s W8A8 PoT minmax quantized forward, bit_config [8]*50' % args.model,
+                   'per_step_sample': '%d images of the 256-image batch' % sample},
+        'cpu_baseline': {'value': round(rate, 3), 'unit': 'images/s', 'cores': threads, 'kind': 'port',
+                         'sample': '%d-image forward per step, oracle/fakequant_forward.py (restates '
+                                   'models/vit_fquant.py:700-799)' % sample},
+        'e2e': {'value': round(rate, 3), 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0, 'calibration_s': round(calib_s, 2)}))
+
+
+def time_gemm(lib_mod, m, n, k, flags, iters, stream_obj):
+    """Average device time (ms) of the fc1-shaped tensor-core GEMM with its GELU + re-quant epilogue."""
+    import ctypes as C
+    import torch
+    dev = 'cuda'
+    a = torch.randint(-128, 128, (m, k), dtype=torch.int8, device=dev)
+    w = torch.randint(-128, 128, (n, k), dtype=torch.int8, device=dev)
+    out = torch.empty(m, n, dtype=torch.int8, device=dev)
+    vec = lambda v: torch.full((n,), v, dtype=torch.float32, device=dev)
+    acc, bias, osc, ors = vec(2.0 ** -12), vec(0.01), vec(2.0 ** -5), vec(2.0 ** 5)
+    e = lib_mod.Epilogue()
+    e.acc_scale, e.bias, e.out_scale, e.out_rscale = acc.data_ptr(), bias.data_ptr(), osc.data_ptr(), ors.data_ptr()
+    e.flags = flags
+    lib = lib_mod.lib()
+    with torch.cuda.stream(stream_obj):
+        for _ in range(3):
+            lib_mod.check(lib.p2v_gemm_i8(a.data_ptr(), k, w.data_ptr(), out.data_ptr(), n, m, n, k, C.byref(e),
+                                          stream_obj.cuda_stream))
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record(stream_obj)
+        for _ in range(iters):
+            lib_mod.check(lib.p2v_gemm_i8(a.data_ptr(), k, w.data_ptr(), out.data_ptr(), n, m, n, k, C.byref(e),
+                                          stream_obj.cuda_stream))
+        t1.record(stream_obj)
+    stream_obj.synchronize()
+    return t0.elapsed_time(t1) / iters
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from diff_vit_b200 import _cabi
+    from diff_vit_b200.plan import extract_state
+
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: no CUDA device; the quantized forward has no CPU fallback '
+                         '(use --impl reference for the CPU baseline)')
+    torch.cuda.set_device(local)
+    device = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=device)
+    _cabi.check(_cabi.lib().p2v_check_device(local))
+
+    model, calib_s = build_calibrated(args, device)
+    bits = [8] * (4 * model.depth + 2)
+    eng = model.integer_engine()
+    bound = eng.bound(bits)
+    g = torch.Generator(device=device).manual_seed(1 + rank)
+    x = torch.randn(args.batch, 3, 224, 224, device=device, generator=g)   # 154 MB fp32 > 126 MB L2
+    stream = torch.cuda.Stream(device)
+
+    def barrier():
+        torch.cuda.synchronize(device)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(device)
+
+    with torch.cuda.stream(stream):
+        for _ in range(max(args.warmup, 3)):
+            eng.forward_into(x, bits)
+    stream.synchronize()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        t0.record(stream)
+        for _ in range(args.steps):
+            logits = eng.forward_into(x, bits)
+        t1.record(stream)
+    stream.synchronize()
+    barrier()
+    ms = torch.tensor([t0.elapsed_time(t1)], device=device)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    total_ms = float(ms.item())
+    clocks = sampler.stop() if rank == 0 else None
+    value = world * args.batch * args.steps / (total_ms * 1e-3)
+
+    # ---- end to end through the public host-buffer call: pinned H2D of the batch + D2H of the logits ----
+    x_host = torch.empty(x.shape, dtype=torch.float32).pin_memory()
+    x_host.copy_(x)
+    logits_host = torch.empty(args.batch, model.num_classes, dtype=torch.float32).pin_memory()
+    with torch.cuda.stream(stream):
+        eng.forward_host(x_host, logits_host, bits)
+    barrier()
+    w0 = time.perf_counter()
+    with torch.cuda.stream(stream):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(args.e2e_steps):
+            eng.forward_host(x_host, logits_host, bits)     # synchronises the stream before returning
+        e1.record(stream)
+    stream.synchronize()
+    e2e_ms = torch.tensor([max(e0.elapsed_time(e1), (time.perf_counter() - w0) * 1e3)], device=device)
+    if world > 1:
+        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    e2e_value = world * args.batch * args.e2e_steps / (float(e2e_ms.item()) * 1e-3)
+    assert torch.equal(logits_host.to(device), logits), 'host-buffer call disagrees with the device-resident call'
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel: the fc1 GEMM (M x 1536 x 384) with GELU + re-quant epilogue ----
+    hbm, bf16, src = peaks()
+    m = args.batch * (model.patch_embed.num_patches + 1)
+    d, hid = model.embed_dim, model.blocks[0].mlp.fc1.out_features
+    gemm_ms = time_gemm(_cabi, m, hid, d, _cabi.EPI_GELU | _cabi.EPI_OUT_POT, 20, stream)
+    ops = 2.0 * m * hid * d
+    achieved = ops / (gemm_ms * 1e-3) / 1e12
+    peak = 2.0 * bf16
+    roofline = {'bound': 'tensor', 'kernel': 'gemm_i8_tc_kernel<GELU|OUT_POT> fc1 %dx%dx%d' % (m, hid, d),
+                'achieved': round(achieved, 2), 'peak': round(peak, 1), 'unit': 'TFLOP/s',
+                'frac': round(achieved / peak, 4), 'traffic': None,
+                'peak_source': '2 x %s bf16 burst (MEASURED_PEAKS.json has no int8 entry); nominal dense int8 %.0f'
+                               % (src, INT8_NOMINAL_TOPS),
+                'model_achieved_tops': round(value / world * GOP_PER_IMAGE / 1e3, 2),
+                'model_frac_of_peak': round(value / world * GOP_PER_IMAGE / 1e3 / peak, 4)}
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        rate, per = cpu_port_rate(extract_state(model), bits, args.cpu_sample, 2, 1, threads)
+        cpu = {'value': round(rate, 3), 'unit': 'images/s', 'cores': threads, 'kind': 'port',
+               'sample': '%d-image forward x2 after 1 warm-up, oracle/fakequant_forward.py (CPU restatement of '
+                         'models/vit_fquant.py:700-799; /root/reference is not on the GPU box)' % args.cpu_sample}
+
+    in_bytes = x_host.numel() * 4
+    line = {
+        'metric': 'images/sec W8A8 PoT DeiT-S b256', 'value': round(value, 1), 'unit': 'images/s', 'n_gpus': world,
+        'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': round(total_ms / args.steps, 4),
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'int8 (s32 accumulate)',
+        'data': 'synthetic',
+        'config': {'workload': '%s W8A8 PoT minmax quantized forward, bit_config [8]*50, random-init weights' % args.model,
+                   'per_gpu_batch': args.batch, 'global_batch': args.batch * world, 'parallelism': 'dp%d' % world,
+                   'l2': 'input batch %.0f MB fp32 > 126 MB L2' % (in_bytes / 1e6),
+                   'calibration': 'randn(%d,3,224,224), %.1f s, excluded' % (args.calib_batch, calib_s)},
+        'e2e': {'value': round(e2e_value, 1), 'unit': 'images/s', 'h2d_bytes_per_step': in_bytes,
+                'd2h_bytes_per_step': logits_host.numel() * 4, 'steps': args.e2e_steps,
+                'api': 'IntegerEngine.forward_host -> p2v_vit_forward_host (pinned host buffers)'},
+        'gpu_launches': (max(args.warmup, 3) + args.steps + args.e2e_steps + 1) * bound.launches + 23,
+        'launches_per_step': bound.launches,
+        'roofline': roofline, 'cpu_baseline': cpu, 'clocks': clocks,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    a = parse()
+    if a.impl == 'reference':
+        run_reference(a)
+    else:
+        run_ours(a)

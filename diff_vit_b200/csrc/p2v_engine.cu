@@ -27,6 +27,7 @@ void set_error(const char* fmt, ...) {
 }
 
 int make_tmap_kmajor(CUtensorMap* map, const void* ptr, int64_t rows, int64_t k, int64_t ld);
+int gemm_configure();
 int gemm_i8_tc(const CUtensorMap& ta, const CUtensorMap& tb, int8_t* out, int64_t ld_out, int m, int n, int k,
                const p2v_epilogue& epi, cudaStream_t st);
 
@@ -257,6 +258,7 @@ extern "C" int p2v_vit_create(const p2v_vit_desc* desc, int device, p2v_vit** ou
   int rc = p2v_check_device(device);
   if (rc) return rc;
   P2V_CHECK_CUDA(cudaSetDevice(device));
+  if ((rc = gemm_configure())) return rc;
   p2v_vit* h = new p2v_vit();
   h->d = *desc;
   h->blocks.assign(desc->blocks, desc->blocks + desc->depth);

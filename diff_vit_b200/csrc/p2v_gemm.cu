@@ -311,14 +311,39 @@ int make_tmap_kmajor(CUtensorMap* map, const void* ptr, int64_t rows, int64_t k,
   return P2V_OK;
 }
 
+constexpr int kGemmSmemBytes = (int)sizeof(GemmSmem) + 1024;
+
+template <uint32_t FLAGS>
+static int configure_one() {
+  P2V_CHECK_CUDA(cudaFuncSetAttribute(gemm_i8_tc_kernel<FLAGS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      kGemmSmemBytes));
+  return P2V_OK;
+}
+
+// Opt every instantiation into > 48 KiB of dynamic shared memory.  Done once per process, outside any
+// stream capture.
+int gemm_configure() {
+  static int state = 1;  // 1 = not yet done
+  if (state == 1) {
+    int rc = configure_one<0>();
+    if (!rc) rc = configure_one<1>();
+    if (!rc) rc = configure_one<2>();
+    if (!rc) rc = configure_one<3>();
+    if (!rc) rc = configure_one<4>();
+    if (!rc) rc = configure_one<5>();
+    if (!rc) rc = configure_one<6>();
+    if (!rc) rc = configure_one<7>();
+    if (rc) return rc;
+    state = 0;
+  }
+  return P2V_OK;
+}
+
 template <uint32_t FLAGS>
 static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& g, cudaStream_t st) {
-  static bool configured = false;
-  const int smem = (int)sizeof(GemmSmem) + 1024;
-  if (!configured) {
-    P2V_CHECK_CUDA(cudaFuncSetAttribute(gemm_i8_tc_kernel<FLAGS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
-  }
+  const int smem = kGemmSmemBytes;
+  int rc = gemm_configure();
+  if (rc) return rc;
   const int tiles = ((g.m + kBlockM - 1) / kBlockM) * ((g.n + kBlockN - 1) / kBlockN);
   const int grid = tiles < kNumSMs ? tiles : kNumSMs;
   gemm_i8_tc_kernel<FLAGS><<<grid, kGemmThreads, smem, st>>>(ta, tb, g);

@@ -1,0 +1,212 @@
+"""Per-kernel parity on the GPU, every call through the C ABI (ctypes, raw device pointers).
+Checkers: exact int64 matmul in numpy and the host build of the kernels' scalar arithmetic
+(tests/hostmath), which the CPU suite pins to the reference's codes."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+import hostmath
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def cabi():
+    from diff_vit_b200 import _cabi
+    _cabi.check(_cabi.lib().p2v_check_device(0))
+    return _cabi
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _rand_i8(rng, *shape, lo=-128, hi=127):
+    return rng.integers(lo, hi + 1, size=shape, dtype=np.int64).astype(np.int8)
+
+
+GEMM_SHAPES = [(128, 128, 128), (256, 384, 128), (300, 192, 192), (50, 1000, 384), (1970, 1536, 384),
+               (1970, 384, 1536), (6, 16, 128), (129, 136, 80), (20000, 384, 384)]
+
+
+@pytest.mark.parametrize('m,n,k', GEMM_SHAPES)
+def test_gemm_tensor_core_accumulators_exact(cabi, m, n, k):
+    rng = np.random.default_rng(m * 7 + n * 3 + k)
+    a, w = _rand_i8(rng, m, k), _rand_i8(rng, n, k)
+    ad, wd = torch.from_numpy(a).cuda(), torch.from_numpy(w).cuda()
+    acc = torch.full((m, n), -7, dtype=torch.int32, device='cuda')
+    cabi.check(cabi.lib().p2v_gemm_i8_acc(ad.data_ptr(), k, wd.data_ptr(), acc.data_ptr(), m, n, k, _stream()))
+    torch.cuda.synchronize()
+    ref = a.astype(np.int64) @ w.astype(np.int64).T
+    np.testing.assert_array_equal(acc.cpu().numpy().astype(np.int64), ref)
+
+
+def _epilogue_case(rng, n, pot, gelu, residual):
+    from diff_vit_b200.plan import LinearPlan
+    acc_scale = (2.0 ** rng.integers(-14, -9, size=n)).astype(np.float32)
+    bias = (rng.standard_normal(n) * 0.05).astype(np.float32)
+    if pot:
+        out_scale = np.full(n, 2.0 ** -5, np.float32)
+    else:
+        out_scale = (rng.uniform(0.5, 1.0, size=n) * 2.0 ** -5 * 2.0 ** rng.integers(0, 3, size=n)).astype(np.float32)
+    lp = LinearPlan(w=None, acc_scale=torch.from_numpy(acc_scale), bias=torch.from_numpy(bias),
+                    out_scale=torch.from_numpy(out_scale), out_rscale=torch.from_numpy(1.0 / out_scale), out_zp=0.0,
+                    flags=(1 if gelu else 0) | (4 if pot else 0))
+    if residual:
+        lp.res_scale = torch.from_numpy((rng.uniform(0.5, 1.0, size=n) * 2.0 ** -6).astype(np.float32))
+        lp.out2_scale = torch.from_numpy((rng.uniform(0.5, 1.0, size=n) * 2.0 ** -5).astype(np.float32))
+    return lp
+
+
+@pytest.mark.parametrize('impl', ['p2v_gemm_i8', 'p2v_gemm_i8_simt'])
+@pytest.mark.parametrize('pot,gelu,residual', [(True, False, False), (True, True, False), (False, False, True),
+                                               (False, False, False), (True, False, True)])
+@pytest.mark.parametrize('m,n,k', [(394, 384, 384), (197, 1000, 192)])
+def test_gemm_epilogues_match_host_arithmetic(cabi, impl, pot, gelu, residual, m, n, k):
+    rng = np.random.default_rng(1 + m + n + k + 2 * pot + 4 * gelu + 8 * residual)
+    a, w = _rand_i8(rng, m, k), _rand_i8(rng, n, k, lo=-100, hi=100)
+    lp = _epilogue_case(rng, n, pot, gelu, residual)
+    lp.w = torch.from_numpy(w)
+    res = _rand_i8(rng, m, n) if residual else None
+    want, want_aux, want_f32 = hostmath.gemm_epilogue(a, lp, residual=res, want_f32=True)
+
+    dev = lambda t: None if t is None else (torch.from_numpy(t) if isinstance(t, np.ndarray) else t).cuda().contiguous()
+    keep = dict(a=dev(a), w=dev(w), acc=dev(lp.acc_scale), bias=dev(lp.bias), os=dev(lp.out_scale), ors=dev(lp.out_rscale),
+                rs=dev(lp.res_scale), o2=dev(lp.out2_scale), res=dev(res))
+    out = torch.zeros(m, n, dtype=torch.int8, device='cuda')
+    aux = torch.zeros(m, n, dtype=torch.int8, device='cuda')
+    f32 = torch.zeros(m, n, dtype=torch.float32, device='cuda')
+    e = cabi.Epilogue()
+    e.acc_scale, e.bias, e.out_scale, e.out_rscale = (keep[x].data_ptr() for x in ('acc', 'bias', 'os', 'ors'))
+    e.flags = lp.flags | cabi.EPI_OUT_F32 | (cabi.EPI_RESIDUAL if residual else 0)
+    e.out_f32 = f32.data_ptr()
+    if residual:
+        e.res_scale, e.out2_scale, e.residual, e.aux_codes = (keep['rs'].data_ptr(), keep['o2'].data_ptr(),
+                                                             keep['res'].data_ptr(), aux.data_ptr())
+    fn = getattr(cabi.lib(), impl)
+    cabi.check(fn(keep['a'].data_ptr(), k, keep['w'].data_ptr(), out.data_ptr(), n, m, n, k, C.byref(e), _stream()))
+    torch.cuda.synchronize()
+    got = out.cpu().numpy()
+    diff = np.abs(got.astype(np.int64) - want.astype(np.int64))
+    if gelu:   # device erff vs host erff: <= 1 LSB on <= 0.1 % of elements
+        assert diff.max() <= 1 and (diff != 0).mean() <= 1e-3
+    else:
+        np.testing.assert_array_equal(got, want)
+        np.testing.assert_array_equal(f32.cpu().numpy(), want_f32)
+        if residual:
+            np.testing.assert_array_equal(aux.cpu().numpy(), want_aux)
+
+
+def _ln_plan(rng, d, pot):
+    from diff_vit_b200.plan import LayerNormPlan
+    base = np.float32(0.0123)
+    mask = (2.0 ** rng.integers(0, 4, size=d)).astype(np.float32)
+    mask[rng.integers(0, d)] = 1.0
+    gamma = rng.uniform(0.5, 1.5, size=d).astype(np.float32) * rng.choice([-1.0, 1.0], size=d, p=[0.1, 0.9]).astype(np.float32)
+    beta = (rng.standard_normal(d) * 0.1).astype(np.float32)
+    cs = (2.0 ** rng.integers(0, 3, size=d)).astype(np.float32)
+    cs2 = (2.0 ** rng.integers(0, 3, size=d)).astype(np.float32)
+    s_out = np.float32(2.0 ** -5) if pot else np.float32(0.0291)
+    ln_out = (s_out * cs).astype(np.float32)
+    t = torch.from_numpy
+    return LayerNormPlan(in_mask=t(mask), gamma=t(gamma), beta=t(beta), ln_out_scale=t(ln_out),
+                         ln_out_rscale=t((1.0 / ln_out).astype(np.float32)), post_mul=t((ln_out / cs2 / s_out).astype(np.float32)),
+                         post_div1=t(cs2), post_div2=float(s_out), post_zp=0.0, in_scale1=float(base), pot=int(pot))
+
+
+@pytest.mark.parametrize('rows,d,stride_rows', [(197 * 3, 384, 1), (64, 192, 1), (33, 128, 1), (5, 768, 1), (4, 384, 197)])
+@pytest.mark.parametrize('pot', [True, False])
+def test_layernorm_int_matches_host_arithmetic(cabi, rows, d, stride_rows, pot):
+    rng = np.random.default_rng(rows + d + pot)
+    p = _ln_plan(rng, d, pot)
+    x = _rand_i8(rng, rows * stride_rows, d)
+    x[0] = 127
+    x[0, ::2] = -128                                     # maximal variance row
+    want, want_codes = hostmath.layernorm(x, stride_rows * d, rows, d, p)
+    keep = {k: getattr(p, k).cuda() for k in ('in_mask', 'gamma', 'beta', 'ln_out_scale', 'ln_out_rscale', 'post_mul', 'post_div1')}
+    c = cabi.LayerNorm()
+    for k, v in keep.items():
+        setattr(c, k, v.data_ptr())
+    c.post_div2, c.post_zp, c.in_scale1, c.pot = p.post_div2, p.post_zp, p.in_scale1, p.pot
+    xd = torch.from_numpy(x).cuda()
+    out = torch.zeros(rows, d, dtype=torch.int8, device='cuda')
+    codes = torch.zeros(rows, d, dtype=torch.int32, device='cuda')
+    cabi.check(cabi.lib().p2v_layernorm_int(xd.data_ptr(), stride_rows * d, out.data_ptr(), codes.data_ptr(), rows, d,
+                                            C.byref(c), _stream()))
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(codes.cpu().numpy(), want_codes)
+    np.testing.assert_array_equal(out.cpu().numpy(), want)
+
+
+@pytest.mark.parametrize('b,n,heads', [(2, 197, 3), (3, 10, 2), (1, 224, 1), (2, 33, 6), (1, 1, 1)])
+@pytest.mark.parametrize('spread', [1, 6])
+def test_attention_int_matches_host_arithmetic(cabi, b, n, heads, spread):
+    from diff_vit_b200.plan import AttentionPlan, softmax_exp_lut
+    rng = np.random.default_rng(b * 100 + n + heads + spread)
+    qkv = _rand_i8(rng, b * n, 3 * heads * 64, lo=-20 * spread, hi=20 * spread)
+    s_att = torch.tensor([2.0 ** -4])
+    p = AttentionPlan(score_mul=float(2.0 ** -7), score_zp=0.0, out_mul=2.0 ** -15 * 2.0 ** -1, out_zp=0.0, levels=16,
+                      exp_lut=softmax_exp_lut(s_att))
+    want, want_sc, want_sm = hostmath.attention(qkv, b, n, heads, p)
+    lut = p.exp_lut.cuda()
+    c = cabi.Attention()
+    c.score_mul, c.score_zp, c.out_mul, c.out_zp, c.softmax_levels = p.score_mul, 0.0, p.out_mul, 0.0, 16
+    c.exp_lut = lut.data_ptr()
+    sc = torch.zeros(b, heads, n, n, dtype=torch.int8, device='cuda')
+    sm = torch.zeros(b, heads, n, n, dtype=torch.uint8, device='cuda')
+    c.dump_scores, c.dump_softmax = sc.data_ptr(), sm.data_ptr()
+    qd = torch.from_numpy(qkv).cuda()
+    out = torch.zeros(b * n, heads * 64, dtype=torch.int8, device='cuda')
+    cabi.check(cabi.lib().p2v_attention_int(qd.data_ptr(), out.data_ptr(), b, n, heads, C.byref(c), _stream()))
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(sc.cpu().numpy(), want_sc)
+    np.testing.assert_array_equal(sm.cpu().numpy(), want_sm)
+    np.testing.assert_array_equal(out.cpu().numpy(), want)
+    if spread == 6 and n >= 33:
+        assert want_sm.max() == 16 and want_sm.min() <= 2    # the whole code range, including 'zero'
+    # no dump pointers: same result
+    c.dump_scores = c.dump_softmax = None
+    out2 = torch.zeros_like(out)
+    cabi.check(cabi.lib().p2v_attention_int(qd.data_ptr(), out2.data_ptr(), b, n, heads, C.byref(c), _stream()))
+    torch.cuda.synchronize()
+    assert torch.equal(out, out2)
+
+
+def test_quant_patchify_and_embed(cabi):
+    rng = np.random.default_rng(5)
+    b, c, hw, p, d = 3, 3, 48, 16, 128
+    x = (rng.standard_normal((b, c, hw, hw)) * 1.5).astype(np.float32)
+    x[0, 0, 0, :8] = [0.046875, -0.046875, 0.078125, 4.5, -4.5, 0.015625, -0.015625, 1e-9]   # ties and clamps at 2^-5
+    xd = torch.from_numpy(x).cuda()
+    g = hw // p
+    out = torch.zeros(b * g * g, c * p * p, dtype=torch.int8, device='cuda')
+    cabi.check(cabi.lib().p2v_quant_patchify(xd.data_ptr(), out.data_ptr(), b, c, hw, hw, p, 2.0 ** -5, 0.0, _stream()))
+    torch.cuda.synchronize()
+    q = np.clip(np.rint(x / np.float32(2.0 ** -5)), -128, 127).astype(np.int8)
+    want = q.reshape(b, c, g, p, g, p).transpose(0, 2, 4, 1, 3, 5).reshape(b * g * g, -1)
+    np.testing.assert_array_equal(out.cpu().numpy(), want)
+
+    npatch = g * g
+    pe = _rand_i8(rng, b * npatch, d)
+    cls = (rng.standard_normal(d) * 0.02).astype(np.float32)
+    pos = (np.rint(rng.standard_normal((npatch + 1, d)) * 20) * 2.0 ** -10).astype(np.float32)
+    osc = (rng.uniform(0.5, 1, size=d) * 2.0 ** -6).astype(np.float32)
+    want = np.empty((b * (npatch + 1), d), np.int8)
+    hostmath.lib().hm_embed(pe.ctypes.data_as(C.c_void_p), want.ctypes.data_as(C.c_void_p), b, npatch, d,
+                            C.c_float(2.0 ** -6), C.c_float(0), C.c_float(2.0 ** -5), C.c_float(0),
+                            cls.ctypes.data_as(C.c_void_p), pos.ctypes.data_as(C.c_void_p), osc.ctypes.data_as(C.c_void_p))
+    ped, clsd, posd, oscd = (torch.from_numpy(t).cuda() for t in (pe, cls, pos, osc))
+    got = torch.zeros(b * (npatch + 1), d, dtype=torch.int8, device='cuda')
+    cabi.check(cabi.lib().p2v_embed_assemble(ped.data_ptr(), got.data_ptr(), b, npatch, d, 2.0 ** -6, 0.0, 2.0 ** -5, 0.0,
+                                             clsd.data_ptr(), posd.data_ptr(), oscd.data_ptr(), _stream()))
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(got.cpu().numpy(), want)
+
+
+def test_error_reporting(cabi):
+    rc = cabi.lib().p2v_gemm_i8(None, 0, None, None, 0, 0, 0, 0, None, None)
+    assert rc == -1 and b'null' in cabi.lib().p2v_last_error()
+    with pytest.raises(cabi.P2VError):
+        cabi.check(cabi.lib().p2v_quant_patchify(1, 1, 1, 3, 30, 30, 16, 1.0, 0.0, None))

@@ -1,0 +1,111 @@
+"""Whole-model parity on the GPU: the sm_100a engine (through VisionTransformer.forward and the C ABI)
+against the reference's golden codes and against the CPU oracle on the same calibrated state."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import checksum
+from oracle import fakequant_forward as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def _compare(dump, ref, exact_keys=None, tol_frac=1e-3):
+    """ref: {key: array-like codes}.  Returns (#elements, #mismatching) and asserts |diff| <= 1."""
+    total = bad = 0
+    for k, g in ref.items():
+        if k not in dump:
+            continue
+        g = np.asarray(g).astype(np.int64)
+        if k == 'ln/norm':
+            g = g[:, 0]
+        v = dump[k].astype(np.int64).reshape(g.shape)
+        d = np.abs(g - v)
+        assert d.max() <= 1, '%s: max code difference %d' % (k, d.max())
+        total += d.size
+        bad += int((d != 0).sum())
+    assert bad <= tol_frac * total, '%d of %d codes differ' % (bad, total)
+    return total, bad
+
+
+@pytest.mark.parametrize('tag', ['w8', 'w4', 'mixed'])
+def test_micro_model_every_layer_vs_reference_golden(micro_model, micro_golden, tag):
+    z = micro_golden
+    bc = {'w8': [8] * 10, 'w4': [4] * 10, 'mixed': [int(v) for v in z['mixed/bit_config']]}[tag]
+    eng = micro_model.integer_engine()
+    x = torch.from_numpy(z['x_eval']).cuda()
+    logits, dump = eng.forward_dump(x, bc)
+    ref = {k[len(tag) + 1:]: z[k] for k in z.files if k.startswith(tag + '/act/') or k.startswith(tag + '/softmax/')
+           or k.startswith(tag + '/ln/')}
+    total, bad = _compare(dump, ref)
+    assert total > 100000
+    # GELU (erff) is the only step that is not bit-defined; everything upstream of the first fc1 is exact
+    for k in ('act/patch_embed.qact', 'act/qact1', 'act/blocks.0.attn.qact0', 'act/blocks.0.attn.qact1',
+              'act/blocks.0.attn.qact_attn1', 'softmax/blocks.0.attn.log_int_softmax', 'act/blocks.0.attn.qact2',
+              'act/blocks.0.attn.qact3', 'act/blocks.0.qact2', 'act/blocks.0.mlp.qact0'):
+        np.testing.assert_array_equal(dump[k].astype(np.int64).reshape(ref[k].shape), ref[k].astype(np.int64), err_msg=k)
+    scale = float(micro_model.act_out.quantizer.scale)
+    assert np.abs(logits.cpu().numpy() - z[tag + '/logits']).max() <= scale
+    # the drop-in call: model(x, bit_config, plot) -> (logits, FLOPs, global_distance)
+    out, flops, gd = micro_model(x, bc, False)
+    assert torch.equal(out, logits) and gd == [] and flops == list(z['calib/flops'])
+    # graph replay is deterministic and equals the eager launch sequence
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):           # a non-default stream: captured into a CUDA graph, then replayed
+        again = eng.forward_into(x, bc).clone()
+        again2 = eng.forward_into(x, bc).clone()
+    side.synchronize()
+    assert torch.equal(again, logits) and torch.equal(again2, logits)
+    # host tensors are accepted (copied in and out)
+    out_h, _, _ = micro_model(torch.from_numpy(z['x_eval']), bc, False)
+    assert not out_h.is_cuda and torch.equal(out_h, logits.cpu())
+
+
+def test_deit_tiny_c1_vs_reference_golden_and_oracle(tiny_model, tiny_state, tiny_golden):
+    z = tiny_golden
+    x = tiny_model._c1_batch
+    eng = tiny_model.integer_engine()
+    logits, dump = eng.forward_dump(x.cuda(), [8] * 50)
+    ref_logits, ref = orc.forward(tiny_state, x, [8] * 50, capture=True)
+    total, bad = _compare(dump, {k: v.numpy() for k, v in ref.items()})
+    print('deit_tiny C1: %d codes compared, %d differ' % (total, bad))
+    assert total > 3e8
+    scale = float(tiny_state['act']['act_out'][0])
+    assert np.abs(logits.cpu().numpy() - z['w8/logits']).max() <= scale
+    assert (logits.cpu().numpy() != z['w8/logits']).mean() <= 0.01
+    # golden full tensors for the first two images
+    for k in z.files:
+        if k.startswith('w8/act/') or k.startswith('w8/softmax/'):
+            g = z[k].astype(np.int64)
+            key = k[3:]
+            v = dump[key].astype(np.int64)
+            v = v.reshape((32,) + g.shape[1:])[:g.shape[0]]
+            d = np.abs(v - g)
+            assert d.max() <= 1 and (d != 0).mean() <= 1e-3, key
+    # int4 weights through the same kernels
+    l4, _ = eng.forward_dump(x[:8].cuda(), [4] * 50)
+    r4, _ = orc.forward(tiny_state, x[:8], [4] * 50)
+    assert np.abs(l4.cpu().numpy() - r4.numpy()).max() <= scale
+
+
+def test_full_size_properties_deit_small():
+    """BASELINE config 2 sizes (deit_small, batch 256): size-independent properties of the integer path."""
+    import diff_vit_b200 as dv
+    torch.manual_seed(0)
+    model = dv.deit_small_patch16_224(pretrained=False, cfg=dv.Config(True, True, 'minmax')).eval().cuda()
+    g = torch.Generator(device='cuda').manual_seed(1)
+    dv.calibrate_model(model, [torch.randn(8, 3, 224, 224, device='cuda', generator=g)])
+    x = torch.randn(256, 3, 224, 224, device='cuda', generator=g)
+    eng = model.integer_engine()
+    full = eng.forward_into(x, [8] * 50).clone()
+    scale = float(model.act_out.quantizer.scale)
+    codes = full / scale
+    assert torch.equal(codes, codes.round()) and codes.abs().max() <= 128       # logits are int8 codes x 2^e
+    # batch independence: any shard of the batch gives the same rows (what data parallelism relies on)
+    for lo, hi in ((0, 32), (100, 164), (255, 256)):
+        part = eng.forward_into(x[lo:hi].contiguous(), [8] * 50).clone()
+        assert torch.equal(part, full[lo:hi])
+    perm = torch.randperm(256, device='cuda', generator=g)
+    assert torch.equal(eng.forward_into(x[perm].contiguous(), [8] * 50), full[perm])
+    assert full.std() > 0
