@@ -17,6 +17,8 @@
 // mma.sync m16n8k32 (IMMA): the score fragment layout (row g, cols 2t,2t+1 of each 8-key tile) is re-used
 // directly as the A operand of the AV product by permuting the key order of V when it is transposed into
 // shared memory, so the 4-bit codes never round-trip through memory.
+#include <math.h>
+
 #include "p2v_common.cuh"
 #include "p2v_math.cuh"
 
@@ -53,13 +55,40 @@ __device__ __forceinline__ int av_perm(int j) {
   return (s << 5) + (h << 4) + (t << 2) + i;
 }
 
-__global__ void __launch_bounds__(kAttWarps * 32)
+// Fast evaluation of the log2 code k = log_round(RNE(S / e)) (p2v_math.cuh softmax_log_code).
+// With y = S/e + 1/2 the code is a step function of y with steps at 2, 3, 6, 12, 24, ...:
+//   k = floor(log2(y / 3)) + 2 for y >= 3.
+// u = fma(S, fl(1/(3e)), 1/6) approximates y/3 to a few ulp, so k = exponent(u) + 2 unless u lies within
+// kCodeGuard ulps of a power of two (a step) or below 1 (y < 3: the one or two dominant keys of a row);
+// those elements (~1e-5 of all, plus <= 2 per row) take the exact IEEE-division path.  Both paths return
+// the same code, the fast one just proves it cheaply.
+constexpr uint32_t kCodeGuard = 64;  // ulps: |u - 2^j| / 2^j < 2^-17, far above the ~4 ulp error of u
+
+__device__ __forceinline__ uint32_t prob16(float fsum, int d, const float* lut_f, const float* lut_r3, int levels) {
+  const float u = __fmaf_rn(fsum, lut_r3[d], 0.16666667f);
+  const uint32_t bits = __float_as_uint(u);
+  int k;
+  if ((((bits + kCodeGuard) & 0x7fffffu) < 2 * kCodeGuard) || bits < 0x3f800000u) {
+    k = softmax_log_code(fsum, lut_f[d], levels);          // exact path
+  } else {
+    k = (int)(bits >> 23) - 125;
+    k = k > levels ? levels : k;
+  }
+  // probability 2^-k in units of 2^-15 (k <= 15), 0 for the "zero" code: 0x8000 >> k
+  uint32_t v;
+  asm("shr.u32 %0, %1, %2;" : "=r"(v) : "r"(0x8000u), "r"((uint32_t)k));
+  return v;
+}
+
+template <bool kDump>
+__global__ void __launch_bounds__(kAttWarps * 32, 2)
 attention_int_kernel(const int8_t* __restrict__ qkv, int8_t* __restrict__ out, int n, int heads,
-                     const p2v_attention p) {
+                     const p2v_attention p, int out_shift) {
   __shared__ __align__(16) uint8_t Ks[kMaxKeys * kQKStride];
   __shared__ __align__(16) uint8_t Qs[kAttRows * kQKStride];
   __shared__ __align__(16) uint8_t Vt[kHd * kVtStride];
   __shared__ float lut_f[256];
+  __shared__ float lut_r3[256];
   __shared__ unsigned long long lut_i[256];
 
   const int bh = blockIdx.x;
@@ -76,6 +105,7 @@ attention_int_kernel(const int8_t* __restrict__ qkv, int8_t* __restrict__ out, i
   for (int i = tid; i < 256; i += blockDim.x) {
     const float e = p.exp_lut[i];
     lut_f[i] = e;
+    lut_r3[i] = __fdiv_rn(1.0f, 3.0f * e);   // 3e is exact (e has <= 22 significant bits)
     lut_i[i] = (unsigned long long)e;
   }
   for (int i = tid; i < nkp * 4; i += blockDim.x) {
@@ -91,21 +121,34 @@ attention_int_kernel(const int8_t* __restrict__ qkv, int8_t* __restrict__ out, i
     if (row < n) v = __ldg(reinterpret_cast<const uint4*>(base + row * row_stride + head * kHd) + part);
     *reinterpret_cast<uint4*>(Qs + r * kQKStride + part * 16) = v;
   }
-  for (int i = tid; i < nkp * 4; i += blockDim.x) {
-    const int j = i >> 2, part = i & 3;
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (j < n) v = __ldg(reinterpret_cast<const uint4*>(base + j * row_stride + (2 * heads + head) * kHd) + part);
-    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-    const int pj = av_perm(j);
+  // V^T with the key permutation of the AV product: 4 consecutive positions kappa = 16h + 4t + {0,1,2,3}
+  // hold keys {j0, j0+1, j0+8, j0+9}, j0 = 32s + 16h + 2t.  One thread transposes a 4-key x 4-channel
+  // block with byte permutes and writes four 32-bit words.
+  for (int i = tid; i < (nkp >> 2) * (kHd >> 2); i += blockDim.x) {
+    const int c4 = i & 15, kq = i >> 4;                 // channel quad, key quad
+    const int s5 = kq >> 3, h = (kq >> 2) & 1, tt = kq & 3;
+    const int j0 = (s5 << 5) + (h << 4) + (tt << 1);
+    uint32_t r[4];
 #pragma unroll
-    for (int b = 0; b < 16; ++b) Vt[(part * 16 + b) * kVtStride + pj] = (uint8_t)((w[b >> 2] >> (8 * (b & 3))) & 0xff);
+    for (int q = 0; q < 4; ++q) {
+      const int j = j0 + (q >> 1) * 8 + (q & 1);
+      r[q] = j < n ? __ldg(reinterpret_cast<const uint32_t*>(base + j * row_stride + (2 * heads + head) * kHd) + c4) : 0u;
+    }
+    const uint32_t lo01 = __byte_perm(r[0], r[1], 0x5140), hi01 = __byte_perm(r[0], r[1], 0x7362);
+    const uint32_t lo23 = __byte_perm(r[2], r[3], 0x5140), hi23 = __byte_perm(r[2], r[3], 0x7362);
+    const int col = (s5 << 5) + (h << 4) + (tt << 2);
+    uint8_t* dst = Vt + (c4 * 4) * kVtStride + col;
+    *reinterpret_cast<uint32_t*>(dst) = __byte_perm(lo01, lo23, 0x5410);
+    *reinterpret_cast<uint32_t*>(dst + kVtStride) = __byte_perm(lo01, lo23, 0x7632);
+    *reinterpret_cast<uint32_t*>(dst + 2 * kVtStride) = __byte_perm(hi01, hi23, 0x5410);
+    *reinterpret_cast<uint32_t*>(dst + 3 * kVtStride) = __byte_perm(hi01, hi23, 0x7632);
   }
   __syncthreads();
 
   const int r0 = row_base + warp * 16;
   if (r0 >= n) return;  // warp-uniform; no block-level sync follows
 
-  // ---- S = Q K^T, re-quantized to int8 score codes, packed 4 per register ----------------------------
+  // ---- S = Q K^T, re-quantized to int8 score codes, kept biased (+128) and packed 4 per register ------
   uint32_t qa[2][4];
 #pragma unroll
   for (int ks = 0; ks < 2; ++ks) {
@@ -115,8 +158,8 @@ attention_int_kernel(const int8_t* __restrict__ qkv, int8_t* __restrict__ out, i
     qa[ks][2] = *reinterpret_cast<const uint32_t*>(q0 + 16);
     qa[ks][3] = *reinterpret_cast<const uint32_t*>(q0 + 8 * kQKStride + 16);
   }
-  uint32_t codeA[kMaxTiles / 2], codeB[kMaxTiles / 2];  // rows g and g+8
-  int maxA = -128, maxB = -128;
+  uint32_t codeA[kMaxTiles / 2], codeB[kMaxTiles / 2];  // rows g and g+8, bytes = code + 128
+  int maxA = 0, maxB = 0;                               // biased maxima
 #pragma unroll
   for (int j = 0; j < kMaxTiles; ++j) {
     if ((j & 1) == 0) { codeA[j >> 1] = 0; codeB[j >> 1] = 0; }
@@ -129,14 +172,20 @@ attention_int_kernel(const int8_t* __restrict__ qkv, int8_t* __restrict__ out, i
       }
       int sc[4];
 #pragma unroll
-      for (int e = 0; e < 4; ++e)
-        sc[e] = clamp_i(rne(fadd(fmul((float)c[e], p.score_mul), p.score_zp)), -128, 127);
+      for (int e = 0; e < 4; ++e) {
+        // clamp(RNE(acc * mul + zp)) + 128: acc * mul is exact for the power-of-two multiplier
+        int q;
+        asm("cvt.rni.sat.s8.f32 %0, %1;" : "=r"(q) : "f"(__fmaf_rn((float)c[e], p.score_mul, p.score_zp)));
+        sc[e] = q + 128;
+      }
       const int col = j * 8 + t * 2;
-      if (col < n) { maxA = max(maxA, sc[0]); maxB = max(maxB, sc[2]); }
-      if (col + 1 < n) { maxA = max(maxA, sc[1]); maxB = max(maxB, sc[3]); }
+      if (col >= n) { sc[0] = 0; sc[2] = 0; }        // padded keys: below every real (biased) code
+      if (col + 1 >= n) { sc[1] = 0; sc[3] = 0; }
+      maxA = max(maxA, max(sc[0], sc[1]));
+      maxB = max(maxB, max(sc[2], sc[3]));
       const int sh = (j & 1) * 16;
-      codeA[j >> 1] |= ((uint32_t)(sc[0] & 0xff) | ((uint32_t)(sc[1] & 0xff) << 8)) << sh;
-      codeB[j >> 1] |= ((uint32_t)(sc[2] & 0xff) | ((uint32_t)(sc[3] & 0xff) << 8)) << sh;
+      codeA[j >> 1] |= ((uint32_t)sc[0] | ((uint32_t)sc[1] << 8)) << sh;
+      codeB[j >> 1] |= ((uint32_t)sc[2] | ((uint32_t)sc[3] << 8)) << sh;
     }
   }
   maxA = max(maxA, __shfl_xor_sync(0xffffffffu, maxA, 1));
@@ -147,17 +196,14 @@ attention_int_kernel(const int8_t* __restrict__ qkv, int8_t* __restrict__ out, i
   // ---- exact integer row sums of the integer exp --------------------------------------------------------
   unsigned long long sumA = 0, sumB = 0;
 #pragma unroll
-  for (int j = 0; j < kMaxTiles; ++j) {
-    if (j < ntiles) {
-      const int sh = (j & 1) * 16;
-      const int col = j * 8 + t * 2;
+  for (int j2 = 0; j2 < kMaxTiles / 2; ++j2) {
+    if (j2 * 2 < ntiles) {
 #pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        if (col + e < n) {
-          const int a = (int)(int8_t)((codeA[j >> 1] >> (sh + 8 * e)) & 0xff);
-          const int b = (int)(int8_t)((codeB[j >> 1] >> (sh + 8 * e)) & 0xff);
-          sumA += lut_i[maxA - a];
-          sumB += lut_i[maxB - b];
+      for (int i = 0; i < 4; ++i) {
+        const int col = (j2 * 2 + (i >> 1)) * 8 + t * 2 + (i & 1);
+        if (col < n) {
+          sumA += lut_i[maxA - (int)((codeA[j2] >> (8 * i)) & 0xff)];
+          sumB += lut_i[maxB - (int)((codeB[j2] >> (8 * i)) & 0xff)];
         }
       }
     }
@@ -170,8 +216,8 @@ attention_int_kernel(const int8_t* __restrict__ qkv, int8_t* __restrict__ out, i
 
   // ---- log2 codes -> two u8 probability planes -> P V ------------------------------------------------------
   const int rowA = r0 + g, rowB = r0 + g + 8;
-  int8_t* dsc = p.dump_scores ? p.dump_scores + ((int64_t)bh * n) * n : nullptr;
-  uint8_t* dsm = p.dump_softmax ? p.dump_softmax + ((int64_t)bh * n) * n : nullptr;
+  int8_t* dsc = kDump ? p.dump_scores + ((int64_t)bh * n) * n : nullptr;
+  uint8_t* dsm = kDump ? p.dump_softmax + ((int64_t)bh * n) * n : nullptr;
   int hi[8][4], lo[8][4];
 #pragma unroll
   for (int jn = 0; jn < 8; ++jn)
@@ -181,28 +227,31 @@ attention_int_kernel(const int8_t* __restrict__ qkv, int8_t* __restrict__ out, i
 #pragma unroll
   for (int s = 0; s < kMaxTiles / 4; ++s) {
     if (s * 4 < ntiles) {
-      uint32_t pa_hi[4] = {0, 0, 0, 0}, pa_lo[4] = {0, 0, 0, 0};  // a0..a3 of the two planes
+      uint32_t pa_hi[4], pa_lo[4];  // a0..a3 of the two planes
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {        // hh = 0: tiles 4s, 4s+1 (a0/a1); hh = 1: tiles 4s+2, 4s+3 (a2/a3)
         const uint32_t wa = codeA[2 * s + hh], wb = codeB[2 * s + hh];
+        uint32_t va[4], vb[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int col = (4 * s + 2 * hh + (i >> 1)) * 8 + t * 2 + (i & 1);
-          if (col < n) {
-            const int a = (int)(int8_t)((wa >> (8 * i)) & 0xff);
-            const int b = (int)(int8_t)((wb >> (8 * i)) & 0xff);
-            const int ka = softmax_log_code(fsumA, lut_f[maxA - a], p.softmax_levels);
-            const int kb = softmax_log_code(fsumB, lut_f[maxB - b], p.softmax_levels);
-            if (ka <= 7) pa_hi[2 * hh] |= (uint32_t)(1u << (7 - ka)) << (8 * i);
-            else if (ka <= 15) pa_lo[2 * hh] |= (uint32_t)(1u << (15 - ka)) << (8 * i);
-            if (kb <= 7) pa_hi[2 * hh + 1] |= (uint32_t)(1u << (7 - kb)) << (8 * i);
-            else if (kb <= 15) pa_lo[2 * hh + 1] |= (uint32_t)(1u << (15 - kb)) << (8 * i);
-            if (dsc != nullptr) {
-              if (rowA < n) { dsc[(int64_t)rowA * n + col] = (int8_t)a; dsm[(int64_t)rowA * n + col] = (uint8_t)ka; }
-              if (rowB < n) { dsc[(int64_t)rowB * n + col] = (int8_t)b; dsm[(int64_t)rowB * n + col] = (uint8_t)kb; }
-            }
+          const int da = maxA - (int)((wa >> (8 * i)) & 0xff), db = maxB - (int)((wb >> (8 * i)) & 0xff);
+          va[i] = col < n ? prob16(fsumA, da, lut_f, lut_r3, p.softmax_levels) : 0u;
+          vb[i] = col < n ? prob16(fsumB, db, lut_f, lut_r3, p.softmax_levels) : 0u;
+          if (kDump && col < n) {
+            const int ka = va[i] ? 15 - (31 - __clz(va[i])) : p.softmax_levels;
+            const int kb = vb[i] ? 15 - (31 - __clz(vb[i])) : p.softmax_levels;
+            if (rowA < n) { dsc[(int64_t)rowA * n + col] = (int8_t)(maxA - da - 128); dsm[(int64_t)rowA * n + col] = (uint8_t)ka; }
+            if (rowB < n) { dsc[(int64_t)rowB * n + col] = (int8_t)(maxB - db - 128); dsm[(int64_t)rowB * n + col] = (uint8_t)kb; }
           }
         }
+        // 16-bit probabilities -> low-byte plane and high-byte plane, 4 keys per register
+        const uint32_t a01 = va[0] | (va[1] << 16), a23 = va[2] | (va[3] << 16);
+        const uint32_t b01 = vb[0] | (vb[1] << 16), b23 = vb[2] | (vb[3] << 16);
+        pa_lo[2 * hh] = __byte_perm(a01, a23, 0x6420);
+        pa_hi[2 * hh] = __byte_perm(a01, a23, 0x7531);
+        pa_lo[2 * hh + 1] = __byte_perm(b01, b23, 0x6420);
+        pa_hi[2 * hh + 1] = __byte_perm(b01, b23, 0x7531);
       }
 #pragma unroll
       for (int jn = 0; jn < 8; ++jn) {
@@ -216,14 +265,21 @@ attention_int_kernel(const int8_t* __restrict__ qkv, int8_t* __restrict__ out, i
 
   // ---- re-quantize and store ----------------------------------------------------------------------------
   const int64_t out_stride = (int64_t)heads * kHd;
+  const int izp = (int)p.out_zp;
 #pragma unroll
   for (int jn = 0; jn < 8; ++jn) {
     int q[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       const int acc = hi[jn][e] * 256 + lo[jn][e];
-      const double v = rint((double)acc * p.out_mul) + (double)p.out_zp;
-      q[e] = (int)fmin(fmax(v, -128.0), 127.0);
+      if (out_shift > 0) {
+        // RNE(acc / 2^sh) in integers: add half minus one plus the parity of the truncated result
+        const int r = (acc + ((1 << (out_shift - 1)) - 1) + ((acc >> out_shift) & 1)) >> out_shift;
+        q[e] = min(max(r + izp, -128), 127);
+      } else {
+        const double v = rint((double)acc * p.out_mul) + (double)p.out_zp;
+        q[e] = (int)fmin(fmax(v, -128.0), 127.0);
+      }
     }
     const int col = head * kHd + jn * 8 + t * 2;
     if (rowA < n)
@@ -247,7 +303,14 @@ extern "C" int p2v_attention_int(const int8_t* qkv, int8_t* out, int b, int n, i
   P2V_REQUIRE((p->dump_scores == nullptr) == (p->dump_softmax == nullptr),
               "p2v_attention_int: dump_scores and dump_softmax must be given together");
   dim3 grid(b * heads, (n + kAttRows - 1) / kAttRows);
-  attention_int_kernel<<<grid, kAttWarps * 32, 0, (cudaStream_t)stream>>>(qkv, out, n, heads, *p);
+  // power-of-two output multiplier 2^-sh (every minmax-calibrated model): integer RNE shift in the kernel
+  int out_shift = 0, ex = 0;
+  if (p->out_mul > 0 && frexp(p->out_mul, &ex) == 0.5 && ex <= 0 && ex >= -29 && p->out_zp == (float)(int)p->out_zp)
+    out_shift = 1 - ex;
+  if (p->dump_scores != nullptr)
+    attention_int_kernel<true><<<grid, kAttWarps * 32, 0, (cudaStream_t)stream>>>(qkv, out, n, heads, *p, out_shift);
+  else
+    attention_int_kernel<false><<<grid, kAttWarps * 32, 0, (cudaStream_t)stream>>>(qkv, out, n, heads, *p, out_shift);
   P2V_CHECK_CUDA(cudaGetLastError());
   return P2V_OK;
 }

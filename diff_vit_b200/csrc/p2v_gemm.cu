@@ -13,8 +13,9 @@
 //   warp 0      TMA producer      : A/B k-blocks into a 4-stage smem ring (full/empty mbarriers)
 //   warp 1      MMA issuer        : 4 x (M128 x N128 x K32) per k-block into one of 2 TMEM accumulators
 //   warp 2      TMEM allocator
-//   warps 4-7   epilogue          : TMEM -> registers -> int8 codes -> global, overlapped with the next
-//                                   tile's MMAs through the second accumulator (tmem full/empty mbarriers)
+//   warps 4-19  epilogue          : 16 warps, each one TMEM lane quarter x 32 columns: TMEM -> registers ->
+//                                   int8 codes -> global, overlapped with the next tile's MMAs through the
+//                                   second accumulator (tmem full/empty mbarriers)
 #include <cuda.h>
 
 #include "p2v_common.cuh"
@@ -29,13 +30,18 @@ constexpr int kUmmaK = 32;    // K per tcgen05.mma for 8-bit operands
 constexpr int kStages = 4;
 constexpr int kAccStages = 2;
 constexpr int kTileBytes = kBlockM * kBlockK;  // 16 KiB per operand per stage
-constexpr int kGemmThreads = 256;
+constexpr int kEpiWarps = 16;                  // 4 TMEM lane quarters x 4 column groups of 32
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kGemmThreads = 128 + kEpiThreads;
 constexpr uint32_t kTmemCols = kAccStages * kBlockN;  // 256 columns of 32-bit accumulators
+
+// per-channel epilogue constants staged in shared memory, one array per field (broadcast float4 reads)
+enum { CH_A = 0, CH_B, CH_RSO, CH_SO, CH_SR, CH_RSO2, CH_SO2, CH_FIELDS };
 
 struct GemmSmem {
   alignas(1024) uint8_t a[kStages][kTileBytes];
   alignas(1024) uint8_t b[kStages][kTileBytes];
-  EpiChannel chan[kAccStages][kBlockN];
+  alignas(16) float chan[kAccStages][CH_FIELDS][kBlockN];
   alignas(8) uint64_t full[kStages];
   uint64_t empty[kStages];
   uint64_t acc_full[kAccStages];
@@ -51,89 +57,153 @@ struct GemmArgs {
   int32_t* raw_acc;  // test hook: dump accumulators instead of codes
 };
 
-__device__ __forceinline__ uint32_t pack4(int q0, int q1, int q2, int q3) {
-  return (uint32_t)(q0 & 0xff) | ((uint32_t)(q1 & 0xff) << 8) | ((uint32_t)(q2 & 0xff) << 16) |
-         ((uint32_t)(q3 & 0xff) << 24);
+// RNE + saturate + pack of four fp32 values into four int8 (two F2IP.S8.F32 on sm_100)
+__device__ __forceinline__ uint32_t pack_sat4(float v0, float v1, float v2, float v3) {
+  // cvt.pack d, a, b, c: d[7:0] = sat(b), d[15:8] = sat(a), d[31:16] = c[15:0]
+  uint32_t hi, r;
+  const int i0 = __float2int_rn(v0), i1 = __float2int_rn(v1), i2 = __float2int_rn(v2), i3 = __float2int_rn(v3);
+  asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(hi) : "r"(i3), "r"(i2), "r"(0));
+  asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(i1), "r"(i0), "r"(hi));
+  return r;
 }
 
-// Epilogue of one 32-column chunk held by one thread (= one output row).
+// RNE(fl(y / s) + zp), the unclamped code of a quantizer with a non-power-of-two scale, without paying an
+// IEEE division per element: t = y * fl(1/s) + zp is within a few ulp of the exact operand of the
+// rounding, so rint(t) can differ from the exact result only when t lies within kTieGuard of a
+// half-integer; only those elements (~0.2 %) take the exact division.  For |t| >= 512 both paths
+// saturate to the same int8 code, so the absolute guard is sufficient.
+constexpr float kTieGuard = 0.0009765625f;  // 2^-10 >> 4 ulp(512)
+__device__ __forceinline__ float div_round(float y, float s, float rs, float zp) {
+  const float t = fadd(fmul(y, rs), zp);
+  float r = rintf(t);
+  if (fabsf(fabsf(fsub(t, r)) - 0.5f) < kTieGuard) r = rintf(fadd(fdiv(y, s), zp));
+  return r;
+}
+
+__device__ __forceinline__ float clamp_code(float r) { return fminf(fmaxf(r, -128.f), 127.f); }
+
+// Epilogue of 16 consecutive columns of one output row (one thread).  ch: this accumulator stage's
+// channel constants, c: column offset inside the tile.
 template <uint32_t FLAGS>
-__device__ __forceinline__ void epilogue_chunk(const uint32_t (&acc)[32], const EpiChannel* chan, const GemmArgs& g,
-                                               int row, int col0) {
-  const int ncols = min(32, g.n - col0);
+__device__ __forceinline__ void epilogue16(const uint32_t (&acc)[16], const float (*ch)[kBlockN], int c,
+                                           const GemmArgs& g, int row, int col0) {
+  const int ncols = min(16, g.n - col0);
   if (ncols <= 0) return;
   const int64_t off = (int64_t)row * g.ld_out + col0;
   if (g.raw_acc != nullptr) {
     for (int j = 0; j < ncols; ++j) g.raw_acc[(int64_t)row * g.n + col0 + j] = (int32_t)acc[j];
     return;
   }
-  const bool vec = (ncols == 32) && ((g.ld_out & 15) == 0) && ((col0 & 15) == 0);
-  int res[32];
+  const bool vec = (ncols == 16) && ((g.ld_out & 15) == 0) && ((col0 & 15) == 0);
+  constexpr bool kFold = (FLAGS & EPI_OUT_POT) && !(FLAGS & EPI_GELU);  // scale and bias pre-multiplied by 1/s_out
+  float code[16];   // first-stage codes (clamped, integral)
+  uint32_t resw[4] = {0, 0, 0, 0};
   if (FLAGS & EPI_RESIDUAL) {
     if (vec) {
-      const uint4* rp = reinterpret_cast<const uint4*>(g.epi.residual + off);
-      uint4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
-      const uint32_t w[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
-#pragma unroll
-      for (int j = 0; j < 32; ++j) res[j] = (int)(int8_t)((w[j >> 2] >> (8 * (j & 3))) & 0xff);
+      const uint4 r4 = __ldg(reinterpret_cast<const uint4*>(g.epi.residual + off));
+      resw[0] = r4.x; resw[1] = r4.y; resw[2] = r4.z; resw[3] = r4.w;
     } else {
-      for (int j = 0; j < 32; ++j) res[j] = j < ncols ? (int)g.epi.residual[off + j] : 0;
+      for (int j = 0; j < ncols; ++j) resw[j >> 2] |= (uint32_t)(uint8_t)g.epi.residual[off + j] << (8 * (j & 3));
     }
   }
-  int q[32];
 #pragma unroll
-  for (int j = 0; j < 32; ++j) {
-    const EpiChannel c = chan[j];
-    int code = epilogue_code<FLAGS>((int)acc[j], c, g.epi.out_zp);
+  for (int j4 = 0; j4 < 16; j4 += 4) {
+    const float4 A = *reinterpret_cast<const float4*>(&ch[CH_A][c + j4]);
+    const float4 B = *reinterpret_cast<const float4*>(&ch[CH_B][c + j4]);
+    const float a4[4] = {A.x, A.y, A.z, A.w}, b4[4] = {B.x, B.y, B.z, B.w};
+    float rso[4] = {1.f, 1.f, 1.f, 1.f}, so[4] = {1.f, 1.f, 1.f, 1.f};
+    if (!kFold) {
+      const float4 R = *reinterpret_cast<const float4*>(&ch[CH_RSO][c + j4]);
+      rso[0] = R.x; rso[1] = R.y; rso[2] = R.z; rso[3] = R.w;
+    }
+    if (!(FLAGS & EPI_OUT_POT) || (FLAGS & EPI_RESIDUAL)) {
+      const float4 S = *reinterpret_cast<const float4*>(&ch[CH_SO][c + j4]);
+      so[0] = S.x; so[1] = S.y; so[2] = S.z; so[3] = S.w;
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int j = j4 + e;
+      float y = ffma((float)(int)acc[j], a4[e], b4[e]);   // kFold: already on the output grid
+      if (FLAGS & EPI_GELU) y = gelu_erf(y);
+      float r;
+      if (kFold) r = rintf(y);
+      else if (FLAGS & EPI_OUT_POT) r = rintf(fmul(y, rso[e]));
+      else r = div_round(y, so[e], rso[e], g.epi.out_zp);
+      code[j] = (FLAGS & EPI_RESIDUAL) ? clamp_code(r) : r;   // without residual the pack saturates
+    }
     if (FLAGS & EPI_RESIDUAL) {
-      res[j] = residual_code(code, res[j], c);  // res[] now holds the block-level code
+      const float4 SR = *reinterpret_cast<const float4*>(&ch[CH_SR][c + j4]);
+      const float4 R2 = *reinterpret_cast<const float4*>(&ch[CH_RSO2][c + j4]);
+      const float4 S2 = *reinterpret_cast<const float4*>(&ch[CH_SO2][c + j4]);
+      const float sr[4] = {SR.x, SR.y, SR.z, SR.w}, r2[4] = {R2.x, R2.y, R2.z, R2.w}, s2[4] = {S2.x, S2.y, S2.z, S2.w};
+      const uint32_t w = resw[j4 >> 2];
+      const float res[4] = {(float)(int8_t)(w & 0xff), (float)(int8_t)((w >> 8) & 0xff),
+                            (float)(int8_t)((w >> 16) & 0xff), (float)(int8_t)(w >> 24)};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int j = j4 + e;
+        // fp32: dequantize residual stream and branch, add, re-quantize on the block-level grid
+        const float sum = fadd(fmul(res[e], sr[e]), fmul(code[j], so[e]));
+        const float first = code[j];
+        code[j] = div_round(sum, s2[e], r2[e], 0.f);
+        if (j < ncols) {
+          if (g.epi.aux_codes != nullptr) g.epi.aux_codes[off + j] = (int8_t)first;   // branch codes (qact3 / mlp.qact2)
+          if (g.epi.out_f32 != nullptr)
+            g.epi.out_f32[(int64_t)row * g.n + col0 + j] = fmul(fsub(first, g.epi.out_zp), so[e]);
+        }
+      }
     }
-    q[j] = code;
   }
-  if (g.epi.out_f32 != nullptr) {
-    for (int j = 0; j < ncols; ++j)
-      g.epi.out_f32[(int64_t)row * g.n + col0 + j] = fmul(fsub((float)q[j], g.epi.out_zp), chan[j].out_scale);
+  if (!(FLAGS & EPI_RESIDUAL) && g.epi.out_f32 != nullptr) {
+    for (int j = 0; j < ncols; ++j) {
+      const float q = clamp_code(code[j]);
+      g.epi.out_f32[(int64_t)row * g.n + col0 + j] = fmul(fsub(q, g.epi.out_zp), ch[CH_SO][c + j]);
+    }
   }
-  const int* fin = (FLAGS & EPI_RESIDUAL) ? res : q;
   if (vec) {
-    uint4 o0 = make_uint4(pack4(fin[0], fin[1], fin[2], fin[3]), pack4(fin[4], fin[5], fin[6], fin[7]),
-                          pack4(fin[8], fin[9], fin[10], fin[11]), pack4(fin[12], fin[13], fin[14], fin[15]));
-    uint4 o1 = make_uint4(pack4(fin[16], fin[17], fin[18], fin[19]), pack4(fin[20], fin[21], fin[22], fin[23]),
-                          pack4(fin[24], fin[25], fin[26], fin[27]), pack4(fin[28], fin[29], fin[30], fin[31]));
-    uint4* op = reinterpret_cast<uint4*>(g.out + off);
-    op[0] = o0;
-    op[1] = o1;
-    if ((FLAGS & EPI_RESIDUAL) && g.epi.aux_codes != nullptr) {
-      uint4* ap = reinterpret_cast<uint4*>(g.epi.aux_codes + off);
-      ap[0] = make_uint4(pack4(q[0], q[1], q[2], q[3]), pack4(q[4], q[5], q[6], q[7]),
-                         pack4(q[8], q[9], q[10], q[11]), pack4(q[12], q[13], q[14], q[15]));
-      ap[1] = make_uint4(pack4(q[16], q[17], q[18], q[19]), pack4(q[20], q[21], q[22], q[23]),
-                         pack4(q[24], q[25], q[26], q[27]), pack4(q[28], q[29], q[30], q[31]));
-    }
+    *reinterpret_cast<uint4*>(g.out + off) =
+        make_uint4(pack_sat4(code[0], code[1], code[2], code[3]), pack_sat4(code[4], code[5], code[6], code[7]),
+                   pack_sat4(code[8], code[9], code[10], code[11]), pack_sat4(code[12], code[13], code[14], code[15]));
   } else {
-    for (int j = 0; j < ncols; ++j) g.out[off + j] = (int8_t)fin[j];
-    if ((FLAGS & EPI_RESIDUAL) && g.epi.aux_codes != nullptr)
-      for (int j = 0; j < ncols; ++j) g.epi.aux_codes[off + j] = (int8_t)q[j];
+    for (int j = 0; j < ncols; ++j) g.out[off + j] = (int8_t)clamp_code(code[j]);
   }
 }
 
-__device__ __forceinline__ void load_channels(EpiChannel* chan, const p2v_epilogue& e, int n0, int n, int tid,
-                                              int nthreads, uint32_t flags) {
-  for (int j = tid; j < kBlockN; j += nthreads) {
-    EpiChannel c = {0.f, 0.f, 1.f, 1.f, 0.f, 1.f};
+// Stage the per-channel constants of one 128-column tile (epilogue warps only).
+template <uint32_t FLAGS>
+__device__ __forceinline__ void load_channels(float (*ch)[kBlockN], const p2v_epilogue& e, int n0, int n, int tid) {
+  constexpr bool kFold = (FLAGS & EPI_OUT_POT) && !(FLAGS & EPI_GELU);
+  for (int j = tid; j < kBlockN; j += kEpiThreads) {
     const int col = n0 + j;
+    float A = 0.f, B = 0.f, RSO = 1.f, SO = 1.f, SR = 0.f, RSO2 = 1.f, SO2 = 1.f;
     if (col < n && e.acc_scale != nullptr) {
-      c.acc_scale = e.acc_scale[col];
-      c.bias = e.bias ? e.bias[col] : 0.f;
-      c.out_scale = e.out_scale[col];
-      c.out_rscale = e.out_rscale ? e.out_rscale[col] : 0.f;
-      if (flags & EPI_RESIDUAL) {
-        c.res_scale = e.res_scale[col];
-        c.out2_scale = e.out2_scale[col];
+      A = e.acc_scale[col];
+      B = e.bias ? e.bias[col] : 0.f;
+      SO = e.out_scale[col];
+      RSO = e.out_rscale ? e.out_rscale[col] : __frcp_rn(SO);
+      if (kFold) {  // exact: scaling by a power of two commutes with the single rounding of acc*A + B
+        A = fmul(A, RSO);
+        B = fmul(B, RSO);
+      }
+      if (FLAGS & EPI_RESIDUAL) {
+        SR = e.res_scale[col];
+        SO2 = e.out2_scale[col];
+        RSO2 = __frcp_rn(SO2);
       }
     }
-    chan[j] = c;
+    ch[CH_A][j] = A; ch[CH_B][j] = B; ch[CH_RSO][j] = RSO; ch[CH_SO][j] = SO;
+    ch[CH_SR][j] = SR; ch[CH_RSO2][j] = RSO2; ch[CH_SO2][j] = SO2;
   }
+}
+
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
 }
 
 template <uint32_t FLAGS>
@@ -160,7 +230,7 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     }
     for (int i = 0; i < kAccStages; ++i) {
       mbar_init(&s.acc_full[i], 1);
-      mbar_init(&s.acc_empty[i], 4);  // one arrive per epilogue warp
+      mbar_init(&s.acc_empty[i], kEpiWarps);  // one arrive per epilogue warp
     }
     fence_mbar_init();
   }
@@ -212,27 +282,33 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       }
     }
   } else if (warp >= 4) {
-    const int ew = warp - 4;           // TMEM lane quarter this warp may access (warp id % 4)
+    const int ew = warp - 4;
+    const int quarter = ew & 3;        // TMEM lane quarter this warp may access (= warp id % 4)
+    const int cgroup = ew >> 2;        // 32-column group of the tile
     const int etid = threadIdx.x - 128;
     uint32_t acc = 0, acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m0 = (tile / tiles_n) * kBlockM, n0 = (tile % tiles_n) * kBlockN;
-      // per-channel constants of this tile -> smem (only the epilogue warps touch chan[acc])
-      load_channels(s.chan[acc], g.epi, n0, g.n, etid, 128, FLAGS);
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      // per-channel constants of this tile -> smem.  chan[acc] was last read two tiles ago; every epilogue
+      // warp has passed the barrier of the tile in between, so the overwrite is safe.
+      load_channels<FLAGS>(s.chan[acc], g.epi, n0, g.n, etid);
+      asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
       mbar_wait(&s.acc_full[acc], acc_phase);
       tc_fence_after_sync();
-      const int row = m0 + ew * 32 + lane;
-#pragma unroll 1
-      for (int c = 0; c < kBlockN / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(tmem_base + ((uint32_t)(ew * 32) << 16) + acc * kBlockN + c * 32, v);
-        tmem_ld_wait();
-        if (row < g.m) epilogue_chunk<FLAGS>(v, &s.chan[acc][c * 32], g, row, n0 + c * 32);
-      }
+      const int row = m0 + quarter * 32 + lane;
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * kBlockN + cgroup * 32;
+      uint32_t v0[16], v1[16];
+      tmem_ld_32x16(taddr, v0);
+      tmem_ld_32x16(taddr + 16, v1);
+      tmem_ld_wait();
+      // the accumulator is in registers: release it to the MMA warp before the arithmetic
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(&s.acc_empty[acc]);
+      if (row < g.m) {
+        epilogue16<FLAGS>(v0, s.chan[acc], cgroup * 32, g, row, n0 + cgroup * 32);
+        epilogue16<FLAGS>(v1, s.chan[acc], cgroup * 32 + 16, g, row, n0 + cgroup * 32 + 16);
+      }
       if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
     }
   }
