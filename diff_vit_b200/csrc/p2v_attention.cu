@@ -64,32 +64,36 @@ __device__ __forceinline__ int av_perm(int j) {
 // the same code, the fast one just proves it cheaply.
 constexpr uint32_t kCodeGuard = 64;  // ulps: |u - 2^j| / 2^j < 2^-17, far above the ~4 ulp error of u
 
+__device__ __noinline__ int exact_log_code(float fsum, float e, int levels) { return softmax_log_code(fsum, e, levels); }
+
+// probability 2^-k in units of 2^-15 (k <= 15), 0 for the "zero" code
 __device__ __forceinline__ uint32_t prob16(float fsum, int d, const float* lut_f, const float* lut_r3, int levels) {
   const float u = __fmaf_rn(fsum, lut_r3[d], 0.16666667f);
   const uint32_t bits = __float_as_uint(u);
-  int k;
-  if ((((bits + kCodeGuard) & 0x7fffffu) < 2 * kCodeGuard) || bits < 0x3f800000u) {
-    k = softmax_log_code(fsum, lut_f[d], levels);          // exact path
-  } else {
-    k = (int)(bits >> 23) - 125;
-    k = k > levels ? levels : k;
-  }
-  // probability 2^-k in units of 2^-15 (k <= 15), 0 for the "zero" code: 0x8000 >> k
+  int k = (int)(bits >> 23) - 125;
+  if ((((bits + kCodeGuard) & 0x7fffffu) < 2 * kCodeGuard) || bits < 0x3f800000u)
+    k = exact_log_code(fsum, lut_f[d], levels);
   uint32_t v;
-  asm("shr.u32 %0, %1, %2;" : "=r"(v) : "r"(0x8000u), "r"((uint32_t)k));
+  asm("shr.u32 %0, %1, %2;" : "=r"(v) : "r"(0x8000u), "r"((uint32_t)k));   // shifts >= 32 give 0
   return v;
 }
 
+struct AttSmem {
+  alignas(16) uint8_t Ks[kMaxKeys * kQKStride];
+  alignas(16) uint8_t Qs[kAttRows * kQKStride];
+  alignas(16) uint8_t Vt[kHd * kVtStride];
+  alignas(16) uint8_t codes[kAttWarps][16 * kVtStride];   // biased score codes in AV key order, per warp
+  float lut_f[256];
+  float lut_r3[256];
+  unsigned long long lut_i[256];
+};
+
 template <bool kDump>
-__global__ void __launch_bounds__(kAttWarps * 32, 2)
+__global__ void __launch_bounds__(kAttWarps * 32) __maxnreg__(96)
 attention_int_kernel(const int8_t* __restrict__ qkv, int8_t* __restrict__ out, int n, int heads,
                      const p2v_attention p, int out_shift) {
-  __shared__ __align__(16) uint8_t Ks[kMaxKeys * kQKStride];
-  __shared__ __align__(16) uint8_t Qs[kAttRows * kQKStride];
-  __shared__ __align__(16) uint8_t Vt[kHd * kVtStride];
-  __shared__ float lut_f[256];
-  __shared__ float lut_r3[256];
-  __shared__ unsigned long long lut_i[256];
+  extern __shared__ __align__(16) uint8_t att_smem_raw[];
+  AttSmem& sm = *reinterpret_cast<AttSmem*>(att_smem_raw);
 
   const int bh = blockIdx.x;
   const int img = bh / heads, head = bh % heads;
@@ -104,22 +108,22 @@ attention_int_kernel(const int8_t* __restrict__ qkv, int8_t* __restrict__ out, i
   // ---- stage Q, K (row-major, padded stride) and V (transposed + permuted) in shared memory ----------
   for (int i = tid; i < 256; i += blockDim.x) {
     const float e = p.exp_lut[i];
-    lut_f[i] = e;
-    lut_r3[i] = __fdiv_rn(1.0f, 3.0f * e);   // 3e is exact (e has <= 22 significant bits)
-    lut_i[i] = (unsigned long long)e;
+    sm.lut_f[i] = e;
+    sm.lut_r3[i] = __fdiv_rn(1.0f, 3.0f * e);   // 3e is exact (e has <= 22 significant bits)
+    sm.lut_i[i] = (unsigned long long)e;
   }
   for (int i = tid; i < nkp * 4; i += blockDim.x) {
     const int j = i >> 2, part = i & 3;
     uint4 v = make_uint4(0, 0, 0, 0);
     if (j < n) v = __ldg(reinterpret_cast<const uint4*>(base + j * row_stride + (heads + head) * kHd) + part);
-    *reinterpret_cast<uint4*>(Ks + j * kQKStride + part * 16) = v;
+    *reinterpret_cast<uint4*>(sm.Ks + j * kQKStride + part * 16) = v;
   }
   for (int i = tid; i < kAttRows * 4; i += blockDim.x) {
     const int r = i >> 2, part = i & 3;
     const int row = row_base + r;
     uint4 v = make_uint4(0, 0, 0, 0);
     if (row < n) v = __ldg(reinterpret_cast<const uint4*>(base + row * row_stride + head * kHd) + part);
-    *reinterpret_cast<uint4*>(Qs + r * kQKStride + part * 16) = v;
+    *reinterpret_cast<uint4*>(sm.Qs + r * kQKStride + part * 16) = v;
   }
   // V^T with the key permutation of the AV product: 4 consecutive positions kappa = 16h + 4t + {0,1,2,3}
   // hold keys {j0, j0+1, j0+8, j0+9}, j0 = 32s + 16h + 2t.  One thread transposes a 4-key x 4-channel
@@ -137,7 +141,7 @@ attention_int_kernel(const int8_t* __restrict__ qkv, int8_t* __restrict__ out, i
     const uint32_t lo01 = __byte_perm(r[0], r[1], 0x5140), hi01 = __byte_perm(r[0], r[1], 0x7362);
     const uint32_t lo23 = __byte_perm(r[2], r[3], 0x5140), hi23 = __byte_perm(r[2], r[3], 0x7362);
     const int col = (s5 << 5) + (h << 4) + (tt << 2);
-    uint8_t* dst = Vt + (c4 * 4) * kVtStride + col;
+    uint8_t* dst = sm.Vt + (c4 * 4) * kVtStride + col;
     *reinterpret_cast<uint32_t*>(dst) = __byte_perm(lo01, lo23, 0x5410);
     *reinterpret_cast<uint32_t*>(dst + kVtStride) = __byte_perm(lo01, lo23, 0x7632);
     *reinterpret_cast<uint32_t*>(dst + 2 * kVtStride) = __byte_perm(hi01, hi23, 0x5410);
@@ -148,63 +152,79 @@ attention_int_kernel(const int8_t* __restrict__ qkv, int8_t* __restrict__ out, i
   const int r0 = row_base + warp * 16;
   if (r0 >= n) return;  // warp-uniform; no block-level sync follows
 
-  // ---- S = Q K^T, re-quantized to int8 score codes, kept biased (+128) and packed 4 per register ------
+  // Score codes of this warp's 16 rows live in shared memory in AV key order: the two codes a thread
+  // produces for tile j (row g, keys 8j+2t, 8j+2t+1) land at byte 32s + 16h + 4t + 2(j&1) of the row
+  // (s = j/4, h = (j/2)&1), so that every later pass reads back, as one 32-bit word, exactly the four
+  // codes this same thread wrote: no cross-thread hazard, and the word is the A fragment of the AV MMA.
+  uint8_t* crowA = sm.codes[warp] + g * kVtStride + t * 4;
+  uint8_t* crowB = crowA + 8 * kVtStride;
+
+  // ---- S = Q K^T, re-quantized to int8 score codes (+128 bias) -------------------------------------------
   uint32_t qa[2][4];
 #pragma unroll
   for (int ks = 0; ks < 2; ++ks) {
-    const uint8_t* q0 = Qs + (warp * 16 + g) * kQKStride + ks * 32 + t * 4;
+    const uint8_t* q0 = sm.Qs + (warp * 16 + g) * kQKStride + ks * 32 + t * 4;
     qa[ks][0] = *reinterpret_cast<const uint32_t*>(q0);
     qa[ks][1] = *reinterpret_cast<const uint32_t*>(q0 + 8 * kQKStride);
     qa[ks][2] = *reinterpret_cast<const uint32_t*>(q0 + 16);
     qa[ks][3] = *reinterpret_cast<const uint32_t*>(q0 + 8 * kQKStride + 16);
   }
-  uint32_t codeA[kMaxTiles / 2], codeB[kMaxTiles / 2];  // rows g and g+8, bytes = code + 128
-  int maxA = 0, maxB = 0;                               // biased maxima
+  int maxA = 0, maxB = 0;   // biased maxima
+#pragma unroll 2
+  for (int j = 0; j < ntiles; ++j) {
+    int c[4] = {0, 0, 0, 0};
 #pragma unroll
-  for (int j = 0; j < kMaxTiles; ++j) {
-    if ((j & 1) == 0) { codeA[j >> 1] = 0; codeB[j >> 1] = 0; }
-    if (j < ntiles) {
-      int c[4] = {0, 0, 0, 0};
-#pragma unroll
-      for (int ks = 0; ks < 2; ++ks) {
-        const uint8_t* kp = Ks + (j * 8 + g) * kQKStride + ks * 32 + t * 4;
-        mma_s8s8(c, qa[ks], *reinterpret_cast<const uint32_t*>(kp), *reinterpret_cast<const uint32_t*>(kp + 16));
-      }
-      int sc[4];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        // clamp(RNE(acc * mul + zp)) + 128: acc * mul is exact for the power-of-two multiplier
-        int q;
-        asm("cvt.rni.sat.s8.f32 %0, %1;" : "=r"(q) : "f"(__fmaf_rn((float)c[e], p.score_mul, p.score_zp)));
-        sc[e] = q + 128;
-      }
-      const int col = j * 8 + t * 2;
-      if (col >= n) { sc[0] = 0; sc[2] = 0; }        // padded keys: below every real (biased) code
-      if (col + 1 >= n) { sc[1] = 0; sc[3] = 0; }
-      maxA = max(maxA, max(sc[0], sc[1]));
-      maxB = max(maxB, max(sc[2], sc[3]));
-      const int sh = (j & 1) * 16;
-      codeA[j >> 1] |= ((uint32_t)sc[0] | ((uint32_t)sc[1] << 8)) << sh;
-      codeB[j >> 1] |= ((uint32_t)sc[2] | ((uint32_t)sc[3] << 8)) << sh;
+    for (int ks = 0; ks < 2; ++ks) {
+      const uint8_t* kp = sm.Ks + (j * 8 + g) * kQKStride + ks * 32 + t * 4;
+      mma_s8s8(c, qa[ks], *reinterpret_cast<const uint32_t*>(kp), *reinterpret_cast<const uint32_t*>(kp + 16));
     }
+    int sc[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      // clamp(RNE(acc * mul + zp)) + 128: acc * mul is exact for the power-of-two multiplier
+      int q;
+      asm("cvt.rni.sat.s8.f32 %0, %1;" : "=r"(q) : "f"(__fmaf_rn((float)c[e], p.score_mul, p.score_zp)));
+      sc[e] = q + 128;
+    }
+    const int col = j * 8 + t * 2;
+    if (col >= n) { sc[0] = 0; sc[2] = 0; }        // padded keys: never above a real (biased) code
+    if (col + 1 >= n) { sc[1] = 0; sc[3] = 0; }
+    maxA = max(maxA, max(sc[0], sc[1]));
+    maxB = max(maxB, max(sc[2], sc[3]));
+    const int pos = ((j >> 2) << 5) + (((j >> 1) & 1) << 4) + ((j & 1) << 1);
+    *reinterpret_cast<uint16_t*>(crowA + pos) = (uint16_t)(sc[0] | (sc[1] << 8));
+    *reinterpret_cast<uint16_t*>(crowB + pos) = (uint16_t)(sc[2] | (sc[3] << 8));
   }
   maxA = max(maxA, __shfl_xor_sync(0xffffffffu, maxA, 1));
   maxA = max(maxA, __shfl_xor_sync(0xffffffffu, maxA, 2));
   maxB = max(maxB, __shfl_xor_sync(0xffffffffu, maxB, 1));
   maxB = max(maxB, __shfl_xor_sync(0xffffffffu, maxB, 2));
+  __syncwarp();
+
+  // key index of byte i of word w (w = 2s + h) for this lane
+  auto key_of = [&](int w, int i) { return ((w >> 1) << 5) + ((w & 1) << 4) + ((i >> 1) << 3) + t * 2 + (i & 1); };
+  const int nwords = ntiles >> 1;
+  const int full_words = n >> 4;          // words whose four keys are < n for every lane
 
   // ---- exact integer row sums of the integer exp --------------------------------------------------------
   unsigned long long sumA = 0, sumB = 0;
+#pragma unroll 2
+  for (int w = 0; w < full_words; ++w) {
+    const uint32_t wa = *reinterpret_cast<const uint32_t*>(crowA + w * 16);
+    const uint32_t wb = *reinterpret_cast<const uint32_t*>(crowB + w * 16);
 #pragma unroll
-  for (int j2 = 0; j2 < kMaxTiles / 2; ++j2) {
-    if (j2 * 2 < ntiles) {
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int col = (j2 * 2 + (i >> 1)) * 8 + t * 2 + (i & 1);
-        if (col < n) {
-          sumA += lut_i[maxA - (int)((codeA[j2] >> (8 * i)) & 0xff)];
-          sumB += lut_i[maxB - (int)((codeB[j2] >> (8 * i)) & 0xff)];
-        }
+    for (int i = 0; i < 4; ++i) {
+      sumA += sm.lut_i[maxA - (int)((wa >> (8 * i)) & 0xff)];
+      sumB += sm.lut_i[maxB - (int)((wb >> (8 * i)) & 0xff)];
+    }
+  }
+  for (int w = full_words; w < nwords; ++w) {
+    const uint32_t wa = *reinterpret_cast<const uint32_t*>(crowA + w * 16);
+    const uint32_t wb = *reinterpret_cast<const uint32_t*>(crowB + w * 16);
+    for (int i = 0; i < 4; ++i) {
+      if (key_of(w, i) < n) {
+        sumA += sm.lut_i[maxA - (int)((wa >> (8 * i)) & 0xff)];
+        sumB += sm.lut_i[maxB - (int)((wb >> (8 * i)) & 0xff)];
       }
     }
   }
@@ -224,42 +244,50 @@ attention_int_kernel(const int8_t* __restrict__ qkv, int8_t* __restrict__ out, i
 #pragma unroll
     for (int e = 0; e < 4; ++e) { hi[jn][e] = 0; lo[jn][e] = 0; }
 
+#pragma unroll 1
+  for (int s = 0; s < (ntiles >> 2); ++s) {
+    uint32_t pa_hi[4], pa_lo[4];  // a0..a3 of the two planes
+    const bool full = (2 * s + 1) < full_words;
 #pragma unroll
-  for (int s = 0; s < kMaxTiles / 4; ++s) {
-    if (s * 4 < ntiles) {
-      uint32_t pa_hi[4], pa_lo[4];  // a0..a3 of the two planes
+    for (int hh = 0; hh < 2; ++hh) {        // hh = 0: keys of a0/a1; hh = 1: keys of a2/a3
+      const int w = 2 * s + hh;
+      const uint32_t wa = *reinterpret_cast<const uint32_t*>(crowA + w * 16);
+      const uint32_t wb = *reinterpret_cast<const uint32_t*>(crowB + w * 16);
+      uint32_t va[4], vb[4];
 #pragma unroll
-      for (int hh = 0; hh < 2; ++hh) {        // hh = 0: tiles 4s, 4s+1 (a0/a1); hh = 1: tiles 4s+2, 4s+3 (a2/a3)
-        const uint32_t wa = codeA[2 * s + hh], wb = codeB[2 * s + hh];
-        uint32_t va[4], vb[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int col = (4 * s + 2 * hh + (i >> 1)) * 8 + t * 2 + (i & 1);
-          const int da = maxA - (int)((wa >> (8 * i)) & 0xff), db = maxB - (int)((wb >> (8 * i)) & 0xff);
-          va[i] = col < n ? prob16(fsumA, da, lut_f, lut_r3, p.softmax_levels) : 0u;
-          vb[i] = col < n ? prob16(fsumB, db, lut_f, lut_r3, p.softmax_levels) : 0u;
-          if (kDump && col < n) {
-            const int ka = va[i] ? 15 - (31 - __clz(va[i])) : p.softmax_levels;
-            const int kb = vb[i] ? 15 - (31 - __clz(vb[i])) : p.softmax_levels;
+      for (int i = 0; i < 4; ++i) {
+        const int da = maxA - (int)((wa >> (8 * i)) & 0xff), db = maxB - (int)((wb >> (8 * i)) & 0xff);
+        va[i] = prob16(fsumA, da, sm.lut_f, sm.lut_r3, p.softmax_levels);
+        vb[i] = prob16(fsumB, db, sm.lut_f, sm.lut_r3, p.softmax_levels);
+        if (!full) {
+          const bool ok = key_of(w, i) < n;
+          va[i] = ok ? va[i] : 0u;
+          vb[i] = ok ? vb[i] : 0u;
+        }
+        if (kDump) {
+          const int col = key_of(w, i);
+          if (col < n) {
+            const int ka = va[i] ? __clz(va[i]) - 16 : p.softmax_levels;
+            const int kb = vb[i] ? __clz(vb[i]) - 16 : p.softmax_levels;
             if (rowA < n) { dsc[(int64_t)rowA * n + col] = (int8_t)(maxA - da - 128); dsm[(int64_t)rowA * n + col] = (uint8_t)ka; }
             if (rowB < n) { dsc[(int64_t)rowB * n + col] = (int8_t)(maxB - db - 128); dsm[(int64_t)rowB * n + col] = (uint8_t)kb; }
           }
         }
-        // 16-bit probabilities -> low-byte plane and high-byte plane, 4 keys per register
-        const uint32_t a01 = va[0] | (va[1] << 16), a23 = va[2] | (va[3] << 16);
-        const uint32_t b01 = vb[0] | (vb[1] << 16), b23 = vb[2] | (vb[3] << 16);
-        pa_lo[2 * hh] = __byte_perm(a01, a23, 0x6420);
-        pa_hi[2 * hh] = __byte_perm(a01, a23, 0x7531);
-        pa_lo[2 * hh + 1] = __byte_perm(b01, b23, 0x6420);
-        pa_hi[2 * hh + 1] = __byte_perm(b01, b23, 0x7531);
       }
+      // 16-bit probabilities -> low-byte plane and high-byte plane, 4 keys per register
+      const uint32_t a01 = va[0] | (va[1] << 16), a23 = va[2] | (va[3] << 16);
+      const uint32_t b01 = vb[0] | (vb[1] << 16), b23 = vb[2] | (vb[3] << 16);
+      pa_lo[2 * hh] = __byte_perm(a01, a23, 0x6420);
+      pa_hi[2 * hh] = __byte_perm(a01, a23, 0x7531);
+      pa_lo[2 * hh + 1] = __byte_perm(b01, b23, 0x6420);
+      pa_hi[2 * hh + 1] = __byte_perm(b01, b23, 0x7531);
+    }
 #pragma unroll
-      for (int jn = 0; jn < 8; ++jn) {
-        const uint8_t* vp = Vt + (jn * 8 + g) * kVtStride + s * 32 + t * 4;
-        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(vp), b1 = *reinterpret_cast<const uint32_t*>(vp + 16);
-        mma_u8s8(hi[jn], pa_hi[0], pa_hi[1], pa_hi[2], pa_hi[3], b0, b1);
-        mma_u8s8(lo[jn], pa_lo[0], pa_lo[1], pa_lo[2], pa_lo[3], b0, b1);
-      }
+    for (int jn = 0; jn < 8; ++jn) {
+      const uint8_t* vp = sm.Vt + (jn * 8 + g) * kVtStride + s * 32 + t * 4;
+      const uint32_t b0 = *reinterpret_cast<const uint32_t*>(vp), b1 = *reinterpret_cast<const uint32_t*>(vp + 16);
+      mma_u8s8(hi[jn], pa_hi[0], pa_hi[1], pa_hi[2], pa_hi[3], b0, b1);
+      mma_u8s8(lo[jn], pa_lo[0], pa_lo[1], pa_lo[2], pa_lo[3], b0, b1);
     }
   }
 
@@ -291,6 +319,19 @@ attention_int_kernel(const int8_t* __restrict__ qkv, int8_t* __restrict__ out, i
   }
 }
 
+static int attention_configure() {
+  static int state = 1;
+  if (state == 1) {
+    P2V_CHECK_CUDA(cudaFuncSetAttribute(attention_int_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)sizeof(AttSmem)));
+    P2V_CHECK_CUDA(cudaFuncSetAttribute(attention_int_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)sizeof(AttSmem)));
+    state = 0;
+  }
+  return P2V_OK;
+}
+int attention_configure_once() { return attention_configure(); }
+
 }  // namespace p2v
 
 using namespace p2v;
@@ -307,10 +348,13 @@ extern "C" int p2v_attention_int(const int8_t* qkv, int8_t* out, int b, int n, i
   int out_shift = 0, ex = 0;
   if (p->out_mul > 0 && frexp(p->out_mul, &ex) == 0.5 && ex <= 0 && ex >= -29 && p->out_zp == (float)(int)p->out_zp)
     out_shift = 1 - ex;
+  int rc = attention_configure_once();
+  if (rc) return rc;
+  const size_t smem = sizeof(AttSmem);
   if (p->dump_scores != nullptr)
-    attention_int_kernel<true><<<grid, kAttWarps * 32, 0, (cudaStream_t)stream>>>(qkv, out, n, heads, *p, out_shift);
+    attention_int_kernel<true><<<grid, kAttWarps * 32, smem, (cudaStream_t)stream>>>(qkv, out, n, heads, *p, out_shift);
   else
-    attention_int_kernel<false><<<grid, kAttWarps * 32, 0, (cudaStream_t)stream>>>(qkv, out, n, heads, *p, out_shift);
+    attention_int_kernel<false><<<grid, kAttWarps * 32, smem, (cudaStream_t)stream>>>(qkv, out, n, heads, *p, out_shift);
   P2V_CHECK_CUDA(cudaGetLastError());
   return P2V_OK;
 }

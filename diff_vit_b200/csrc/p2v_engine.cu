@@ -28,6 +28,7 @@ void set_error(const char* fmt, ...) {
 
 int make_tmap_kmajor(CUtensorMap* map, const void* ptr, int64_t rows, int64_t k, int64_t ld);
 int gemm_configure();
+int attention_configure_once();
 int gemm_i8_tc(const CUtensorMap& ta, const CUtensorMap& tb, int8_t* out, int64_t ld_out, int m, int n, int k,
                const p2v_epilogue& epi, cudaStream_t st);
 
@@ -259,6 +260,7 @@ extern "C" int p2v_vit_create(const p2v_vit_desc* desc, int device, p2v_vit** ou
   if (rc) return rc;
   P2V_CHECK_CUDA(cudaSetDevice(device));
   if ((rc = gemm_configure())) return rc;
+  if ((rc = attention_configure_once())) return rc;
   p2v_vit* h = new p2v_vit();
   h->d = *desc;
   h->blocks.assign(desc->blocks, desc->blocks + desc->depth);

@@ -91,7 +91,9 @@ __device__ __forceinline__ void epilogue16(const uint32_t (&acc)[16], const floa
   if (ncols <= 0) return;
   const int64_t off = (int64_t)row * g.ld_out + col0;
   if (g.raw_acc != nullptr) {
-    for (int j = 0; j < ncols; ++j) g.raw_acc[(int64_t)row * g.n + col0 + j] = (int32_t)acc[j];
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      if (j < ncols) g.raw_acc[(int64_t)row * g.n + col0 + j] = (int32_t)acc[j];
     return;
   }
   const bool vec = (ncols == 16) && ((g.ld_out & 15) == 0) && ((col0 & 15) == 0);
@@ -103,7 +105,9 @@ __device__ __forceinline__ void epilogue16(const uint32_t (&acc)[16], const floa
       const uint4 r4 = __ldg(reinterpret_cast<const uint4*>(g.epi.residual + off));
       resw[0] = r4.x; resw[1] = r4.y; resw[2] = r4.z; resw[3] = r4.w;
     } else {
-      for (int j = 0; j < ncols; ++j) resw[j >> 2] |= (uint32_t)(uint8_t)g.epi.residual[off + j] << (8 * (j & 3));
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        if (j < ncols) resw[j >> 2] |= (uint32_t)(uint8_t)g.epi.residual[off + j] << (8 * (j & 3));
     }
   }
 #pragma unroll
@@ -155,9 +159,12 @@ __device__ __forceinline__ void epilogue16(const uint32_t (&acc)[16], const floa
     }
   }
   if (!(FLAGS & EPI_RESIDUAL) && g.epi.out_f32 != nullptr) {
-    for (int j = 0; j < ncols; ++j) {
-      const float q = clamp_code(code[j]);
-      g.epi.out_f32[(int64_t)row * g.n + col0 + j] = fmul(fsub(q, g.epi.out_zp), ch[CH_SO][c + j]);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      if (j < ncols) {
+        const float q = clamp_code(code[j]);
+        g.epi.out_f32[(int64_t)row * g.n + col0 + j] = fmul(fsub(q, g.epi.out_zp), ch[CH_SO][c + j]);
+      }
     }
   }
   if (vec) {
@@ -165,7 +172,9 @@ __device__ __forceinline__ void epilogue16(const uint32_t (&acc)[16], const floa
         make_uint4(pack_sat4(code[0], code[1], code[2], code[3]), pack_sat4(code[4], code[5], code[6], code[7]),
                    pack_sat4(code[8], code[9], code[10], code[11]), pack_sat4(code[12], code[13], code[14], code[15]));
   } else {
-    for (int j = 0; j < ncols; ++j) g.out[off + j] = (int8_t)clamp_code(code[j]);
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      if (j < ncols) g.out[off + j] = (int8_t)clamp_code(code[j]);
   }
 }
 
