@@ -89,7 +89,7 @@ struct AttSmem {
 };
 
 template <bool kDump>
-__global__ void __launch_bounds__(kAttWarps * 32) __maxnreg__(96)
+__global__ void __maxnreg__(96)
 attention_int_kernel(const int8_t* __restrict__ qkv, int8_t* __restrict__ out, int n, int heads,
                      const p2v_attention p, int out_shift) {
   extern __shared__ __align__(16) uint8_t att_smem_raw[];

@@ -84,8 +84,8 @@ __device__ __forceinline__ float clamp_code(float r) { return fminf(fmaxf(r, -12
 
 // Epilogue of 16 consecutive columns of one output row (one thread).  ch: this accumulator stage's
 // channel constants, c: column offset inside the tile.
-template <uint32_t FLAGS>
-__device__ __forceinline__ void epilogue16(const uint32_t (&acc)[16], const float (*ch)[kBlockN], int c,
+template <uint32_t FLAGS, int CW>
+__device__ __forceinline__ void epilogue16(const uint32_t (&acc)[16], const float (*ch)[CW], int c,
                                            const GemmArgs& g, int row, int col0) {
   const int ncols = min(16, g.n - col0);
   if (ncols <= 0) return;
@@ -179,10 +179,10 @@ __device__ __forceinline__ void epilogue16(const uint32_t (&acc)[16], const floa
 }
 
 // Stage the per-channel constants of one 128-column tile (epilogue warps only).
-template <uint32_t FLAGS>
-__device__ __forceinline__ void load_channels(float (*ch)[kBlockN], const p2v_epilogue& e, int n0, int n, int tid) {
+template <uint32_t FLAGS, int CW>
+__device__ __forceinline__ void load_channels(float (*ch)[CW], const p2v_epilogue& e, int n0, int n, int tid) {
   constexpr bool kFold = (FLAGS & EPI_OUT_POT) && !(FLAGS & EPI_GELU);
-  for (int j = tid; j < kBlockN; j += kEpiThreads) {
+  for (int j = tid; j < CW; j += kEpiThreads) {
     const int col = n0 + j;
     float A = 0.f, B = 0.f, RSO = 1.f, SO = 1.f, SR = 0.f, RSO2 = 1.f, SO2 = 1.f;
     if (col < n && e.acc_scale != nullptr) {
@@ -300,7 +300,7 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       const int m0 = (tile / tiles_n) * kBlockM, n0 = (tile % tiles_n) * kBlockN;
       // per-channel constants of this tile -> smem.  chan[acc] was last read two tiles ago; every epilogue
       // warp has passed the barrier of the tile in between, so the overwrite is safe.
-      load_channels<FLAGS>(s.chan[acc], g.epi, n0, g.n, etid);
+      load_channels<FLAGS, kBlockN>(s.chan[acc], g.epi, n0, g.n, etid);
       asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
       mbar_wait(&s.acc_full[acc], acc_phase);
       tc_fence_after_sync();
@@ -315,8 +315,8 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       __syncwarp();
       if (lane == 0) mbar_arrive(&s.acc_empty[acc]);
       if (row < g.m) {
-        epilogue16<FLAGS>(v0, s.chan[acc], cgroup * 32, g, row, n0 + cgroup * 32);
-        epilogue16<FLAGS>(v1, s.chan[acc], cgroup * 32 + 16, g, row, n0 + cgroup * 32 + 16);
+        epilogue16<FLAGS, kBlockN>(v0, s.chan[acc], cgroup * 32, g, row, n0 + cgroup * 32);
+        epilogue16<FLAGS, kBlockN>(v1, s.chan[acc], cgroup * 32 + 16, g, row, n0 + cgroup * 32 + 16);
       }
       if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
     }
@@ -324,6 +324,161 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   tc_fence_before_sync();
   __syncthreads();
   if (warp == 2) tmem_dealloc<kTmemCols>(tmem_base);
+}
+
+// ---- weight-stationary variant for k <= 384 ---------------------------------------------------------------
+// With D = 384 three of the four GEMMs of a block have a K of only three k-blocks, and streaming both
+// operands per 128x128 tile re-reads them from L2 so often that L2->SM bandwidth, not the tensor pipe,
+// sets the pace (ncu: 340 MB of operand traffic for the 19 MB qkv input).  Here a CTA owns a slab of up to
+// 256 output columns for its whole lifetime: the slab's weights ([256, k] <= 96 KiB) are loaded once and
+// stay in shared memory, only A tiles stream through a 6-stage ring, each k-block feeds ONE
+// M128 x N256 x K32 MMA chain into a 256-column accumulator, and two accumulators ping-pong so the 16
+// epilogue warps drain one while the tensor pipe fills the other.  Per-channel constants are staged once.
+constexpr int kBsMaxKb = 3;        // k <= 384
+constexpr int kBsStagesA = 6;
+constexpr int kBsSlabCols = 256;
+constexpr int kBsMaxSlabs = 16;
+
+struct BsSlab {
+  int n0, nw;            // first column, width (<= 256)
+  int cta_begin, cta_count;
+};
+struct BsPlan {
+  int nslabs;
+  BsSlab slab[kBsMaxSlabs];
+};
+
+struct BsSmem {
+  alignas(1024) uint8_t b[kBsMaxKb][2][kTileBytes];   // [k-block][128-column half] = rows of the slab
+  alignas(1024) uint8_t a[kBsStagesA][kTileBytes];
+  alignas(16) float chan[CH_FIELDS][kBsSlabCols];
+  alignas(8) uint64_t full[kBsStagesA];
+  uint64_t empty[kBsStagesA];
+  uint64_t b_full;
+  uint64_t acc_full[2];
+  uint64_t acc_empty[2];
+  uint32_t tmem_base;
+};
+
+template <uint32_t FLAGS>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_i8_bs_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                  const GemmArgs g, const BsPlan plan) {
+  extern __shared__ uint8_t smem_raw[];
+  BsSmem& s = *reinterpret_cast<BsSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int tiles_m = (g.m + kBlockM - 1) / kBlockM;
+  const int num_kb = (g.k + kBlockK - 1) / kBlockK;
+
+  // which slab does this CTA own, and which of the slab's CTAs is it
+  int n0 = 0, nw = 0, local = 0, cnt = 0;
+  for (int i = 0; i < plan.nslabs; ++i) {
+    const BsSlab sl = plan.slab[i];
+    if ((int)blockIdx.x >= sl.cta_begin && (int)blockIdx.x < sl.cta_begin + sl.cta_count) {
+      n0 = sl.n0; nw = sl.nw; local = (int)blockIdx.x - sl.cta_begin; cnt = sl.cta_count;
+    }
+  }
+  const int nsub = (nw + kBlockN - 1) / kBlockN;   // 128-column halves in use (0 for an idle CTA)
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kBsStagesA; ++i) {
+      mbar_init(&s.full[i], 1);
+      mbar_init(&s.empty[i], 1);
+    }
+    mbar_init(&s.b_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s.acc_full[i], 1);
+      mbar_init(&s.acc_empty[i], kEpiWarps);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc<512>(&s.tmem_base);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = s.tmem_base;
+
+  if (nsub > 0) {
+    if (warp == 0) {
+      if (elect_one()) {
+        // the slab's weights, once
+        mbar_expect_tx(&s.b_full, (uint32_t)(num_kb * nsub * kTileBytes));
+        for (int kb = 0; kb < num_kb; ++kb)
+          for (int h = 0; h < nsub; ++h) tma_load_2d(s.b[kb][h], &tmap_b, &s.b_full, kb * kBlockK, n0 + h * kBlockN);
+        uint32_t stage = 0, phase = 0;
+        for (int tile = local; tile < tiles_m; tile += cnt) {
+          for (int kb = 0; kb < num_kb; ++kb) {
+            mbar_wait(&s.empty[stage], phase ^ 1);
+            mbar_expect_tx(&s.full[stage], kTileBytes);
+            tma_load_2d(s.a[stage], &tmap_a, &s.full[stage], kb * kBlockK, tile * kBlockM);
+            if (++stage == kBsStagesA) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    } else if (warp == 1) {
+      if (elect_one()) {
+        const uint32_t idesc = umma_idesc_i8(kBlockM, nsub * kBlockN);
+        mbar_wait(&s.b_full, 0);
+        uint32_t stage = 0, phase = 0, it = 0;
+        for (int tile = local; tile < tiles_m; tile += cnt, ++it) {
+          const uint32_t p = it & 1;
+          mbar_wait(&s.acc_empty[p], ((it >> 1) & 1) ^ 1);
+          tc_fence_after_sync();
+          const uint32_t tmem_d = tmem_base + p * kBsSlabCols;
+          for (int kb = 0; kb < num_kb; ++kb) {
+            mbar_wait(&s.full[stage], phase);
+            tc_fence_after_sync();
+            const uint64_t da = umma_desc_sw128_kmajor(smem_u32(s.a[stage]));
+            const uint64_t db = umma_desc_sw128_kmajor(smem_u32(s.b[kb][0]));   // 256 rows: both halves
+#pragma unroll
+            for (int k = 0; k < kBlockK / kUmmaK; ++k)
+              tc_mma_i8(tmem_d, da + (uint64_t)(k * (kUmmaK >> 4)), db + (uint64_t)(k * (kUmmaK >> 4)), idesc,
+                        (uint32_t)((kb | k) != 0));
+            tc_commit(&s.empty[stage]);
+            if (++stage == kBsStagesA) { stage = 0; phase ^= 1; }
+          }
+          tc_commit(&s.acc_full[p]);
+        }
+      }
+    } else if (warp >= 4) {
+      const int ew = warp - 4;
+      const int quarter = ew & 3, cgroup = ew >> 2;
+      load_channels<FLAGS, kBsSlabCols>(s.chan, g.epi, n0, g.n, (int)threadIdx.x - 128);
+      asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+      uint32_t it = 0;
+      for (int tile = local; tile < tiles_m; tile += cnt, ++it) {
+        const uint32_t p = it & 1;
+        mbar_wait(&s.acc_full[p], (it >> 1) & 1);
+        tc_fence_after_sync();
+        const int row = tile * kBlockM + quarter * 32 + lane;
+        for (int h = 0; h < nsub; ++h) {
+          const int c = h * kBlockN + cgroup * 32;
+          const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + p * kBsSlabCols + c;
+          uint32_t v0[16], v1[16];
+          tmem_ld_32x16(taddr, v0);
+          tmem_ld_32x16(taddr + 16, v1);
+          tmem_ld_wait();
+          if (h == nsub - 1) {   // both halves are in registers or done: hand the accumulator back
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s.acc_empty[p]);
+          }
+          if (row < g.m) {
+            epilogue16<FLAGS, kBsSlabCols>(v0, s.chan, c, g, row, n0 + c);
+            epilogue16<FLAGS, kBsSlabCols>(v1, s.chan, c + 16, g, row, n0 + c + 16);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<512>(tmem_base);
 }
 
 // ---- CUDA-core cross-check (dp4a) -----------------------------------------------------------------------
@@ -397,12 +552,49 @@ int make_tmap_kmajor(CUtensorMap* map, const void* ptr, int64_t rows, int64_t k,
 }
 
 constexpr int kGemmSmemBytes = (int)sizeof(GemmSmem) + 1024;
+constexpr int kBsSmemBytes = (int)sizeof(BsSmem) + 1024;
 
 template <uint32_t FLAGS>
 static int configure_one() {
   P2V_CHECK_CUDA(cudaFuncSetAttribute(gemm_i8_tc_kernel<FLAGS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       kGemmSmemBytes));
+  P2V_CHECK_CUDA(cudaFuncSetAttribute(gemm_i8_bs_kernel<FLAGS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      kBsSmemBytes));
   return P2V_OK;
+}
+
+static int g_gemm_mode = 0;   // 0 = auto, 1 = streaming kernel only, 2 = weight-stationary whenever legal
+
+// Split n into slabs of <= 256 columns and hand each slab CTAs in proportion to its width.
+static bool make_bs_plan(int n, int k, int grid, BsPlan* plan) {
+  if (k > kBsMaxKb * kBlockK) return false;
+  const int nslabs = (n + kBsSlabCols - 1) / kBsSlabCols;
+  if (nslabs > kBsMaxSlabs || nslabs > grid) return false;
+  int units_total = 0, units[kBsMaxSlabs];
+  for (int i = 0; i < nslabs; ++i) {
+    const int nw = (n - i * kBsSlabCols) < kBsSlabCols ? (n - i * kBsSlabCols) : kBsSlabCols;
+    plan->slab[i].n0 = i * kBsSlabCols;
+    plan->slab[i].nw = nw;
+    units[i] = (nw + kBlockN - 1) / kBlockN;
+    units_total += units[i];
+  }
+  int given = 0;
+  for (int i = 0; i < nslabs; ++i) {
+    int c = grid * units[i] / units_total;
+    plan->slab[i].cta_count = c < 1 ? 1 : c;
+    given += plan->slab[i].cta_count;
+  }
+  for (int i = 0; given < grid; i = (i + 1) % nslabs) {   // leftovers to the widest slabs first
+    if (units[i] == 2 || nslabs == 1 || i >= nslabs - 1) { plan->slab[i].cta_count++; given++; }
+  }
+  if (given > grid) return false;
+  int begin = 0;
+  for (int i = 0; i < nslabs; ++i) {
+    plan->slab[i].cta_begin = begin;
+    begin += plan->slab[i].cta_count;
+  }
+  plan->nslabs = nslabs;
+  return true;
 }
 
 // Opt every instantiation into > 48 KiB of dynamic shared memory.  Done once per process, outside any
@@ -429,7 +621,15 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArg
   const int smem = kGemmSmemBytes;
   int rc = gemm_configure();
   if (rc) return rc;
-  const int tiles = ((g.m + kBlockM - 1) / kBlockM) * ((g.n + kBlockN - 1) / kBlockN);
+  const int tiles_m = (g.m + kBlockM - 1) / kBlockM;
+  const int tiles = tiles_m * ((g.n + kBlockN - 1) / kBlockN);
+  BsPlan plan;
+  // weight-stationary pays off once every CTA re-uses its slab for several row tiles
+  if (g_gemm_mode != 1 && (g_gemm_mode == 2 || tiles >= 2 * kNumSMs) && make_bs_plan(g.n, g.k, kNumSMs, &plan)) {
+    gemm_i8_bs_kernel<FLAGS><<<kNumSMs, kGemmThreads, kBsSmemBytes, st>>>(ta, tb, g, plan);
+    P2V_CHECK_CUDA(cudaGetLastError());
+    return P2V_OK;
+  }
   const int grid = tiles < kNumSMs ? tiles : kNumSMs;
   gemm_i8_tc_kernel<FLAGS><<<grid, kGemmThreads, smem, st>>>(ta, tb, g);
   P2V_CHECK_CUDA(cudaGetLastError());
@@ -485,6 +685,12 @@ extern "C" int p2v_gemm_i8(const int8_t* a, int64_t lda, const int8_t* w, int8_t
   if ((rc = make_tmap_kmajor(&ta, a, m, k, lda))) return rc;
   if ((rc = make_tmap_kmajor(&tb, w, n, k, k))) return rc;
   return gemm_i8_tc(ta, tb, out, ld_out, m, n, k, *epi, (cudaStream_t)stream);
+}
+
+extern "C" int p2v_gemm_set_mode(int mode) {
+  P2V_REQUIRE(mode >= 0 && mode <= 2, "p2v_gemm_set_mode: mode must be 0 (auto), 1 (streaming) or 2 (weight-stationary)");
+  g_gemm_mode = mode;
+  return P2V_OK;
 }
 
 extern "C" int p2v_gemm_i8_acc(const int8_t* a, int64_t lda, const int8_t* w, int32_t* acc, int m, int n, int k,

@@ -78,10 +78,105 @@ __global__ void embed_assemble_kernel(const int8_t* __restrict__ pe, int8_t* __r
 }
 
 // ---- integer LayerNorm ---------------------------------------------------------------------------------
-// One warp per row; each lane owns 4-channel groups (32-bit loads; rows are 4-byte aligned by contract).
-// kMaxGroups bounds d <= 32 * 4 * kMaxGroups.
+// One warp per row, grid-stride over rows; each lane owns the same 4-channel groups in every row, so for
+// d <= 128 * kRegGroups the per-channel constants are loaded once into registers and reused for all rows
+// of the warp.  Power-of-two output grids (every minmax-calibrated model) fold 1/s_out into gamma and
+// beta: fl(t*gamma) * 2^-e == fl(t * (gamma * 2^-e)), so the folded form rounds exactly like the
+// reference's (t * gamma) / s_out and (beta - u * gamma) / s_out.
 constexpr int kLnMaxGroups = 8;  // d <= 1024
 
+__device__ __forceinline__ uint32_t pack_sat4f(float v0, float v1, float v2, float v3) {
+  uint32_t hi, r;
+  const int i0 = __float2int_rn(v0), i1 = __float2int_rn(v1), i2 = __float2int_rn(v2), i3 = __float2int_rn(v3);
+  asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(hi) : "r"(i3), "r"(i2), "r"(0));
+  asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(i1), "r"(i0), "r"(hi));
+  return r;
+}
+
+// LN code of one element on a power-of-two grid with pre-folded affine (go = gamma/s_out, bo = beta/s_out)
+__device__ __forceinline__ float ln_code_folded(float xq, const LnRow& row, float go, float bo) {
+  const float A = fmul(row.t, go);
+  const float absA = fabsf(A);
+  const float sign = A > 0.f ? 1.f : (A < 0.f ? -1.f : 0.f);
+  int e = (int)((f2u(absA) >> 23) & 0xffu) - 127;
+  int N = 7 - e;
+  N = N < 0 ? 0 : (N > 31 ? 31 : N);
+  const float p2N = pow2i(N);
+  float M = floorf(fmul(absA, p2N));
+  M = fminf(M, 255.f);
+  const float Bq = rne(fmul(fsub(bo, fmul(row.u, go)), p2N));
+  const float y = fadd(fmul(fmul(sign, M), xq), Bq);
+  return rne(fmul(y, pow2i(-N)));
+}
+
+template <int G>
+__global__ void __launch_bounds__(256)
+layernorm_int_pot_kernel(const int8_t* __restrict__ in, int64_t in_row_stride, int8_t* __restrict__ out,
+                         int32_t* __restrict__ ln_codes, int rows, int d, const p2v_layernorm p) {
+  const int lane = threadIdx.x & 31;
+  const int warps_total = gridDim.x * (blockDim.x >> 5);
+  const int groups = d >> 2;
+  float go[G][4], bo[G][4], pm[G][4];
+  int mk[G][4];
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    const int grp = g * 32 + lane;
+    if (grp < groups) {
+      const int c0 = grp * 4;
+      const float4 ga = *reinterpret_cast<const float4*>(p.gamma + c0);
+      const float4 be = *reinterpret_cast<const float4*>(p.beta + c0);
+      const float4 rs = *reinterpret_cast<const float4*>(p.ln_out_rscale + c0);
+      const float4 m4 = *reinterpret_cast<const float4*>(p.post_mul + c0);
+      const float4 im = *reinterpret_cast<const float4*>(p.in_mask + c0);
+      go[g][0] = fmul(ga.x, rs.x); go[g][1] = fmul(ga.y, rs.y); go[g][2] = fmul(ga.z, rs.z); go[g][3] = fmul(ga.w, rs.w);
+      bo[g][0] = fmul(be.x, rs.x); bo[g][1] = fmul(be.y, rs.y); bo[g][2] = fmul(be.z, rs.z); bo[g][3] = fmul(be.w, rs.w);
+      pm[g][0] = m4.x; pm[g][1] = m4.y; pm[g][2] = m4.z; pm[g][3] = m4.w;
+      mk[g][0] = (int)im.x; mk[g][1] = (int)im.y; mk[g][2] = (int)im.z; mk[g][3] = (int)im.w;
+    }
+  }
+  for (int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < rows; row += warps_total) {
+    const int8_t* src = in + (int64_t)row * in_row_stride;
+    float xq[G][4];
+    int sum = 0, sumsq = 0;   // |x| <= 1024, d <= 128 G: per-lane partial sums stay far below 2^31
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      const int grp = g * 32 + lane;
+      if (grp < groups) {
+        const uint32_t word = __ldg(reinterpret_cast<const uint32_t*>(src + grp * 4));
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int v = (int)(int8_t)((word >> (8 * j)) & 0xff) * mk[g][j];
+          xq[g][j] = (float)v;
+          sum += v;
+          sumsq += v * v;
+        }
+      }
+    }
+    long long sumsq64 = sumsq;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      sumsq64 += __shfl_xor_sync(0xffffffffu, sumsq64, o);
+    }
+    const LnRow st = ln_row_stats((long long)sum, sumsq64, d, p.in_scale1);
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      const int grp = g * 32 + lane;
+      if (grp < groups) {
+        float v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float code = ln_code_folded(xq[g][j], st, go[g][j], bo[g][j]);
+          if (ln_codes != nullptr) ln_codes[(int64_t)row * d + grp * 4 + j] = (int)code;
+          v[j] = fadd(fmul(code, pm[g][j]), p.post_zp);
+        }
+        *reinterpret_cast<uint32_t*>(out + (int64_t)row * d + grp * 4) = pack_sat4f(v[0], v[1], v[2], v[3]);
+      }
+    }
+  }
+}
+
+// General path (non-power-of-two grids, or d > 128 * 3): constants re-read per row, IEEE divisions.
 template <bool POT>
 __global__ void __launch_bounds__(256)
 layernorm_int_kernel(const int8_t* __restrict__ in, int64_t in_row_stride, int8_t* __restrict__ out,
@@ -212,14 +307,18 @@ extern "C" int p2v_layernorm_int(const int8_t* in, int64_t in_row_stride, int8_t
   P2V_REQUIRE(p->in_mask && p->gamma && p->beta && p->ln_out_scale, "p2v_layernorm_int: missing vectors");
   const int warps = 8;
   const int grid = (rows + warps - 1) / warps;
+  cudaStream_t st = (cudaStream_t)stream;
   if (p->pot) {
     P2V_REQUIRE(p->ln_out_rscale && p->post_mul, "p2v_layernorm_int: pot path needs ln_out_rscale and post_mul");
-    layernorm_int_kernel<true><<<grid, warps * 32, 0, (cudaStream_t)stream>>>(in, in_row_stride, out, ln_codes, rows,
-                                                                               d, *p);
+    const int groups = (d / 4 + 31) / 32;
+    const int pgrid = grid < kNumSMs * 4 ? grid : kNumSMs * 4;   // persistent warps: constants stay in registers
+    if (groups == 1) layernorm_int_pot_kernel<1><<<pgrid, warps * 32, 0, st>>>(in, in_row_stride, out, ln_codes, rows, d, *p);
+    else if (groups == 2) layernorm_int_pot_kernel<2><<<pgrid, warps * 32, 0, st>>>(in, in_row_stride, out, ln_codes, rows, d, *p);
+    else if (groups == 3) layernorm_int_pot_kernel<3><<<pgrid, warps * 32, 0, st>>>(in, in_row_stride, out, ln_codes, rows, d, *p);
+    else layernorm_int_kernel<true><<<grid, warps * 32, 0, st>>>(in, in_row_stride, out, ln_codes, rows, d, *p);
   } else {
     P2V_REQUIRE(p->post_div1, "p2v_layernorm_int: non-pot path needs post_div1");
-    layernorm_int_kernel<false><<<grid, warps * 32, 0, (cudaStream_t)stream>>>(in, in_row_stride, out, ln_codes, rows,
-                                                                                d, *p);
+    layernorm_int_kernel<false><<<grid, warps * 32, 0, st>>>(in, in_row_stride, out, ln_codes, rows, d, *p);
   }
   P2V_CHECK_CUDA(cudaGetLastError());
   return P2V_OK;

@@ -67,6 +67,9 @@ int p2v_gemm_i8(const int8_t* a, int64_t lda, const int8_t* w, int8_t* out, int6
 /* Same contract on CUDA cores (dp4a); a slow cross-check used by the tests. */
 int p2v_gemm_i8_simt(const int8_t* a, int64_t lda, const int8_t* w, int8_t* out, int64_t ld_out, int m,
                      int n, int k, const p2v_epilogue* epi, void* stream);
+/* Kernel selection for p2v_gemm_i8 (test hook): 0 = automatic, 1 = operand-streaming kernel only,
+ * 2 = weight-stationary kernel whenever k <= 384. */
+int p2v_gemm_set_mode(int mode);
 /* Raw int32 accumulators of the tensor-core kernel (test hook). */
 int p2v_gemm_i8_acc(const int8_t* a, int64_t lda, const int8_t* w, int32_t* acc, int m, int n, int k,
                     void* stream);

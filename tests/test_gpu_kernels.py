@@ -28,11 +28,20 @@ def _rand_i8(rng, *shape, lo=-128, hi=127):
 
 
 GEMM_SHAPES = [(128, 128, 128), (256, 384, 128), (300, 192, 192), (50, 1000, 384), (1970, 1536, 384),
-               (1970, 384, 1536), (6, 16, 128), (129, 136, 80), (20000, 384, 384)]
+               (1970, 384, 1536), (6, 16, 128), (129, 136, 80), (20000, 384, 384), (50432, 1152, 384),
+               (5000, 4000, 256), (3000, 576, 192)]
+
+
+@pytest.fixture(params=[1, 2], ids=['streaming', 'weight_stationary'])
+def gemm_mode(request, cabi):
+    """Both tensor-core kernels: operand-streaming (any k) and weight-stationary (k <= 384)."""
+    cabi.check(cabi.lib().p2v_gemm_set_mode(request.param))
+    yield request.param
+    cabi.check(cabi.lib().p2v_gemm_set_mode(0))
 
 
 @pytest.mark.parametrize('m,n,k', GEMM_SHAPES)
-def test_gemm_tensor_core_accumulators_exact(cabi, m, n, k):
+def test_gemm_tensor_core_accumulators_exact(cabi, gemm_mode, m, n, k):
     rng = np.random.default_rng(m * 7 + n * 3 + k)
     a, w = _rand_i8(rng, m, k), _rand_i8(rng, n, k)
     ad, wd = torch.from_numpy(a).cuda(), torch.from_numpy(w).cuda()
@@ -64,7 +73,9 @@ def _epilogue_case(rng, n, pot, gelu, residual):
 @pytest.mark.parametrize('pot,gelu,residual', [(True, False, False), (True, True, False), (False, False, True),
                                                (False, False, False), (True, False, True)])
 @pytest.mark.parametrize('m,n,k', [(394, 384, 384), (197, 1000, 192)])
-def test_gemm_epilogues_match_host_arithmetic(cabi, impl, pot, gelu, residual, m, n, k):
+def test_gemm_epilogues_match_host_arithmetic(cabi, gemm_mode, impl, pot, gelu, residual, m, n, k):
+    if impl == 'p2v_gemm_i8_simt' and gemm_mode == 2:
+        pytest.skip('the CUDA-core cross-check has a single kernel')
     rng = np.random.default_rng(1 + m + n + k + 2 * pot + 4 * gelu + 8 * residual)
     a, w = _rand_i8(rng, m, k), _rand_i8(rng, n, k, lo=-100, hi=100)
     lp = _epilogue_case(rng, n, pot, gelu, residual)
