@@ -13,7 +13,7 @@
 // The probabilities 2^(15-k) span 16 bits, so P is split into two u8 planes (k <= 7 -> 2^(7-k) in units of
 // 2^8; k >= 8 -> 2^(15-k)) and the AV product is two u8 x s8 tensor-core MMAs recombined as (hi << 8) + lo.
 //
-// One CTA = one (image, head) x 112 query rows; one warp = 16 query rows, all keys.  Both products use
+// One CTA = one (image, head), K/V staged once; each of its 7 warps walks 16-row query tiles, all keys.  Both products use
 // mma.sync m16n8k32 (IMMA): the score fragment layout (row g, cols 2t,2t+1 of each 8-key tile) is re-used
 // directly as the A operand of the AV product by permuting the key order of V when it is transposed into
 // shared memory, so the 4-bit codes never round-trip through memory.
@@ -57,30 +57,34 @@ __device__ __forceinline__ int av_perm(int j) {
 
 // Fast evaluation of the log2 code k = log_round(RNE(S / e)) (p2v_math.cuh softmax_log_code).
 // With y = S/e + 1/2 the code is a step function of y with steps at 2, 3, 6, 12, 24, ...:
-//   k = floor(log2(y / 3)) + 2 for y >= 3.
+//   k = floor(log2(y / 3)) + 2 for y >= 3, and the probability in units of 2^-15 is 1 << (15 - k).
 // u = fma(S, fl(1/(3e)), 1/6) approximates y/3 to a few ulp, so k = exponent(u) + 2 unless u lies within
-// kCodeGuard ulps of a power of two (a step) or below 1 (y < 3: the one or two dominant keys of a row);
-// those elements (~1e-5 of all, plus <= 2 per row) take the exact IEEE-division path.  Both paths return
-// the same code, the fast one just proves it cheaply.
+// kCodeGuard ulps of a power of two (a step) or below 1 (y < 3: a key holding more than 40 % of the row
+// mass, where the one irregular step y = 2 lives).  Flagged elements (~1e-5 of all plus the dominant keys
+// of peaked rows) are recomputed with the exact IEEE-division formula; both paths give the same code.
 constexpr uint32_t kCodeGuard = 64;  // ulps: |u - 2^j| / 2^j < 2^-17, far above the ~4 ulp error of u
 
-__device__ __noinline__ int exact_log_code(float fsum, float e, int levels) { return softmax_log_code(fsum, e, levels); }
+__device__ __noinline__ uint32_t exact_prob16(float fsum, float e, int levels) {
+  const int k = softmax_log_code(fsum, e, levels);
+  return k >= 16 ? 0u : (0x8000u >> k);
+}
 
-// probability 2^-k in units of 2^-15 (k <= 15), 0 for the "zero" code
-__device__ __forceinline__ uint32_t prob16(float fsum, int d, const float* lut_f, const float* lut_r3, int levels) {
-  const float u = __fmaf_rn(fsum, lut_r3[d], 0.16666667f);
-  const uint32_t bits = __float_as_uint(u);
-  int k = (int)(bits >> 23) - 125;
-  if ((((bits + kCodeGuard) & 0x7fffffu) < 2 * kCodeGuard) || bits < 0x3f800000u)
-    k = exact_log_code(fsum, lut_f[d], levels);
-  uint32_t v;
-  asm("shr.u32 %0, %1, %2;" : "=r"(v) : "r"(0x8000u), "r"((uint32_t)k));   // shifts >= 32 give 0
-  return v;
+// four keys of one packed code word -> four 16-bit probabilities; returns a 4-bit mask of guarded elements
+__device__ __forceinline__ uint32_t prob16x4(uint32_t w, int mx, float fsum, const float* lut_r3, uint32_t (&v)[4]) {
+  uint32_t flags = 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int d = mx - (int)((w >> (8 * i)) & 0xff);
+    const uint32_t bits = __float_as_uint(__fmaf_rn(fsum, lut_r3[d], 0.16666667f));
+    flags |= ((((bits + kCodeGuard) & 0x7fffffu) < 2 * kCodeGuard) || bits < 0x3f800000u) ? (1u << i) : 0u;
+    // 1 << (15 - k), k = E - 125: shift counts >= 32 (k >= 16, or the wrapped negative) give 0
+    asm("shl.b32 %0, %1, %2;" : "=r"(v[i]) : "r"(1u), "r"(140u - (bits >> 23)));
+  }
+  return flags;
 }
 
 struct AttSmem {
   alignas(16) uint8_t Ks[kMaxKeys * kQKStride];
-  alignas(16) uint8_t Qs[kAttRows * kQKStride];
   alignas(16) uint8_t Vt[kHd * kVtStride];
   alignas(16) uint8_t codes[kAttWarps][16 * kVtStride];   // biased score codes in AV key order, per warp
   float lut_f[256];
@@ -88,8 +92,12 @@ struct AttSmem {
   unsigned long long lut_i[256];
 };
 
+// One CTA = one (image, head): K and V are staged once, each of the 7 warps walks 16-row query tiles.
+#ifndef P2V_ATT_MIN_CTAS
+#define P2V_ATT_MIN_CTAS 2
+#endif
 template <bool kDump>
-__global__ void __maxnreg__(96)
+__global__ void __launch_bounds__(kAttWarps * 32, P2V_ATT_MIN_CTAS)
 attention_int_kernel(const int8_t* __restrict__ qkv, int8_t* __restrict__ out, int n, int heads,
                      const p2v_attention p, int out_shift) {
   extern __shared__ __align__(16) uint8_t att_smem_raw[];
@@ -97,7 +105,6 @@ attention_int_kernel(const int8_t* __restrict__ qkv, int8_t* __restrict__ out, i
 
   const int bh = blockIdx.x;
   const int img = bh / heads, head = bh % heads;
-  const int row_base = blockIdx.y * kAttRows;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
   const int nkp = (n + 31) & ~31;   // padded key count
@@ -105,11 +112,11 @@ attention_int_kernel(const int8_t* __restrict__ qkv, int8_t* __restrict__ out, i
   const int64_t row_stride = (int64_t)3 * heads * kHd;
   const int8_t* base = qkv + (int64_t)img * n * row_stride;
 
-  // ---- stage Q, K (row-major, padded stride) and V (transposed + permuted) in shared memory ----------
+  // ---- stage K (row-major, padded stride) and V (transposed + permuted) in shared memory ---------------
   for (int i = tid; i < 256; i += blockDim.x) {
     const float e = p.exp_lut[i];
     sm.lut_f[i] = e;
-    sm.lut_r3[i] = __fdiv_rn(1.0f, 3.0f * e);   // 3e is exact (e has <= 22 significant bits)
+    sm.lut_r3[i] = __fdiv_rn(1.0f, 3.0f * e);   // 3e is exact (<= 24 significant bits)
     sm.lut_i[i] = (unsigned long long)e;
   }
   for (int i = tid; i < nkp * 4; i += blockDim.x) {
@@ -117,13 +124,6 @@ attention_int_kernel(const int8_t* __restrict__ qkv, int8_t* __restrict__ out, i
     uint4 v = make_uint4(0, 0, 0, 0);
     if (j < n) v = __ldg(reinterpret_cast<const uint4*>(base + j * row_stride + (heads + head) * kHd) + part);
     *reinterpret_cast<uint4*>(sm.Ks + j * kQKStride + part * 16) = v;
-  }
-  for (int i = tid; i < kAttRows * 4; i += blockDim.x) {
-    const int r = i >> 2, part = i & 3;
-    const int row = row_base + r;
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (row < n) v = __ldg(reinterpret_cast<const uint4*>(base + row * row_stride + head * kHd) + part);
-    *reinterpret_cast<uint4*>(sm.Qs + r * kQKStride + part * 16) = v;
   }
   // V^T with the key permutation of the AV product: 4 consecutive positions kappa = 16h + 4t + {0,1,2,3}
   // hold keys {j0, j0+1, j0+8, j0+9}, j0 = 32s + 16h + 2t.  One thread transposes a 4-key x 4-channel
@@ -149,173 +149,194 @@ attention_int_kernel(const int8_t* __restrict__ qkv, int8_t* __restrict__ out, i
   }
   __syncthreads();
 
-  const int r0 = row_base + warp * 16;
-  if (r0 >= n) return;  // warp-uniform; no block-level sync follows
-
   // Score codes of this warp's 16 rows live in shared memory in AV key order: the two codes a thread
   // produces for tile j (row g, keys 8j+2t, 8j+2t+1) land at byte 32s + 16h + 4t + 2(j&1) of the row
   // (s = j/4, h = (j/2)&1), so that every later pass reads back, as one 32-bit word, exactly the four
   // codes this same thread wrote: no cross-thread hazard, and the word is the A fragment of the AV MMA.
   uint8_t* crowA = sm.codes[warp] + g * kVtStride + t * 4;
   uint8_t* crowB = crowA + 8 * kVtStride;
-
-  // ---- S = Q K^T, re-quantized to int8 score codes (+128 bias) -------------------------------------------
-  uint32_t qa[2][4];
-#pragma unroll
-  for (int ks = 0; ks < 2; ++ks) {
-    const uint8_t* q0 = sm.Qs + (warp * 16 + g) * kQKStride + ks * 32 + t * 4;
-    qa[ks][0] = *reinterpret_cast<const uint32_t*>(q0);
-    qa[ks][1] = *reinterpret_cast<const uint32_t*>(q0 + 8 * kQKStride);
-    qa[ks][2] = *reinterpret_cast<const uint32_t*>(q0 + 16);
-    qa[ks][3] = *reinterpret_cast<const uint32_t*>(q0 + 8 * kQKStride + 16);
-  }
-  int maxA = 0, maxB = 0;   // biased maxima
-#pragma unroll 2
-  for (int j = 0; j < ntiles; ++j) {
-    int c[4] = {0, 0, 0, 0};
-#pragma unroll
-    for (int ks = 0; ks < 2; ++ks) {
-      const uint8_t* kp = sm.Ks + (j * 8 + g) * kQKStride + ks * 32 + t * 4;
-      mma_s8s8(c, qa[ks], *reinterpret_cast<const uint32_t*>(kp), *reinterpret_cast<const uint32_t*>(kp + 16));
-    }
-    int sc[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      // clamp(RNE(acc * mul + zp)) + 128: acc * mul is exact for the power-of-two multiplier
-      int q;
-      asm("cvt.rni.sat.s8.f32 %0, %1;" : "=r"(q) : "f"(__fmaf_rn((float)c[e], p.score_mul, p.score_zp)));
-      sc[e] = q + 128;
-    }
-    const int col = j * 8 + t * 2;
-    if (col >= n) { sc[0] = 0; sc[2] = 0; }        // padded keys: never above a real (biased) code
-    if (col + 1 >= n) { sc[1] = 0; sc[3] = 0; }
-    maxA = max(maxA, max(sc[0], sc[1]));
-    maxB = max(maxB, max(sc[2], sc[3]));
-    const int pos = ((j >> 2) << 5) + (((j >> 1) & 1) << 4) + ((j & 1) << 1);
-    *reinterpret_cast<uint16_t*>(crowA + pos) = (uint16_t)(sc[0] | (sc[1] << 8));
-    *reinterpret_cast<uint16_t*>(crowB + pos) = (uint16_t)(sc[2] | (sc[3] << 8));
-  }
-  maxA = max(maxA, __shfl_xor_sync(0xffffffffu, maxA, 1));
-  maxA = max(maxA, __shfl_xor_sync(0xffffffffu, maxA, 2));
-  maxB = max(maxB, __shfl_xor_sync(0xffffffffu, maxB, 1));
-  maxB = max(maxB, __shfl_xor_sync(0xffffffffu, maxB, 2));
-  __syncwarp();
-
   // key index of byte i of word w (w = 2s + h) for this lane
   auto key_of = [&](int w, int i) { return ((w >> 1) << 5) + ((w & 1) << 4) + ((i >> 1) << 3) + t * 2 + (i & 1); };
-  const int nwords = ntiles >> 1;
-  const int full_words = n >> 4;          // words whose four keys are < n for every lane
-
-  // ---- exact integer row sums of the integer exp --------------------------------------------------------
-  unsigned long long sumA = 0, sumB = 0;
-#pragma unroll 2
-  for (int w = 0; w < full_words; ++w) {
-    const uint32_t wa = *reinterpret_cast<const uint32_t*>(crowA + w * 16);
-    const uint32_t wb = *reinterpret_cast<const uint32_t*>(crowB + w * 16);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      sumA += sm.lut_i[maxA - (int)((wa >> (8 * i)) & 0xff)];
-      sumB += sm.lut_i[maxB - (int)((wb >> (8 * i)) & 0xff)];
-    }
-  }
-  for (int w = full_words; w < nwords; ++w) {
-    const uint32_t wa = *reinterpret_cast<const uint32_t*>(crowA + w * 16);
-    const uint32_t wb = *reinterpret_cast<const uint32_t*>(crowB + w * 16);
-    for (int i = 0; i < 4; ++i) {
-      if (key_of(w, i) < n) {
-        sumA += sm.lut_i[maxA - (int)((wa >> (8 * i)) & 0xff)];
-        sumB += sm.lut_i[maxB - (int)((wb >> (8 * i)) & 0xff)];
-      }
-    }
-  }
-  sumA += __shfl_xor_sync(0xffffffffu, sumA, 1);
-  sumA += __shfl_xor_sync(0xffffffffu, sumA, 2);
-  sumB += __shfl_xor_sync(0xffffffffu, sumB, 1);
-  sumB += __shfl_xor_sync(0xffffffffu, sumB, 2);
-  const float fsumA = __ull2float_rn(sumA), fsumB = __ull2float_rn(sumB);
-
-  // ---- log2 codes -> two u8 probability planes -> P V ------------------------------------------------------
-  const int rowA = r0 + g, rowB = r0 + g + 8;
-  int8_t* dsc = kDump ? p.dump_scores + ((int64_t)bh * n) * n : nullptr;
-  uint8_t* dsm = kDump ? p.dump_softmax + ((int64_t)bh * n) * n : nullptr;
-  int hi[8][4], lo[8][4];
-#pragma unroll
-  for (int jn = 0; jn < 8; ++jn)
-#pragma unroll
-    for (int e = 0; e < 4; ++e) { hi[jn][e] = 0; lo[jn][e] = 0; }
-
-#pragma unroll 1
-  for (int s = 0; s < (ntiles >> 2); ++s) {
-    uint32_t pa_hi[4], pa_lo[4];  // a0..a3 of the two planes
-    const bool full = (2 * s + 1) < full_words;
-#pragma unroll
-    for (int hh = 0; hh < 2; ++hh) {        // hh = 0: keys of a0/a1; hh = 1: keys of a2/a3
-      const int w = 2 * s + hh;
-      const uint32_t wa = *reinterpret_cast<const uint32_t*>(crowA + w * 16);
-      const uint32_t wb = *reinterpret_cast<const uint32_t*>(crowB + w * 16);
-      uint32_t va[4], vb[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int da = maxA - (int)((wa >> (8 * i)) & 0xff), db = maxB - (int)((wb >> (8 * i)) & 0xff);
-        va[i] = prob16(fsumA, da, sm.lut_f, sm.lut_r3, p.softmax_levels);
-        vb[i] = prob16(fsumB, db, sm.lut_f, sm.lut_r3, p.softmax_levels);
-        if (!full) {
-          const bool ok = key_of(w, i) < n;
-          va[i] = ok ? va[i] : 0u;
-          vb[i] = ok ? vb[i] : 0u;
-        }
-        if (kDump) {
-          const int col = key_of(w, i);
-          if (col < n) {
-            const int ka = va[i] ? __clz(va[i]) - 16 : p.softmax_levels;
-            const int kb = vb[i] ? __clz(vb[i]) - 16 : p.softmax_levels;
-            if (rowA < n) { dsc[(int64_t)rowA * n + col] = (int8_t)(maxA - da - 128); dsm[(int64_t)rowA * n + col] = (uint8_t)ka; }
-            if (rowB < n) { dsc[(int64_t)rowB * n + col] = (int8_t)(maxB - db - 128); dsm[(int64_t)rowB * n + col] = (uint8_t)kb; }
-          }
-        }
-      }
-      // 16-bit probabilities -> low-byte plane and high-byte plane, 4 keys per register
-      const uint32_t a01 = va[0] | (va[1] << 16), a23 = va[2] | (va[3] << 16);
-      const uint32_t b01 = vb[0] | (vb[1] << 16), b23 = vb[2] | (vb[3] << 16);
-      pa_lo[2 * hh] = __byte_perm(a01, a23, 0x6420);
-      pa_hi[2 * hh] = __byte_perm(a01, a23, 0x7531);
-      pa_lo[2 * hh + 1] = __byte_perm(b01, b23, 0x6420);
-      pa_hi[2 * hh + 1] = __byte_perm(b01, b23, 0x7531);
-    }
-#pragma unroll
-    for (int jn = 0; jn < 8; ++jn) {
-      const uint8_t* vp = sm.Vt + (jn * 8 + g) * kVtStride + s * 32 + t * 4;
-      const uint32_t b0 = *reinterpret_cast<const uint32_t*>(vp), b1 = *reinterpret_cast<const uint32_t*>(vp + 16);
-      mma_u8s8(hi[jn], pa_hi[0], pa_hi[1], pa_hi[2], pa_hi[3], b0, b1);
-      mma_u8s8(lo[jn], pa_lo[0], pa_lo[1], pa_lo[2], pa_lo[3], b0, b1);
-    }
-  }
-
-  // ---- re-quantize and store ----------------------------------------------------------------------------
+  const int nsteps = ntiles >> 2;           // 32-key steps
+  const int full_steps = n >> 5;            // steps whose 32 keys are all < n
+  const float zp_biased = p.score_zp + 128.f;
   const int64_t out_stride = (int64_t)heads * kHd;
   const int izp = (int)p.out_zp;
+
+  for (int r0 = warp * 16; r0 < n; r0 += kAttWarps * 16) {
+    const int rowA = r0 + g, rowB = r0 + g + 8;
+    // ---- Q fragments straight from global memory (each row is read by exactly one warp) -------------------
+    uint32_t qa[2][4];
+    {
+      const int8_t* qA = base + (int64_t)min(rowA, n - 1) * row_stride + head * kHd + t * 4;
+      const int8_t* qB = base + (int64_t)min(rowB, n - 1) * row_stride + head * kHd + t * 4;
 #pragma unroll
-  for (int jn = 0; jn < 8; ++jn) {
-    int q[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const int acc = hi[jn][e] * 256 + lo[jn][e];
-      if (out_shift > 0) {
-        // RNE(acc / 2^sh) in integers: add half minus one plus the parity of the truncated result
-        const int r = (acc + ((1 << (out_shift - 1)) - 1) + ((acc >> out_shift) & 1)) >> out_shift;
-        q[e] = min(max(r + izp, -128), 127);
-      } else {
-        const double v = rint((double)acc * p.out_mul) + (double)p.out_zp;
-        q[e] = (int)fmin(fmax(v, -128.0), 127.0);
+      for (int ks = 0; ks < 2; ++ks) {
+        qa[ks][0] = __ldg(reinterpret_cast<const uint32_t*>(qA + ks * 32));
+        qa[ks][1] = __ldg(reinterpret_cast<const uint32_t*>(qB + ks * 32));
+        qa[ks][2] = __ldg(reinterpret_cast<const uint32_t*>(qA + ks * 32 + 16));
+        qa[ks][3] = __ldg(reinterpret_cast<const uint32_t*>(qB + ks * 32 + 16));
       }
     }
-    const int col = head * kHd + jn * 8 + t * 2;
-    if (rowA < n)
-      *reinterpret_cast<uint16_t*>(out + ((int64_t)img * n + rowA) * out_stride + col) =
-          (uint16_t)((q[0] & 0xff) | ((q[1] & 0xff) << 8));
-    if (rowB < n)
-      *reinterpret_cast<uint16_t*>(out + ((int64_t)img * n + rowB) * out_stride + col) =
-          (uint16_t)((q[2] & 0xff) | ((q[3] & 0xff) << 8));
+
+    // ---- S = Q K^T -> biased int8 score codes: clamp(RNE(acc * mul + zp), -128, 127) + 128 ----------------
+    // acc * mul is exact for the power-of-two multiplier and adding the integer zp + 128 keeps it exact,
+    // so one fma followed by an unsigned saturating RNE conversion is the reference's round-then-clamp.
+    int maxA = 0, maxB = 0;   // biased maxima
+#pragma unroll 1
+    for (int s = 0; s < nsteps; ++s) {
+      const bool full = s < full_steps;
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        const int j = s * 4 + jj;
+        int c[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+          const uint8_t* kp = sm.Ks + (j * 8 + g) * kQKStride + ks * 32 + t * 4;
+          mma_s8s8(c, qa[ks], *reinterpret_cast<const uint32_t*>(kp), *reinterpret_cast<const uint32_t*>(kp + 16));
+        }
+        uint32_t sc[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          asm("cvt.rni.sat.u8.f32 %0, %1;" : "=r"(sc[e]) : "f"(__fmaf_rn((float)c[e], p.score_mul, zp_biased)));
+        if (!full) {   // padded keys: code 0 is never above a real (biased) code
+          const int col = j * 8 + t * 2;
+          if (col >= n) { sc[0] = 0; sc[2] = 0; }
+          if (col + 1 >= n) { sc[1] = 0; sc[3] = 0; }
+        }
+        maxA = max(maxA, (int)max(sc[0], sc[1]));
+        maxB = max(maxB, (int)max(sc[2], sc[3]));
+        const int pos = (s << 5) + ((jj >> 1) << 4) + ((jj & 1) << 1);
+        *reinterpret_cast<uint16_t*>(crowA + pos) = (uint16_t)(sc[0] | (sc[1] << 8));
+        *reinterpret_cast<uint16_t*>(crowB + pos) = (uint16_t)(sc[2] | (sc[3] << 8));
+      }
+    }
+    maxA = max(maxA, __shfl_xor_sync(0xffffffffu, maxA, 1));
+    maxA = max(maxA, __shfl_xor_sync(0xffffffffu, maxA, 2));
+    maxB = max(maxB, __shfl_xor_sync(0xffffffffu, maxB, 1));
+    maxB = max(maxB, __shfl_xor_sync(0xffffffffu, maxB, 2));
+    __syncwarp();
+
+    // ---- exact integer row sums of the integer exp ----------------------------------------------------------
+    unsigned long long sumA = 0, sumB = 0;
+    const unsigned long long* lutA = sm.lut_i + maxA;
+    const unsigned long long* lutB = sm.lut_i + maxB;
+#pragma unroll 2
+    for (int w = 0; w < 2 * full_steps; ++w) {
+      const uint32_t wa = *reinterpret_cast<const uint32_t*>(crowA + w * 16);
+      const uint32_t wb = *reinterpret_cast<const uint32_t*>(crowB + w * 16);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        sumA += *(lutA - (int)((wa >> (8 * i)) & 0xff));
+        sumB += *(lutB - (int)((wb >> (8 * i)) & 0xff));
+      }
+    }
+    for (int w = 2 * full_steps; w < 2 * nsteps; ++w) {
+      const uint32_t wa = *reinterpret_cast<const uint32_t*>(crowA + w * 16);
+      const uint32_t wb = *reinterpret_cast<const uint32_t*>(crowB + w * 16);
+      for (int i = 0; i < 4; ++i) {
+        if (key_of(w, i) < n) {
+          sumA += *(lutA - (int)((wa >> (8 * i)) & 0xff));
+          sumB += *(lutB - (int)((wb >> (8 * i)) & 0xff));
+        }
+      }
+    }
+    sumA += __shfl_xor_sync(0xffffffffu, sumA, 1);
+    sumA += __shfl_xor_sync(0xffffffffu, sumA, 2);
+    sumB += __shfl_xor_sync(0xffffffffu, sumB, 1);
+    sumB += __shfl_xor_sync(0xffffffffu, sumB, 2);
+    const float fsumA = __ull2float_rn(sumA), fsumB = __ull2float_rn(sumB);
+
+    // ---- log2 codes -> two u8 probability planes -> P V ------------------------------------------------------
+    int8_t* dsc = kDump ? p.dump_scores + ((int64_t)bh * n) * n : nullptr;
+    uint8_t* dsm = kDump ? p.dump_softmax + ((int64_t)bh * n) * n : nullptr;
+    int hi[8][4], lo[8][4];
+#pragma unroll
+    for (int jn = 0; jn < 8; ++jn)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { hi[jn][e] = 0; lo[jn][e] = 0; }
+
+#pragma unroll 1
+    for (int s = 0; s < nsteps; ++s) {
+      uint32_t pa_hi[4], pa_lo[4];  // a0..a3 of the two planes
+      const bool full = s < full_steps;
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {        // hh = 0: keys of a0/a1; hh = 1: keys of a2/a3
+        const int w = 2 * s + hh;
+        const uint32_t wa = *reinterpret_cast<const uint32_t*>(crowA + w * 16);
+        const uint32_t wb = *reinterpret_cast<const uint32_t*>(crowB + w * 16);
+        uint32_t va[4], vb[4];
+        const uint32_t fa = prob16x4(wa, maxA, fsumA, sm.lut_r3, va);
+        const uint32_t fb = prob16x4(wb, maxB, fsumB, sm.lut_r3, vb);
+        if (fa | fb) {   // rare: a value next to a step of the code function, or the row maximum
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            if (fa & (1u << i)) va[i] = exact_prob16(fsumA, sm.lut_f[maxA - (int)((wa >> (8 * i)) & 0xff)], p.softmax_levels);
+            if (fb & (1u << i)) vb[i] = exact_prob16(fsumB, sm.lut_f[maxB - (int)((wb >> (8 * i)) & 0xff)], p.softmax_levels);
+          }
+        }
+        if (!full) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const bool ok = key_of(w, i) < n;
+            va[i] = ok ? va[i] : 0u;
+            vb[i] = ok ? vb[i] : 0u;
+          }
+        }
+        if (kDump) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int col = key_of(w, i);
+            if (col < n) {
+              const int ka = va[i] ? __clz(va[i]) - 16 : p.softmax_levels;
+              const int kb = vb[i] ? __clz(vb[i]) - 16 : p.softmax_levels;
+              if (rowA < n) { dsc[(int64_t)rowA * n + col] = (int8_t)((int)((wa >> (8 * i)) & 0xff) - 128); dsm[(int64_t)rowA * n + col] = (uint8_t)ka; }
+              if (rowB < n) { dsc[(int64_t)rowB * n + col] = (int8_t)((int)((wb >> (8 * i)) & 0xff) - 128); dsm[(int64_t)rowB * n + col] = (uint8_t)kb; }
+            }
+          }
+        }
+        // 16-bit probabilities -> low-byte plane and high-byte plane, 4 keys per register
+        const uint32_t a01 = va[0] | (va[1] << 16), a23 = va[2] | (va[3] << 16);
+        const uint32_t b01 = vb[0] | (vb[1] << 16), b23 = vb[2] | (vb[3] << 16);
+        pa_lo[2 * hh] = __byte_perm(a01, a23, 0x6420);
+        pa_hi[2 * hh] = __byte_perm(a01, a23, 0x7531);
+        pa_lo[2 * hh + 1] = __byte_perm(b01, b23, 0x6420);
+        pa_hi[2 * hh + 1] = __byte_perm(b01, b23, 0x7531);
+      }
+#pragma unroll
+      for (int jn = 0; jn < 8; ++jn) {
+        const uint8_t* vp = sm.Vt + (jn * 8 + g) * kVtStride + s * 32 + t * 4;
+        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(vp), b1 = *reinterpret_cast<const uint32_t*>(vp + 16);
+        mma_u8s8(hi[jn], pa_hi[0], pa_hi[1], pa_hi[2], pa_hi[3], b0, b1);
+        mma_u8s8(lo[jn], pa_lo[0], pa_lo[1], pa_lo[2], pa_lo[3], b0, b1);
+      }
+    }
+
+    // ---- re-quantize and store ----------------------------------------------------------------------------
+#pragma unroll
+    for (int jn = 0; jn < 8; ++jn) {
+      int q[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int acc = hi[jn][e] * 256 + lo[jn][e];
+        if (out_shift > 0) {
+          // RNE(acc / 2^sh) in integers: add half minus one plus the parity of the truncated result
+          const int r = (acc + ((1 << (out_shift - 1)) - 1) + ((acc >> out_shift) & 1)) >> out_shift;
+          q[e] = min(max(r + izp, -128), 127);
+        } else {
+          const double v = rint((double)acc * p.out_mul) + (double)p.out_zp;
+          q[e] = (int)fmin(fmax(v, -128.0), 127.0);
+        }
+      }
+      const int col = head * kHd + jn * 8 + t * 2;
+      if (rowA < n)
+        *reinterpret_cast<uint16_t*>(out + ((int64_t)img * n + rowA) * out_stride + col) =
+            (uint16_t)((q[0] & 0xff) | ((q[1] & 0xff) << 8));
+      if (rowB < n)
+        *reinterpret_cast<uint16_t*>(out + ((int64_t)img * n + rowB) * out_stride + col) =
+            (uint16_t)((q[2] & 0xff) | ((q[3] & 0xff) << 8));
+    }
+    __syncwarp();   // the next row tile overwrites this warp's code buffer
   }
 }
 
@@ -326,6 +347,9 @@ static int attention_configure() {
                                         (int)sizeof(AttSmem)));
     P2V_CHECK_CUDA(cudaFuncSetAttribute(attention_int_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)sizeof(AttSmem)));
+    // three CTAs per SM need the full shared-memory carveout
+    P2V_CHECK_CUDA(cudaFuncSetAttribute(attention_int_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    P2V_CHECK_CUDA(cudaFuncSetAttribute(attention_int_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     state = 0;
   }
   return P2V_OK;
@@ -343,7 +367,7 @@ extern "C" int p2v_attention_int(const int8_t* qkv, int8_t* out, int b, int n, i
   P2V_REQUIRE(n <= kMaxKeys, "p2v_attention_int: n=%d tokens exceeds the %d-key tile of this kernel", n, kMaxKeys);
   P2V_REQUIRE((p->dump_scores == nullptr) == (p->dump_softmax == nullptr),
               "p2v_attention_int: dump_scores and dump_softmax must be given together");
-  dim3 grid(b * heads, (n + kAttRows - 1) / kAttRows);
+  dim3 grid(b * heads);
   // power-of-two output multiplier 2^-sh (every minmax-calibrated model): integer RNE shift in the kernel
   int out_shift = 0, ex = 0;
   if (p->out_mul > 0 && frexp(p->out_mul, &ex) == 0.5 && ex <= 0 && ex >= -29 && p->out_zp == (float)(int)p->out_zp)

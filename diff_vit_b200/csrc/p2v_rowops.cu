@@ -97,20 +97,21 @@ __device__ __forceinline__ uint32_t pack_sat4f(float v0, float v1, float v2, flo
 __device__ __forceinline__ float ln_code_folded(float xq, const LnRow& row, float go, float bo) {
   const float A = fmul(row.t, go);
   const float absA = fabsf(A);
-  const float sign = A > 0.f ? 1.f : (A < 0.f ? -1.f : 0.f);
   int e = (int)((f2u(absA) >> 23) & 0xffu) - 127;
   int N = 7 - e;
   N = N < 0 ? 0 : (N > 31 ? 31 : N);
   const float p2N = pow2i(N);
   float M = floorf(fmul(absA, p2N));
   M = fminf(M, 255.f);
+  // sign(A) * M == copysign(M, A): A == 0 forces M == 0, and (-0) * xq + Bq == Bq
+  const float sM = u2f(f2u(M) | (f2u(A) & 0x80000000u));
   const float Bq = rne(fmul(fsub(bo, fmul(row.u, go)), p2N));
-  const float y = fadd(fmul(fmul(sign, M), xq), Bq);
+  const float y = fadd(fmul(sM, xq), Bq);
   return rne(fmul(y, pow2i(-N)));
 }
 
 template <int G>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 layernorm_int_pot_kernel(const int8_t* __restrict__ in, int64_t in_row_stride, int8_t* __restrict__ out,
                          int32_t* __restrict__ ln_codes, int rows, int d, const p2v_layernorm p) {
   const int lane = threadIdx.x & 31;
@@ -134,15 +135,30 @@ layernorm_int_pot_kernel(const int8_t* __restrict__ in, int64_t in_row_stride, i
       mk[g][0] = (int)im.x; mk[g][1] = (int)im.y; mk[g][2] = (int)im.z; mk[g][3] = (int)im.w;
     }
   }
-  for (int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < rows; row += warps_total) {
-    const int8_t* src = in + (int64_t)row * in_row_stride;
+  // software pipeline: the next row's codes are in flight while this row is normalised
+  uint32_t next_w[G];
+  int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    const int grp = g * 32 + lane;
+    next_w[g] = (row < rows && grp < groups) ? __ldg(reinterpret_cast<const uint32_t*>(in + (int64_t)row * in_row_stride + grp * 4)) : 0u;
+  }
+  for (; row < rows; row += warps_total) {
+    uint32_t cur_w[G];
+    const int nrow = row + warps_total;
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      const int grp = g * 32 + lane;
+      cur_w[g] = next_w[g];
+      next_w[g] = (nrow < rows && grp < groups) ? __ldg(reinterpret_cast<const uint32_t*>(in + (int64_t)nrow * in_row_stride + grp * 4)) : 0u;
+    }
     float xq[G][4];
     int sum = 0, sumsq = 0;   // |x| <= 1024, d <= 128 G: per-lane partial sums stay far below 2^31
 #pragma unroll
     for (int g = 0; g < G; ++g) {
       const int grp = g * 32 + lane;
       if (grp < groups) {
-        const uint32_t word = __ldg(reinterpret_cast<const uint32_t*>(src + grp * 4));
+        const uint32_t word = cur_w[g];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int v = (int)(int8_t)((word >> (8 * j)) & 0xff) * mk[g][j];
@@ -311,7 +327,7 @@ extern "C" int p2v_layernorm_int(const int8_t* in, int64_t in_row_stride, int8_t
   if (p->pot) {
     P2V_REQUIRE(p->ln_out_rscale && p->post_mul, "p2v_layernorm_int: pot path needs ln_out_rscale and post_mul");
     const int groups = (d / 4 + 31) / 32;
-    const int pgrid = grid < kNumSMs * 4 ? grid : kNumSMs * 4;   // persistent warps: constants stay in registers
+    const int pgrid = grid < kNumSMs * 3 ? grid : kNumSMs * 3;   // persistent warps (3 resident CTAs per SM): constants stay in registers
     if (groups == 1) layernorm_int_pot_kernel<1><<<pgrid, warps * 32, 0, st>>>(in, in_row_stride, out, ln_codes, rows, d, *p);
     else if (groups == 2) layernorm_int_pot_kernel<2><<<pgrid, warps * 32, 0, st>>>(in, in_row_stride, out, ln_codes, rows, d, *p);
     else if (groups == 3) layernorm_int_pot_kernel<3><<<pgrid, warps * 32, 0, st>>>(in, in_row_stride, out, ln_codes, rows, d, *p);
