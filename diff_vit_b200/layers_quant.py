@@ -62,6 +62,8 @@ class SmoothQuantState:
     def channel_scale(x, weight, alpha):
         """PoT-rounded max|x|_c^alpha / max|W|_c^(1-alpha) (per input channel)."""
         global_max_x = torch.abs(x).max(axis=1).values.max(axis=0).values
+        from . import dist as _dist
+        _dist.reduce_max_(global_max_x)     # activations are sharded over ranks while calibrating
         max_weight = torch.abs(weight).max(axis=0).values
         cs = global_max_x ** alpha / (max_weight ** (1 - alpha))
         return 2 ** ln2_round(cs)

@@ -30,6 +30,10 @@ class BaseObserver:
         v = self.reshape_tensor(v)
         cur_max = v.max(axis=1).values
         cur_min = v.min(axis=1).values
+        if self.module_type == 'activation':   # weights are replicated; activations are sharded over ranks
+            from ... import dist as _dist
+            _dist.reduce_max_(cur_max)
+            _dist.reduce_min_(cur_min)
         self.max_val = cur_max if self.max_val is None else torch.max(cur_max, self.max_val)
         self.min_val = cur_min if self.min_val is None else torch.min(cur_min, self.min_val)
         if self.calibration_mode == 'layer_wise':

@@ -3,6 +3,7 @@
 import numpy as np
 import torch
 
+from ... import dist as _dist
 from .base import BaseObserver
 
 
@@ -30,8 +31,8 @@ class EmaObserver(BaseObserver):
 
     def update(self, v):
         v = self.reshape_tensor(v)
-        cur_max = v.max(axis=1).values
-        cur_min = v.min(axis=1).values
+        cur_max = _dist.reduce_max_(v.max(axis=1).values)
+        cur_min = _dist.reduce_min_(v.min(axis=1).values)
         if self.max_val is None:
             self.max_val, self.min_val = cur_max, cur_min
         else:
@@ -58,6 +59,9 @@ class PercentileObserver(BaseObserver):
 
     def update(self, v):
         assert self.calibration_mode == 'layer_wise'
+        if _dist.is_active():
+            raise NotImplementedError('data-parallel percentile calibration needs an exact distributed order '
+                                      'statistic (all-gather of the tail candidates); calibrate on one rank')
         flat = self.reshape_tensor(v).reshape(-1)
         try:
             cur_max = torch.quantile(flat, self.percentile_alpha)
@@ -105,7 +109,7 @@ class OmseObserver(BaseObserver):
             new_zero_point.clamp_(qmin, qmax)
             inputs_q = ((inputs / new_scale + new_zero_point).round().clamp(qmin, qmax) -
                         new_zero_point) * new_scale
-            score = (inputs - inputs_q).abs().pow(2.0).mean()
+            score = _dist.global_mean((inputs - inputs_q).abs().pow(2.0))
             if score < best_score:
                 best_score = score
                 self.max_val, self.min_val = new_max, new_min

@@ -38,12 +38,13 @@ class MinmaxObserver(BaseObserver):
         raise NotImplementedError(self.module_type)
 
     def _channel_mse(self, a, b):
+        from ... import dist as _dist
         d = (a - b).abs().pow(2.0)
         if self.calibration_mode == 'layer_wise':
-            return d.mean().reshape(1)
+            return _dist.global_mean(d).reshape(1)
         if self.module_type == 'conv_weight':
-            return d.mean(dim=(0, 2, 3))
-        return d.reshape(-1, d.shape[-1]).mean(dim=0)
+            return _dist.global_mean(d, (0, 2, 3))
+        return _dist.global_mean(d.reshape(-1, d.shape[-1]), 0)
 
     def _search_exponent(self, scale, zero_point=None):
         """Pick alpha in {af-1, af, af+1, af+2}, af = floor(log2 scale), minimising the MSE of the

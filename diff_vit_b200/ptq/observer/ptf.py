@@ -4,6 +4,7 @@ One float base scale for the tensor plus a per-channel factor 2^m, m in {0,1,2,3
 Python loop over channels is replaced by one vectorised pass per candidate factor."""
 import torch
 
+from ... import dist as _dist
 from .base import BaseObserver
 
 
@@ -32,7 +33,7 @@ class PtfObserver(BaseObserver):
         choice = torch.zeros_like(max_val)
         for m, s in enumerate((scale1, scale2, scale4, scale8)):
             q = ((inputs / s + zero_point).round().clamp(qmin, qmax) - zero_point) * s
-            score = (inputs - q).abs().pow(2.0).reshape(-1, inputs.shape[-1]).mean(dim=0)
+            score = _dist.global_mean((inputs - q).abs().pow(2.0).reshape(-1, inputs.shape[-1]), 0)
             if best is None:
                 best = score
             else:
