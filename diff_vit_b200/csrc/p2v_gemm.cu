@@ -42,6 +42,7 @@ struct GemmSmem {
   alignas(1024) uint8_t a[kStages][kTileBytes];
   alignas(1024) uint8_t b[kStages][kTileBytes];
   alignas(16) float chan[kAccStages][CH_FIELDS][kBlockN];
+  alignas(16) uint8_t stage[4][32 * 144];
   alignas(8) uint64_t full[kStages];
   uint64_t empty[kStages];
   uint64_t acc_full[kAccStages];
@@ -73,21 +74,44 @@ __device__ __forceinline__ uint32_t pack_sat4(float v0, float v1, float v2, floa
 // half-integer; only those elements (~0.2 %) take the exact division.  For |t| >= 512 both paths
 // saturate to the same int8 code, so the absolute guard is sufficient.
 constexpr float kTieGuard = 0.0009765625f;  // 2^-10 >> 4 ulp(512)
+__device__ __noinline__ float div_round_exact(float y, float s, float zp) { return rintf(fadd(fdiv(y, s), zp)); }
 __device__ __forceinline__ float div_round(float y, float s, float rs, float zp) {
   const float t = fadd(fmul(y, rs), zp);
   float r = rintf(t);
-  if (fabsf(fabsf(fsub(t, r)) - 0.5f) < kTieGuard) r = rintf(fadd(fdiv(y, s), zp));
+  if (fabsf(fabsf(fsub(t, r)) - 0.5f) < kTieGuard) r = div_round_exact(y, s, zp);   // rare: keeps the hot loop small
   return r;
+}
+
+// Four at a time: the common path is branch-free so the four dependency chains interleave; one rarely
+// taken branch per group re-does the flagged elements exactly.
+__device__ __forceinline__ void div_round4(const float (&y)[4], const float (&s)[4], const float (&rs)[4], float zp,
+                                           float (&r)[4]) {
+  uint32_t flags = 0;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float t = fadd(fmul(y[e], rs[e]), zp);
+    r[e] = rintf(t);
+    flags |= (fabsf(fabsf(fsub(t, r[e])) - 0.5f) < kTieGuard) ? (1u << e) : 0u;
+  }
+  if (flags) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+      if (flags & (1u << e)) r[e] = div_round_exact(y[e], s[e], zp);
+  }
 }
 
 __device__ __forceinline__ float clamp_code(float r) { return fminf(fmaxf(r, -128.f), 127.f); }
 
 // Epilogue of 16 consecutive columns of one output row (one thread).  ch: this accumulator stage's
 // channel constants, c: column offset inside the tile.
+// Staged mode (res_staged / out_staged non-null): the residual codes of these 16 columns were brought in, and the
+// packed result leaves, through a shared-memory tile so that global traffic is fully coalesced.
 template <uint32_t FLAGS, int CW>
 __device__ __forceinline__ void epilogue16(const uint32_t (&acc)[16], const float (*ch)[CW], int c,
-                                           const GemmArgs& g, int row, int col0) {
+                                           const GemmArgs& g, int row, int col0, const uint4* res_staged = nullptr,
+                                           uint4* out_staged = nullptr) {
   const int ncols = min(16, g.n - col0);
+  if (out_staged != nullptr) *out_staged = make_uint4(0, 0, 0, 0);
   if (ncols <= 0) return;
   const int64_t off = (int64_t)row * g.ld_out + col0;
   if (g.raw_acc != nullptr) {
@@ -101,7 +125,9 @@ __device__ __forceinline__ void epilogue16(const uint32_t (&acc)[16], const floa
   float code[16];   // first-stage codes (clamped, integral)
   uint32_t resw[4] = {0, 0, 0, 0};
   if (FLAGS & EPI_RESIDUAL) {
-    if (vec) {
+    if (res_staged != nullptr) {
+      resw[0] = res_staged->x; resw[1] = res_staged->y; resw[2] = res_staged->z; resw[3] = res_staged->w;
+    } else if (vec) {
       const uint4 r4 = __ldg(reinterpret_cast<const uint4*>(g.epi.residual + off));
       resw[0] = r4.x; resw[1] = r4.y; resw[2] = r4.z; resw[3] = r4.w;
     } else {
@@ -124,17 +150,23 @@ __device__ __forceinline__ void epilogue16(const uint32_t (&acc)[16], const floa
       const float4 S = *reinterpret_cast<const float4*>(&ch[CH_SO][c + j4]);
       so[0] = S.x; so[1] = S.y; so[2] = S.z; so[3] = S.w;
     }
+    float y4[4], r4[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      const int j = j4 + e;
-      float y = ffma((float)(int)acc[j], a4[e], b4[e]);   // kFold: already on the output grid
-      if (FLAGS & EPI_GELU) y = gelu_erf(y);
-      float r;
-      if (kFold) r = rintf(y);
-      else if (FLAGS & EPI_OUT_POT) r = rintf(fmul(y, rso[e]));
-      else r = div_round(y, so[e], rso[e], g.epi.out_zp);
-      code[j] = (FLAGS & EPI_RESIDUAL) ? clamp_code(r) : r;   // without residual the pack saturates
+      y4[e] = ffma((float)(int)acc[j4 + e], a4[e], b4[e]);   // kFold: already on the output grid
+      if (FLAGS & EPI_GELU) y4[e] = gelu_erf(y4[e]);
     }
+    if (kFold) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) r4[e] = rintf(y4[e]);
+    } else if (FLAGS & EPI_OUT_POT) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) r4[e] = rintf(fmul(y4[e], rso[e]));
+    } else {
+      div_round4(y4, so, rso, g.epi.out_zp, r4);
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) code[j4 + e] = (FLAGS & EPI_RESIDUAL) ? clamp_code(r4[e]) : r4[e];   // the pack saturates
     if (FLAGS & EPI_RESIDUAL) {
       const float4 SR = *reinterpret_cast<const float4*>(&ch[CH_SR][c + j4]);
       const float4 R2 = *reinterpret_cast<const float4*>(&ch[CH_RSO2][c + j4]);
@@ -143,19 +175,24 @@ __device__ __forceinline__ void epilogue16(const uint32_t (&acc)[16], const floa
       const uint32_t w = resw[j4 >> 2];
       const float res[4] = {(float)(int8_t)(w & 0xff), (float)(int8_t)((w >> 8) & 0xff),
                             (float)(int8_t)((w >> 16) & 0xff), (float)(int8_t)(w >> 24)};
+      if (g.epi.aux_codes != nullptr || g.epi.out_f32 != nullptr) {   // dump of the branch codes (qact3 / mlp.qact2)
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int j = j4 + e;
-        // fp32: dequantize residual stream and branch, add, re-quantize on the block-level grid
-        const float sum = fadd(fmul(res[e], sr[e]), fmul(code[j], so[e]));
-        const float first = code[j];
-        code[j] = div_round(sum, s2[e], r2[e], 0.f);
-        if (j < ncols) {
-          if (g.epi.aux_codes != nullptr) g.epi.aux_codes[off + j] = (int8_t)first;   // branch codes (qact3 / mlp.qact2)
-          if (g.epi.out_f32 != nullptr)
-            g.epi.out_f32[(int64_t)row * g.n + col0 + j] = fmul(fsub(first, g.epi.out_zp), so[e]);
+        for (int e = 0; e < 4; ++e) {
+          const int j = j4 + e;
+          if (j < ncols) {
+            if (g.epi.aux_codes != nullptr) g.epi.aux_codes[off + j] = (int8_t)code[j];
+            if (g.epi.out_f32 != nullptr)
+              g.epi.out_f32[(int64_t)row * g.n + col0 + j] = fmul(fsub(code[j], g.epi.out_zp), so[e]);
+          }
         }
       }
+      // fp32: dequantize residual stream and branch, add, re-quantize on the block-level grid
+      float sum[4], q2[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) sum[e] = fadd(fmul(res[e], sr[e]), fmul(code[j4 + e], so[e]));
+      div_round4(sum, s2, r2, 0.f, q2);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) code[j4 + e] = q2[e];
     }
   }
   if (!(FLAGS & EPI_RESIDUAL) && g.epi.out_f32 != nullptr) {
@@ -167,10 +204,12 @@ __device__ __forceinline__ void epilogue16(const uint32_t (&acc)[16], const floa
       }
     }
   }
-  if (vec) {
-    *reinterpret_cast<uint4*>(g.out + off) =
+  if (out_staged != nullptr || vec) {
+    const uint4 packed =
         make_uint4(pack_sat4(code[0], code[1], code[2], code[3]), pack_sat4(code[4], code[5], code[6], code[7]),
                    pack_sat4(code[8], code[9], code[10], code[11]), pack_sat4(code[12], code[13], code[14], code[15]));
+    if (out_staged != nullptr) *out_staged = packed;
+    else *reinterpret_cast<uint4*>(g.out + off) = packed;
   } else {
 #pragma unroll
     for (int j = 0; j < 16; ++j)
@@ -203,6 +242,89 @@ __device__ __forceinline__ void load_channels(float (*ch)[CW], const p2v_epilogu
     ch[CH_A][j] = A; ch[CH_B][j] = B; ch[CH_RSO][j] = RSO; ch[CH_SO][j] = SO;
     ch[CH_SR][j] = SR; ch[CH_RSO2][j] = RSO2; ch[CH_SO2][j] = SO2;
   }
+}
+
+// ---- epilogue of one 32-row x 128-column block (one TMEM lane quarter, four warps) -----------------------------
+// A thread owns one output row, so writing its codes straight to global memory touches 32 different cache
+// lines per store instruction (ncu: L1TEX was the busiest unit of the first version).  Instead the four
+// warps of a quarter exchange through a padded shared-memory tile: residual codes come in, and result codes
+// go out, as 128-byte row segments (8 lanes x 16 B per row).
+constexpr int kStagePitch = 144;                    // 128 B of codes + 16 B pad: conflict-free 16-byte accesses
+constexpr int kStageBytes = 32 * kStagePitch;       // per quarter
+
+__device__ __forceinline__ void quarter_barrier(int quarter) {
+  asm volatile("bar.sync %0, 128;" ::"r"(2 + quarter) : "memory");
+}
+
+template <uint32_t FLAGS, int CW>
+__device__ __forceinline__ void epilogue_block(const uint32_t (&v0)[16], const uint32_t (&v1)[16], const float (*ch)[CW],
+                                               int c, const GemmArgs& g, int row0, int col0, int quarter, int cgroup,
+                                               int lane, uint8_t* stage, bool staged, const uint4* pre0 = nullptr,
+                                               const uint4* pre1 = nullptr) {
+  const int row = row0 + lane;            // this thread's output row
+  const int mycol = col0 + cgroup * 32;   // first of this thread's 32 columns
+  if (!staged) {
+    if (row < g.m) {
+      epilogue16<FLAGS, CW>(v0, ch, c + cgroup * 32, g, row, mycol, pre0);
+      epilogue16<FLAGS, CW>(v1, ch, c + cgroup * 32 + 16, g, row, mycol + 16, pre1);
+    }
+    return;
+  }
+  const int tq = cgroup * 32 + lane;      // 0..127 inside the quarter
+  uint8_t* mine = stage + lane * kStagePitch + cgroup * 32;
+  uint4 r0 = make_uint4(0, 0, 0, 0), r1 = r0;
+  if (FLAGS & EPI_RESIDUAL) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int idx = tq + 128 * i, rr = idx >> 3, ck = idx & 7;
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (row0 + rr < g.m && col0 + ck * 16 < g.n)
+        v = __ldg(reinterpret_cast<const uint4*>(g.epi.residual + (int64_t)(row0 + rr) * g.ld_out + col0 + ck * 16));
+      *reinterpret_cast<uint4*>(stage + rr * kStagePitch + ck * 16) = v;
+    }
+    quarter_barrier(quarter);
+    r0 = *reinterpret_cast<const uint4*>(mine);
+    r1 = *reinterpret_cast<const uint4*>(mine + 16);
+    quarter_barrier(quarter);
+  }
+  uint4 o0 = make_uint4(0, 0, 0, 0), o1 = o0;
+  if (row < g.m) {
+    epilogue16<FLAGS, CW>(v0, ch, c + cgroup * 32, g, row, mycol, &r0, &o0);
+    epilogue16<FLAGS, CW>(v1, ch, c + cgroup * 32 + 16, g, row, mycol + 16, &r1, &o1);
+  }
+  *reinterpret_cast<uint4*>(mine) = o0;
+  *reinterpret_cast<uint4*>(mine + 16) = o1;
+  quarter_barrier(quarter);
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int idx = tq + 128 * i, rr = idx >> 3, ck = idx & 7;
+    if (row0 + rr < g.m && col0 + ck * 16 < g.n)
+      *reinterpret_cast<uint4*>(g.out + (int64_t)(row0 + rr) * g.ld_out + col0 + ck * 16) =
+          *reinterpret_cast<const uint4*>(stage + rr * kStagePitch + ck * 16);
+  }
+  quarter_barrier(quarter);   // the tile is free for the next block
+}
+
+// Coalesced staging needs 16-byte aligned rows and whole 16-column chunks.  It pays off for the light
+// (folded power-of-two) epilogue, whose stores were the busiest unit; the GELU and residual epilogues are
+// instruction-issue bound and the extra barriers cost more than the stores (measured), so they store directly.
+template <uint32_t FLAGS>
+__device__ __forceinline__ bool can_stage(const GemmArgs& g) {
+  return !(FLAGS & (EPI_GELU | EPI_RESIDUAL)) && g.raw_acc == nullptr && (g.ld_out & 15) == 0 && (g.n & 15) == 0 &&
+         (reinterpret_cast<uintptr_t>(g.out) & 15) == 0;
+}
+
+// Early issue of the residual loads of one thread's 32 columns (two 16-byte words), so that their latency
+// overlaps the wait for the accumulator.  Returns false when the vector path does not apply.
+template <uint32_t FLAGS>
+__device__ __forceinline__ bool prefetch_residual(const GemmArgs& g, int row, int col, uint4& r0, uint4& r1) {
+  if (!(FLAGS & EPI_RESIDUAL) || row >= g.m || col + 32 > g.n || (g.ld_out & 15) != 0 || (col & 15) != 0 ||
+      (reinterpret_cast<uintptr_t>(g.epi.residual) & 15) != 0)
+    return false;
+  const uint4* rp = reinterpret_cast<const uint4*>(g.epi.residual + (int64_t)row * g.ld_out + col);
+  r0 = __ldg(rp);
+  r1 = __ldg(rp + 1);
+  return true;
 }
 
 __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&v)[16]) {
@@ -295,6 +417,7 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     const int quarter = ew & 3;        // TMEM lane quarter this warp may access (= warp id % 4)
     const int cgroup = ew >> 2;        // 32-column group of the tile
     const int etid = threadIdx.x - 128;
+    const bool staged = can_stage<FLAGS>(g);
     uint32_t acc = 0, acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m0 = (tile / tiles_n) * kBlockM, n0 = (tile % tiles_n) * kBlockN;
@@ -302,9 +425,10 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       // warp has passed the barrier of the tile in between, so the overwrite is safe.
       load_channels<FLAGS, kBlockN>(s.chan[acc], g.epi, n0, g.n, etid);
       asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+      uint4 pr0 = make_uint4(0, 0, 0, 0), pr1 = pr0;
+      const bool pre = prefetch_residual<FLAGS>(g, m0 + quarter * 32 + lane, n0 + cgroup * 32, pr0, pr1);
       mbar_wait(&s.acc_full[acc], acc_phase);
       tc_fence_after_sync();
-      const int row = m0 + quarter * 32 + lane;
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * kBlockN + cgroup * 32;
       uint32_t v0[16], v1[16];
       tmem_ld_32x16(taddr, v0);
@@ -314,10 +438,8 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(&s.acc_empty[acc]);
-      if (row < g.m) {
-        epilogue16<FLAGS, kBlockN>(v0, s.chan[acc], cgroup * 32, g, row, n0 + cgroup * 32);
-        epilogue16<FLAGS, kBlockN>(v1, s.chan[acc], cgroup * 32 + 16, g, row, n0 + cgroup * 32 + 16);
-      }
+      epilogue_block<FLAGS, kBlockN>(v0, v1, s.chan[acc], 0, g, m0 + quarter * 32, n0, quarter, cgroup, lane,
+                                     s.stage[quarter], staged, pre ? &pr0 : nullptr, pre ? &pr1 : nullptr);
       if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
     }
   }
@@ -352,6 +474,7 @@ struct BsSmem {
   alignas(1024) uint8_t b[kBsMaxKb][2][kTileBytes];   // [k-block][128-column half] = rows of the slab
   alignas(1024) uint8_t a[kBsStagesA][kTileBytes];
   alignas(16) float chan[CH_FIELDS][kBsSlabCols];
+  alignas(16) uint8_t stage[4][32 * 144];
   alignas(8) uint64_t full[kBsStagesA];
   uint64_t empty[kBsStagesA];
   uint64_t b_full;
@@ -451,12 +574,18 @@ gemm_i8_bs_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       load_channels<FLAGS, kBsSlabCols>(s.chan, g.epi, n0, g.n, (int)threadIdx.x - 128);
       asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
       uint32_t it = 0;
+      const bool staged = can_stage<FLAGS>(g);
       for (int tile = local; tile < tiles_m; tile += cnt, ++it) {
         const uint32_t p = it & 1;
+        uint4 pa0 = make_uint4(0, 0, 0, 0), pa1 = pa0, pb0 = pa0, pb1 = pa0;
+        const int prow = tile * kBlockM + quarter * 32 + lane;
+        const bool prea = prefetch_residual<FLAGS>(g, prow, n0 + cgroup * 32, pa0, pa1);
+        const bool preb = nsub > 1 && prefetch_residual<FLAGS>(g, prow, n0 + kBlockN + cgroup * 32, pb0, pb1);
         mbar_wait(&s.acc_full[p], (it >> 1) & 1);
         tc_fence_after_sync();
-        const int row = tile * kBlockM + quarter * 32 + lane;
-        for (int h = 0; h < nsub; ++h) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          if (h >= nsub) break;
           const int c = h * kBlockN + cgroup * 32;
           const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + p * kBsSlabCols + c;
           uint32_t v0[16], v1[16];
@@ -468,10 +597,10 @@ gemm_i8_bs_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             __syncwarp();
             if (lane == 0) mbar_arrive(&s.acc_empty[p]);
           }
-          if (row < g.m) {
-            epilogue16<FLAGS, kBsSlabCols>(v0, s.chan, c, g, row, n0 + c);
-            epilogue16<FLAGS, kBsSlabCols>(v1, s.chan, c + 16, g, row, n0 + c + 16);
-          }
+          epilogue_block<FLAGS, kBsSlabCols>(v0, v1, s.chan, h * kBlockN, g, tile * kBlockM + quarter * 32,
+                                             n0 + h * kBlockN, quarter, cgroup, lane, s.stage[quarter], staged,
+                                             h == 0 ? (prea ? &pa0 : nullptr) : (preb ? &pb0 : nullptr),
+                                             h == 0 ? (prea ? &pa1 : nullptr) : (preb ? &pb1 : nullptr));
         }
       }
     }
