@@ -69,18 +69,24 @@ __device__ __noinline__ uint32_t exact_prob16(float fsum, float e, int levels) {
   return k >= 16 ? 0u : (0x8000u >> k);
 }
 
-// four keys of one packed code word -> four 16-bit probabilities; returns a 4-bit mask of guarded elements
-__device__ __forceinline__ uint32_t prob16x4(uint32_t w, int mx, float fsum, const float* lut_r3, uint32_t (&v)[4]) {
-  uint32_t flags = 0;
+// guard test of one element: next to a step of the code function, or below 1 (dominant key of a peaked row)
+__device__ __forceinline__ bool code_guarded(uint32_t bits) {
+  return (((bits + kCodeGuard) & 0x7fffffu) < 2 * kCodeGuard) || bits < 0x3f800000u;
+}
+
+// four keys of one packed code word -> four 16-bit probabilities; returns true if any element needs the
+// exact path.  lutR = lut_r3 + rowmax (biased), so the table is addressed by the code byte directly.
+__device__ __forceinline__ bool prob16x4(uint32_t w, const float* lutR, float fsum, uint32_t (&v)[4], uint32_t (&bits)[4]) {
+  bool any = false;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const int d = mx - (int)((w >> (8 * i)) & 0xff);
-    const uint32_t bits = __float_as_uint(__fmaf_rn(fsum, lut_r3[d], 0.16666667f));
-    flags |= ((((bits + kCodeGuard) & 0x7fffffu) < 2 * kCodeGuard) || bits < 0x3f800000u) ? (1u << i) : 0u;
+    const uint32_t byte = __byte_perm(w, 0, 0x4440 + i);
+    bits[i] = __float_as_uint(__fmaf_rn(fsum, *(lutR - (int)byte), 0.16666667f));
+    any |= code_guarded(bits[i]);
     // 1 << (15 - k), k = E - 125: shift counts >= 32 (k >= 16, or the wrapped negative) give 0
-    asm("shl.b32 %0, %1, %2;" : "=r"(v[i]) : "r"(1u), "r"(140u - (bits >> 23)));
+    asm("shl.b32 %0, %1, %2;" : "=r"(v[i]) : "r"(1u), "r"(140u - (bits[i] >> 23)));
   }
-  return flags;
+  return any;
 }
 
 struct AttSmem {
@@ -189,6 +195,12 @@ attention_int_kernel(const int8_t* __restrict__ qkv, int8_t* __restrict__ out, i
 #pragma unroll
       for (int jj = 0; jj < 4; ++jj) {
         const int j = s * 4 + jj;
+        if (!full && j * 8 >= n) {   // a tile of padded keys only: code 0, no MMA
+          const int pos0 = (s << 5) + ((jj >> 1) << 4) + ((jj & 1) << 1);
+          *reinterpret_cast<uint16_t*>(crowA + pos0) = 0;
+          *reinterpret_cast<uint16_t*>(crowB + pos0) = 0;
+          continue;
+        }
         int c[4] = {0, 0, 0, 0};
 #pragma unroll
         for (int ks = 0; ks < 2; ++ks) {
@@ -227,8 +239,8 @@ attention_int_kernel(const int8_t* __restrict__ qkv, int8_t* __restrict__ out, i
       const uint32_t wb = *reinterpret_cast<const uint32_t*>(crowB + w * 16);
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        sumA += *(lutA - (int)((wa >> (8 * i)) & 0xff));
-        sumB += *(lutB - (int)((wb >> (8 * i)) & 0xff));
+        sumA += *(lutA - (int)__byte_perm(wa, 0, 0x4440 + i));
+        sumB += *(lutB - (int)__byte_perm(wb, 0, 0x4440 + i));
       }
     }
     for (int w = 2 * full_steps; w < 2 * nsteps; ++w) {
@@ -246,6 +258,8 @@ attention_int_kernel(const int8_t* __restrict__ qkv, int8_t* __restrict__ out, i
     sumB += __shfl_xor_sync(0xffffffffu, sumB, 1);
     sumB += __shfl_xor_sync(0xffffffffu, sumB, 2);
     const float fsumA = __ull2float_rn(sumA), fsumB = __ull2float_rn(sumB);
+    const float* lutRA = sm.lut_r3 + maxA;
+    const float* lutRB = sm.lut_r3 + maxB;
 
     // ---- log2 codes -> two u8 probability planes -> P V ------------------------------------------------------
     int8_t* dsc = kDump ? p.dump_scores + ((int64_t)bh * n) * n : nullptr;
@@ -265,14 +279,14 @@ attention_int_kernel(const int8_t* __restrict__ qkv, int8_t* __restrict__ out, i
         const int w = 2 * s + hh;
         const uint32_t wa = *reinterpret_cast<const uint32_t*>(crowA + w * 16);
         const uint32_t wb = *reinterpret_cast<const uint32_t*>(crowB + w * 16);
-        uint32_t va[4], vb[4];
-        const uint32_t fa = prob16x4(wa, maxA, fsumA, sm.lut_r3, va);
-        const uint32_t fb = prob16x4(wb, maxB, fsumB, sm.lut_r3, vb);
-        if (fa | fb) {   // rare: a value next to a step of the code function, or the row maximum
+        uint32_t va[4], vb[4], ba[4], bb[4];
+        const bool fa = prob16x4(wa, lutRA, fsumA, va, ba);
+        const bool fb = prob16x4(wb, lutRB, fsumB, vb, bb);
+        if (fa | fb) {   // rare: a value next to a step of the code function, or a dominant key
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            if (fa & (1u << i)) va[i] = exact_prob16(fsumA, sm.lut_f[maxA - (int)((wa >> (8 * i)) & 0xff)], p.softmax_levels);
-            if (fb & (1u << i)) vb[i] = exact_prob16(fsumB, sm.lut_f[maxB - (int)((wb >> (8 * i)) & 0xff)], p.softmax_levels);
+            if (code_guarded(ba[i])) va[i] = exact_prob16(fsumA, sm.lut_f[maxA - (int)((wa >> (8 * i)) & 0xff)], p.softmax_levels);
+            if (code_guarded(bb[i])) vb[i] = exact_prob16(fsumB, sm.lut_f[maxB - (int)((wb >> (8 * i)) & 0xff)], p.softmax_levels);
           }
         }
         if (!full) {
