@@ -58,13 +58,17 @@ struct p2v_vit {
   int8_t *patches = nullptr, *pe = nullptr, *x0 = nullptr, *x1 = nullptr, *a = nullptr, *qkv = nullptr,
          *o = nullptr, *hid = nullptr, *cls = nullptr, *logit_codes = nullptr;
   CUtensorMap tm_patches, tm_a_d, tm_o, tm_hid, tm_cls;
-  // graph cache
-  cudaGraphExec_t graph = nullptr;
-  const float* g_x = nullptr;
-  float* g_logits = nullptr;
-  int8_t* g_codes = nullptr;
-  int g_b = 0;
-  void* g_ws = nullptr;
+  // graph cache: one captured launch sequence per (x, logits, codes, batch, workspace) binding, so that
+  // double-buffered inputs (copy of batch i+1 overlapping the forward of batch i) replay without re-capture
+  struct GraphEntry {
+    cudaGraphExec_t exec;
+    const float* x;
+    float* logits;
+    int8_t* codes;
+    int b;
+    void* ws;
+  };
+  std::vector<GraphEntry> graphs;
   // dump layout cache
   int dump_b = 0;
   std::vector<DumpEntry> dump;
@@ -143,10 +147,8 @@ static int bind(p2v_vit* h, int b, void* ws) {
   if ((rc = make_tmap_kmajor(&h->tm_cls, h->cls, b, D, D))) return rc;
   h->bound_b = b;
   h->bound_ws = ws;
-  if (h->graph) {
-    cudaGraphExecDestroy(h->graph);
-    h->graph = nullptr;
-  }
+  for (auto& e : h->graphs) cudaGraphExecDestroy(e.exec);   // tensor maps changed: captured launches are stale
+  h->graphs.clear();
   return P2V_OK;
 }
 
@@ -291,7 +293,7 @@ extern "C" int p2v_vit_create(const p2v_vit_desc* desc, int device, p2v_vit** ou
 
 extern "C" void p2v_vit_destroy(p2v_vit* h) {
   if (!h) return;
-  if (h->graph) cudaGraphExecDestroy(h->graph);
+  for (auto& e : h->graphs) cudaGraphExecDestroy(e.exec);
   delete h;
 }
 
@@ -330,12 +332,10 @@ extern "C" int p2v_vit_forward(p2v_vit* h, const float* x, float* logits, int8_t
     return run(h, x, logits, logit_codes, b, dump, st);
   }
   if (!use_graph || st == nullptr) return run(h, x, logits, logit_codes, b, nullptr, st);
-  if (h->graph == nullptr || h->g_x != x || h->g_logits != logits || h->g_codes != logit_codes || h->g_b != b ||
-      h->g_ws != workspace) {
-    if (h->graph) {
-      cudaGraphExecDestroy(h->graph);
-      h->graph = nullptr;
-    }
+  cudaGraphExec_t exec = nullptr;
+  for (auto& e : h->graphs)
+    if (e.x == x && e.logits == logits && e.codes == logit_codes && e.b == b && e.ws == workspace) exec = e.exec;
+  if (exec == nullptr) {
     cudaGraph_t graph = nullptr;
     P2V_CHECK_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
     int rc = run(h, x, logits, logit_codes, b, nullptr, st);
@@ -348,16 +348,19 @@ extern "C" int p2v_vit_forward(p2v_vit* h, const float* x, float* logits, int8_t
       set_error("cudaStreamEndCapture failed: %s", cudaGetErrorString(ce));
       return P2V_ERR_CUDA;
     }
-    ce = cudaGraphInstantiate(&h->graph, graph, 0);
+    ce = cudaGraphInstantiate(&exec, graph, 0);
     cudaGraphDestroy(graph);
     if (ce != cudaSuccess) {
       set_error("cudaGraphInstantiate failed: %s", cudaGetErrorString(ce));
-      h->graph = nullptr;
       return P2V_ERR_CUDA;
     }
-    h->g_x = x; h->g_logits = logits; h->g_codes = logit_codes; h->g_b = b; h->g_ws = workspace;
+    if (h->graphs.size() >= 8) {
+      cudaGraphExecDestroy(h->graphs.front().exec);
+      h->graphs.erase(h->graphs.begin());
+    }
+    h->graphs.push_back({exec, x, logits, logit_codes, b, workspace});
   }
-  P2V_CHECK_CUDA(cudaGraphLaunch(h->graph, st));
+  P2V_CHECK_CUDA(cudaGraphLaunch(exec, st));
   return P2V_OK;
 }
 

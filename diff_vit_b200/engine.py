@@ -88,8 +88,17 @@ class _BoundPlan:
         d.exp_lut = self._p(p.exp_lut)
         return d
 
-    def buffers(self, batch):
-        """(workspace, logits, logit codes) for a batch size; allocated once so graph replays stay valid."""
+    def buffers(self, batch, slot=0):
+        """(workspace, logits, logit codes) for a batch size; allocated once so graph replays stay valid.
+        `slot` > 0 gives additional logits/code buffers over the same workspace (pipelined host I/O)."""
+        if slot:
+            key = ('slot', batch, slot)
+            if key not in self._buffers:
+                ws, ws_ptr, _, _ = self.buffers(batch)
+                logits = torch.empty(batch, self.plan.arch['num_classes'], dtype=torch.float32, device=self.device)
+                codes = torch.empty(batch, self.plan.arch['num_classes'], dtype=torch.int8, device=self.device)
+                self._buffers[key] = (ws, ws_ptr, logits, codes)
+            return self._buffers[key]
         if batch not in self._buffers:
             nbytes = _cabi.lib().p2v_vit_workspace_bytes(self.handle, batch)
             ws = torch.empty(nbytes + 1024, dtype=torch.uint8, device=self.device)
@@ -142,15 +151,15 @@ class IntegerEngine:
             raise AssertionError("Input image size (%d*%d) doesn't match model (%d*%d)." %
                                  (x.shape[-2], x.shape[-1], arch['img_size'], arch['img_size']))
 
-    def forward_into(self, x, bit_config, use_graph=True):
-        """Launch the forward on the current stream; returns the engine-owned logits buffer."""
+    def forward_into(self, x, bit_config, use_graph=True, slot=0):
+        """Launch the forward on the current stream; returns the engine-owned logits buffer (of `slot`)."""
         bp = self.bound(bit_config)
         self._check_input(x, bp.plan.arch)
         if not x.is_cuda:
             raise RuntimeError('IntegerEngine.forward_into expects a CUDA tensor')
         x = x.contiguous().float()
         b = x.shape[0]
-        _, ws, logits, codes = bp.buffers(b)
+        _, ws, logits, codes = bp.buffers(b, slot)
         _cabi.check(_cabi.lib().p2v_vit_forward(bp.handle, x.data_ptr(), logits.data_ptr(), codes.data_ptr(), b, ws,
                                                 None, 1 if use_graph else 0, _cabi.current_stream()))
         self._last_input = x  # keep the (possibly re-laid-out) input alive until the stream consumed it
@@ -191,6 +200,39 @@ class IntegerEngine:
             else:
                 out[key] = raw.view(np.int8).copy()
         return logits.clone(), out
+
+    def forward_host_pipelined(self, batches_host, logits_host, bit_config):
+        """Serving loop over HOST batches: the pinned-memory H2D copy of batch i+1 and the D2H copy of the logits
+        of batch i-1 overlap the forward of batch i (two device input buffers, two logits buffers, one copy
+        stream, CUDA events).  `batches_host[i]` -> `logits_host[i]`; returns after everything has landed."""
+        bp = self.bound(bit_config)
+        comp = torch.cuda.current_stream(self.device)
+        if not hasattr(self, '_copy_stream'):
+            self._copy_stream = torch.cuda.Stream(self.device)
+        copy = self._copy_stream
+        b = batches_host[0].shape[0]
+        key = ('xpipe', b)
+        if key not in bp._buffers:
+            bp._buffers[key] = ([torch.empty(batches_host[0].shape, dtype=torch.float32, device=self.device) for _ in range(2)],
+                                [torch.cuda.Event() for _ in range(2)], [torch.cuda.Event() for _ in range(2)])
+        xdev, ev_in, ev_done = bp._buffers[key]
+        copy.wait_stream(comp)
+        for i, xh in enumerate(batches_host):
+            slot = i & 1
+            with torch.cuda.stream(copy):
+                if i >= 2:
+                    copy.wait_event(ev_done[slot])          # the forward that read this input buffer has finished
+                xdev[slot].copy_(xh, non_blocking=True)
+                ev_in[slot].record(copy)
+            comp.wait_event(ev_in[slot])
+            logits = self.forward_into(xdev[slot], bit_config, slot=slot + 1)
+            ev_done[slot].record(comp)
+            with torch.cuda.stream(copy):
+                copy.wait_event(ev_done[slot])
+                logits_host[i].copy_(logits, non_blocking=True)
+        copy.synchronize()
+        comp.synchronize()
+        return logits_host
 
     def forward_host(self, x_host, logits_host, bit_config):
         """End-to-end call on HOST buffers (pinned for async copies): H2D, forward, D2H, sync."""

@@ -57,6 +57,13 @@ def test_micro_model_every_layer_vs_reference_golden(micro_model, micro_golden, 
         again2 = eng.forward_into(x, bc).clone()
     side.synchronize()
     assert torch.equal(again, logits) and torch.equal(again2, logits)
+    # pipelined host-buffer serving loop: same logits for every batch, including ones that differ
+    xs = [torch.from_numpy(z['x_eval']).pin_memory(), (torch.from_numpy(z['x_eval']) * 0.5).pin_memory(),
+          torch.from_numpy(z['x_eval']).pin_memory()]
+    outs = [torch.empty(6, 16).pin_memory() for _ in xs]
+    eng.forward_host_pipelined(xs, outs, bc)
+    half, _, _ = micro_model(xs[1].cuda(), bc, False)
+    assert torch.equal(outs[0], logits.cpu()) and torch.equal(outs[2], logits.cpu()) and torch.equal(outs[1], half.cpu())
     # host tensors are accepted (copied in and out)
     out_h, _, _ = micro_model(torch.from_numpy(z['x_eval']), bc, False)
     assert not out_h.is_cuda and torch.equal(out_h, logits.cpu())
