@@ -190,6 +190,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     device = torch.device('cuda', local)
     if world > 1:
+        os.environ.pop('NCCL_DEBUG', None)     # NCCL's version banner would land on stdout next to the JSON line
         dist.init_process_group('nccl', device_id=device)
     _cabi.check(_cabi.lib().p2v_check_device(local))
 
