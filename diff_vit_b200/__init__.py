@@ -30,11 +30,16 @@ def calibrate_model(model, batches):
     import torch
     batches = list(batches)
     model.model_open_calibrate()
-    with torch.no_grad():
-        for i, x in enumerate(batches):
-            if i == len(batches) - 1:
-                model.model_open_last_calibrate()
-            model(x, plot=False)
+    tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False        # the weight search scores fp32 conv outputs, as the reference does
+    try:
+        with torch.no_grad():
+            for i, x in enumerate(batches):
+                if i == len(batches) - 1:
+                    model.model_open_last_calibrate()
+                model(x, plot=False)
+    finally:
+        torch.backends.cudnn.allow_tf32 = tf32
     model.model_close_calibrate()
     model.model_quant()
     return model

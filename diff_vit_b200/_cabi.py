@@ -69,6 +69,8 @@ SYMBOLS = {
     'p2v_layernorm_int': (C.c_int, [_vp, C.c_int64, _vp, _vp, C.c_int, C.c_int, C.POINTER(LayerNorm), _vp]),
     'p2v_attention_int': (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.POINTER(Attention), _vp]),
     'p2v_fake_quant_f32': (C.c_int, [_vp, _vp, _vp, C.c_int64, C.c_int, C.c_int64, _vp, _vp, C.c_int, C.c_int, _vp]),
+    'p2v_observe_minmax': (C.c_int, [_vp, C.c_int64, C.c_int, C.c_int, _vp, _vp, _vp]),
+    'p2v_observe_scale_sse': (C.c_int, [_vp, C.c_int64, C.c_int, C.c_int, _fp, C.c_int, C.c_float, C.c_float, _vp, _vp]),
     'p2v_vit_create': (C.c_int, [C.POINTER(VitDesc), C.c_int, C.POINTER(_vp)]),
     'p2v_vit_destroy': (None, [_vp]),
     'p2v_vit_workspace_bytes': (C.c_int64, [_vp, C.c_int]),

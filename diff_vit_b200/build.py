@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libp2vit_b200.so')
-SOURCES = ['p2v_engine.cu', 'p2v_gemm.cu', 'p2v_rowops.cu', 'p2v_attention.cu']
+SOURCES = ['p2v_engine.cu', 'p2v_gemm.cu', 'p2v_rowops.cu', 'p2v_attention.cu', 'p2v_observe.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '--expt-relaxed-constexpr', '-Xcompiler', '-fPIC', '-Xptxas', '-v']
 

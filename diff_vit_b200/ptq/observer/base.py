@@ -27,9 +27,15 @@ class BaseObserver:
 
     def _track_minmax(self, v):
         """Running per-channel min/max, collapsed to scalars for layer-wise calibration."""
-        v = self.reshape_tensor(v)
-        cur_max = v.max(axis=1).values
-        cur_min = v.min(axis=1).values
+        from . import gpu_stats
+        if self.module_type == 'activation' and gpu_stats.usable(v) and \
+                (self.calibration_mode == 'layer_wise' or v.dim() in (2, 3)):
+            # fused range kernel (csrc/p2v_observe.cu); the scalar case does not need the channel split at all
+            cur_min, cur_max = gpu_stats.minmax(v, per_channel=self.calibration_mode != 'layer_wise')
+        else:
+            v = self.reshape_tensor(v)
+            cur_max = v.max(axis=1).values
+            cur_min = v.min(axis=1).values
         if self.module_type == 'activation':   # weights are replicated; activations are sharded over ranks
             from ... import dist as _dist
             _dist.reduce_max_(cur_max)

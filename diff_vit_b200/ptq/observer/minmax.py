@@ -61,6 +61,12 @@ class MinmaxObserver(BaseObserver):
             target = self.v
         if self.attn and layer_wise:
             raise NotImplementedError('attn-output calibration objective is never enabled by the callers')
+        from . import gpu_stats
+        if self.module_type == 'activation' and zero_point is None and gpu_stats.usable(target):
+            # fused kernel: the four candidate errors in one pass over the activation
+            steps = [float(2.0 ** (float(alpha_floor.reshape(-1)[0]) - 1 + k)) for k in range(4)]
+            sums, count = gpu_stats.scale_sse(target, steps, qmin, qmax, per_channel=False)
+            return alpha_floor - 1 + gpu_stats.first_argmin_mean(sums, count).reshape(1)
         zp = torch.zeros(1, device=target.device) if zero_point is None else zero_point
         view = (-1,) + (1,) * (target.dim() - 1)
         ref_out = self._project(target)

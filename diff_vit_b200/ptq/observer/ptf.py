@@ -29,6 +29,13 @@ class PtfObserver(BaseObserver):
         zero_point = torch.zeros_like(max_val.max(), dtype=torch.int64)
         if inputs.dim() != 3:
             raise NotImplementedError('PTF calibration expects a [B, N, C] activation')
+        from . import gpu_stats
+        if gpu_stats.usable(inputs):
+            # fused kernel: per-channel error of the four power-of-two factors in one pass
+            sums, count = gpu_stats.scale_sse(inputs, [float(s) for s in (scale1, scale2, scale4, scale8)], qmin, qmax,
+                                              per_channel=True)
+            self.scale_mask = 2 ** gpu_stats.first_argmin_mean(sums, count)
+            return scale1 * self.scale_mask, zero_point
         best = None
         choice = torch.zeros_like(max_val)
         for m, s in enumerate((scale1, scale2, scale4, scale8)):

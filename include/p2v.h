@@ -137,6 +137,20 @@ int p2v_attention_int(const int8_t* qkv, int8_t* out, int b, int n, int heads, c
 int p2v_fake_quant_f32(const float* x, float* out, int8_t* codes, int64_t outer, int channels, int64_t inner,
                        const float* scale, const float* zero_point, int qmin, int qmax, void* stream);
 
+/* ---- calibration statistics ------------------------------------------------------- */
+/* Running range of an activation: x is fp32 [rows, channels]; per_channel = 0 reduces the whole tensor to
+ * out_min[0] / out_max[0], per_channel = 1 gives one pair per (contiguous, innermost) channel.  The outputs are
+ * ACCUMULATED: pre-fill with +inf / -inf.  Replaces the max/min of MinmaxObserver.update and PtfObserver.update
+ * (models/ptq/observer/minmax.py:16-39, ptf.py:14-31). */
+int p2v_observe_minmax(const float* x, int64_t rows, int channels, int per_channel, float* out_min, float* out_max,
+                       void* stream);
+/* Squared error of fake-quantizing x with each of n_scales (<= 8, HOST array) candidate scales, zero point 0:
+ * out[k] (per tensor) or out[k * channels + c] (per channel) += sum (x - clamp(RNE(x / s_k), qmin, qmax) * s_k)^2,
+ * fp64.  Replaces the candidate scoring of the activation PoT search (minmax.py:180-242) and of the PTF factor
+ * search (ptf.py:110-131). */
+int p2v_observe_scale_sse(const float* x, int64_t rows, int channels, int per_channel, const float* scales_host,
+                          int n_scales, float qmin, float qmax, double* out, void* stream);
+
 /* ---- whole-model engine ------------------------------------------------------------------------ */
 typedef struct p2v_linear_desc {
   const int8_t* w;          /* [n, k] codes */
