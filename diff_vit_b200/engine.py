@@ -123,8 +123,10 @@ class _BoundPlan:
 class IntegerEngine:
     """Quantized forward of one calibrated model on one CUDA device."""
 
-    def __init__(self, model=None, state=None, device=None):
-        if state is None:
+    def __init__(self, model=None, state=None, device=None, plans=()):
+        """`plans`: ready-made VitPlans (e.g. `plan.load_plan(path)`), used for their bit_config without any
+        calibrated model or state."""
+        if state is None and model is not None:
             state = extract_state(model)
         self.state = state
         if device is None:
@@ -139,10 +141,14 @@ class IntegerEngine:
         if self.device.index is None:
             self.device = torch.device('cuda', torch.cuda.current_device())
         self._plans = {}
+        for plan in plans:
+            self._plans[tuple(int(b) for b in plan.bit_config)] = _BoundPlan(plan, self.device)
 
     def bound(self, bit_config):
         key = tuple(int(b) for b in bit_config)
         if key not in self._plans:
+            if self.state is None:
+                raise KeyError('no plan for bit_config %s and no calibrated state to build one from' % (key,))
             self._plans[key] = _BoundPlan(build_plan(self.state, key), self.device)
         return self._plans[key]
 

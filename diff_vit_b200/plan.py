@@ -304,3 +304,63 @@ class _Builder:
 def build_plan(state, bit_config):
     """Integer plan for one bit_config (index map: 0 conv, 1+4i.. block i qkv/proj/fc1/fc2, -1 head)."""
     return _Builder(state, bit_config).build()
+
+
+# ---- serialised plans -------------------------------------------------------------------------------------------
+# The reference keeps calibrated scales only as Python attributes (SURVEY.md section 5, "checkpoint / resume");
+# an integer plan is self-contained (int8 codes + fp32 vectors + a few scalars), so it can be written once and
+# executed later without the float model, the calibration data or PyTorch modules.
+_PLAN_CLASSES = {c.__name__: c for c in (LinearPlan, LayerNormPlan, AttentionPlan, BlockPlan, VitPlan)}
+
+
+def _flatten(obj, prefix, out):
+    if isinstance(obj, torch.Tensor):
+        out[prefix] = obj.detach().cpu().numpy()
+    elif hasattr(obj, '__dataclass_fields__'):
+        out[prefix + '/__class__'] = type(obj).__name__
+        for f in obj.__dataclass_fields__:
+            _flatten(getattr(obj, f), prefix + '/' + f, out)
+    elif isinstance(obj, (list, tuple)) and obj and hasattr(obj[0], '__dataclass_fields__'):
+        out[prefix + '/__len__'] = len(obj)
+        for i, o in enumerate(obj):
+            _flatten(o, '%s/%d' % (prefix, i), out)
+    elif isinstance(obj, dict):
+        out[prefix + '/__dict__'] = repr(sorted(obj.items()))
+    elif obj is None:
+        out[prefix + '/__none__'] = 1
+    else:
+        out[prefix] = obj
+
+
+def save_plan(plan, path):
+    """Write a VitPlan to a compressed .npz file."""
+    import numpy as np
+    flat = {}
+    _flatten(plan, 'plan', flat)
+    np.savez_compressed(path, **{k: np.asarray(v) for k, v in flat.items()})
+
+
+def _unflatten(z, prefix):
+    import ast
+    if prefix + '/__none__' in z:
+        return None
+    if prefix + '/__dict__' in z:
+        return dict(ast.literal_eval(str(z[prefix + '/__dict__'])))
+    if prefix + '/__len__' in z:
+        return [_unflatten(z, '%s/%d' % (prefix, i)) for i in range(int(z[prefix + '/__len__']))]
+    if prefix + '/__class__' in z:
+        cls = _PLAN_CLASSES[str(z[prefix + '/__class__'])]
+        return cls(**{f: _unflatten(z, prefix + '/' + f) for f in cls.__dataclass_fields__})
+    a = z[prefix]
+    if a.ndim == 0:
+        return a.item()
+    if a.dtype.kind in 'iu' and a.ndim == 1 and prefix.endswith('bit_config'):
+        return tuple(int(v) for v in a)
+    return torch.from_numpy(a.copy())
+
+
+def load_plan(path):
+    """Read a VitPlan written by `save_plan`."""
+    import numpy as np
+    with np.load(path) as z:
+        return _unflatten({k: z[k] for k in z.files}, 'plan')

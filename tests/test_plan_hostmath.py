@@ -104,3 +104,17 @@ def test_omse_zero_points_are_rejected_loudly(micro_golden):
     dv.calibrate_model(fresh, [torch.from_numpy(micro_golden['x_calib'])])    # runs (the reference's own omse raises TypeError)
     with pytest.raises(NotImplementedError):
         build_plan(extract_state(fresh), [8] * 10)
+
+
+def test_plan_round_trips_through_npz(micro_state, micro_golden, tmp_path):
+    from diff_vit_b200.plan import load_plan, save_plan
+    plan = build_plan(micro_state, [int(v) for v in micro_golden['mixed/bit_config']])
+    path = str(tmp_path / 'plan.npz')
+    save_plan(plan, path)
+    back = load_plan(path)
+    assert back.bit_config == plan.bit_config and back.arch == plan.arch
+    a, b = list(plan.tensors()), list(back.tensors())
+    assert len(a) == len(b) > 50 and all(x.dtype == y.dtype and torch.equal(x, y) for x, y in zip(a, b))
+    assert back.blocks[1].attn.out_mul == plan.blocks[1].attn.out_mul and back.blocks[0].norm2.pot == plan.blocks[0].norm2.pot
+    logits, _ = hostmath.run_plan(back, micro_golden['x_eval'])
+    np.testing.assert_array_equal(logits, micro_golden['mixed/logits'])
