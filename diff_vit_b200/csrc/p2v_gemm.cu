@@ -34,6 +34,7 @@ constexpr int kEpiWarps = 16;                  // 4 TMEM lane quarters x 4 colum
 constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kGemmThreads = 128 + kEpiThreads;
 constexpr uint32_t kTmemCols = kAccStages * kBlockN;  // 256 columns of 32-bit accumulators
+constexpr int kChanCols = 512;                        // per-channel constants kept in shared memory
 
 // per-channel epilogue constants staged in shared memory, one array per field (broadcast float4 reads)
 enum { CH_A = 0, CH_B, CH_RSO, CH_SO, CH_SR, CH_RSO2, CH_SO2, CH_FIELDS };
@@ -41,7 +42,7 @@ enum { CH_A = 0, CH_B, CH_RSO, CH_SO, CH_SR, CH_RSO2, CH_SO2, CH_FIELDS };
 struct GemmSmem {
   alignas(1024) uint8_t a[kStages][kTileBytes];
   alignas(1024) uint8_t b[kStages][kTileBytes];
-  alignas(16) float chan[kAccStages][CH_FIELDS][kBlockN];
+  alignas(16) float chan[CH_FIELDS][kChanCols];   // whole n when n <= kChanCols, else two 128-column slots
   alignas(16) uint8_t stage[4][32 * 144];
   alignas(8) uint64_t full[kStages];
   uint64_t empty[kStages];
@@ -71,9 +72,10 @@ __device__ __forceinline__ uint32_t pack_sat4(float v0, float v1, float v2, floa
 // RNE(fl(y / s) + zp), the unclamped code of a quantizer with a non-power-of-two scale, without paying an
 // IEEE division per element: t = y * fl(1/s) + zp is within a few ulp of the exact operand of the
 // rounding, so rint(t) can differ from the exact result only when t lies within kTieGuard of a
-// half-integer; only those elements (~0.2 %) take the exact division.  For |t| >= 512 both paths
-// saturate to the same int8 code, so the absolute guard is sufficient.
-constexpr float kTieGuard = 0.0009765625f;  // 2^-10 >> 4 ulp(512)
+// half-integer; only those elements (~0.02 %) take the exact division.  For |t| >= 512 both paths
+// saturate to the same int8 code, so the absolute guard is sufficient: below 128.5 the operand t = y * fl(1/s)
+// is within 1.5 ulp(128) = 2.3e-5 of the exactly divided one, and the guard is 5x that.
+constexpr float kTieGuard = 0.0001220703125f;  // 2^-13
 __device__ __noinline__ float div_round_exact(float y, float s, float zp) { return rintf(fadd(fdiv(y, s), zp)); }
 __device__ __forceinline__ float div_round(float y, float s, float rs, float zp) {
   const float t = fadd(fmul(y, rs), zp);
@@ -219,10 +221,12 @@ __device__ __forceinline__ void epilogue16(const uint32_t (&acc)[16], const floa
 
 // Stage the per-channel constants of one 128-column tile (epilogue warps only).
 template <uint32_t FLAGS, int CW>
-__device__ __forceinline__ void load_channels(float (*ch)[CW], const p2v_epilogue& e, int n0, int n, int tid) {
+__device__ __forceinline__ void load_channels(float (*ch)[CW], const p2v_epilogue& e, int n0, int n, int tid,
+                                              int dst0 = 0, int count = CW) {
   constexpr bool kFold = (FLAGS & EPI_OUT_POT) && !(FLAGS & EPI_GELU);
-  for (int j = tid; j < CW; j += kEpiThreads) {
-    const int col = n0 + j;
+  for (int jj = tid; jj < count; jj += kEpiThreads) {
+    const int col = n0 + jj;
+    const int j = dst0 + jj;
     float A = 0.f, B = 0.f, RSO = 1.f, SO = 1.f, SR = 0.f, RSO2 = 1.f, SO2 = 1.f;
     if (col < n && e.acc_scale != nullptr) {
       A = e.acc_scale[col];
@@ -312,6 +316,16 @@ template <uint32_t FLAGS>
 __device__ __forceinline__ bool can_stage(const GemmArgs& g) {
   return !(FLAGS & (EPI_GELU | EPI_RESIDUAL)) && g.raw_acc == nullptr && (g.ld_out & 15) == 0 && (g.n & 15) == 0 &&
          (reinterpret_cast<uintptr_t>(g.out) & 15) == 0;
+}
+
+// One 16-column chunk of residual codes of one row, issued early.
+template <uint32_t FLAGS>
+__device__ __forceinline__ bool prefetch_residual16(const GemmArgs& g, int row, int col, uint4& r) {
+  if (!(FLAGS & EPI_RESIDUAL) || row >= g.m || col + 16 > g.n || (g.ld_out & 15) != 0 || (col & 15) != 0 ||
+      (reinterpret_cast<uintptr_t>(g.epi.residual) & 15) != 0)
+    return false;
+  r = __ldg(reinterpret_cast<const uint4*>(g.epi.residual + (int64_t)row * g.ld_out + col));
+  return true;
 }
 
 // Early issue of the residual loads of one thread's 32 columns (two 16-byte words), so that their latency
@@ -418,28 +432,63 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     const int cgroup = ew >> 2;        // 32-column group of the tile
     const int etid = threadIdx.x - 128;
     const bool staged = can_stage<FLAGS>(g);
+    constexpr bool kHeavy = (FLAGS & (EPI_GELU | EPI_RESIDUAL)) != 0;
+    // per-channel constants: resident for the whole kernel when n fits, else reloaded per tile into one of two slots
+    const bool chan_resident = g.n <= kChanCols;
+    if (chan_resident) {
+      load_channels<FLAGS, kChanCols>(s.chan, g.epi, 0, g.n, etid);
+      asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+    }
     uint32_t acc = 0, acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m0 = (tile / tiles_n) * kBlockM, n0 = (tile % tiles_n) * kBlockN;
-      // per-channel constants of this tile -> smem.  chan[acc] was last read two tiles ago; every epilogue
-      // warp has passed the barrier of the tile in between, so the overwrite is safe.
-      load_channels<FLAGS, kBlockN>(s.chan[acc], g.epi, n0, g.n, etid);
-      asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
-      uint4 pr0 = make_uint4(0, 0, 0, 0), pr1 = pr0;
-      const bool pre = prefetch_residual<FLAGS>(g, m0 + quarter * 32 + lane, n0 + cgroup * 32, pr0, pr1);
-      mbar_wait(&s.acc_full[acc], acc_phase);
-      tc_fence_after_sync();
+      int cbase = n0;   // column of this tile's constants inside s.chan
+      if (!chan_resident) {
+        // slot `acc` was last read two tiles ago; every epilogue warp has passed the barrier of the tile in between
+        cbase = acc * kBlockN;
+        load_channels<FLAGS, kChanCols>(s.chan, g.epi, n0, g.n, etid, cbase, kBlockN);
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+      }
+      const int row = m0 + quarter * 32 + lane;
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * kBlockN + cgroup * 32;
-      uint32_t v0[16], v1[16];
-      tmem_ld_32x16(taddr, v0);
-      tmem_ld_32x16(taddr + 16, v1);
-      tmem_ld_wait();
-      // the accumulator is in registers: release it to the MMA warp before the arithmetic
-      tc_fence_before_sync();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&s.acc_empty[acc]);
-      epilogue_block<FLAGS, kBlockN>(v0, v1, s.chan[acc], 0, g, m0 + quarter * 32, n0, quarter, cgroup, lane,
-                                     s.stage[quarter], staged, pre ? &pr0 : nullptr, pre ? &pr1 : nullptr);
+      if (kHeavy && !staged) {
+        // GELU / residual epilogues: one 16-column chunk at a time keeps the hot loop small (instruction cache);
+        // the next chunk's residual codes are in flight while the current one is processed
+        uint4 cur = make_uint4(0, 0, 0, 0), nxt = cur;
+        bool cur_ok = prefetch_residual16<FLAGS>(g, row, n0 + cgroup * 32, cur), nxt_ok = false;
+        mbar_wait(&s.acc_full[acc], acc_phase);
+        tc_fence_after_sync();
+#pragma unroll 1
+        for (int ch = 0; ch < 2; ++ch) {
+          if (ch == 0) nxt_ok = prefetch_residual16<FLAGS>(g, row, n0 + cgroup * 32 + 16, nxt);
+          uint32_t v[16];
+          tmem_ld_32x16(taddr + ch * 16, v);
+          tmem_ld_wait();
+          if (ch == 1) {
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s.acc_empty[acc]);
+          }
+          if (row < g.m)
+            epilogue16<FLAGS, kChanCols>(v, s.chan, cbase + cgroup * 32 + ch * 16, g, row, n0 + cgroup * 32 + ch * 16,
+                                         cur_ok ? &cur : nullptr);
+          cur = nxt;
+          cur_ok = nxt_ok;
+        }
+      } else {
+        mbar_wait(&s.acc_full[acc], acc_phase);
+        tc_fence_after_sync();
+        uint32_t v0[16], v1[16];
+        tmem_ld_32x16(taddr, v0);
+        tmem_ld_32x16(taddr + 16, v1);
+        tmem_ld_wait();
+        // the accumulator is in registers: release it to the MMA warp before the arithmetic
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s.acc_empty[acc]);
+        epilogue_block<FLAGS, kChanCols>(v0, v1, s.chan, cbase, g, m0 + quarter * 32, n0, quarter, cgroup, lane,
+                                         s.stage[quarter], staged);
+      }
       if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
     }
   }
@@ -575,32 +624,57 @@ gemm_i8_bs_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
       uint32_t it = 0;
       const bool staged = can_stage<FLAGS>(g);
+      constexpr bool kHeavy = (FLAGS & (EPI_GELU | EPI_RESIDUAL)) != 0;
       for (int tile = local; tile < tiles_m; tile += cnt, ++it) {
         const uint32_t p = it & 1;
-        uint4 pa0 = make_uint4(0, 0, 0, 0), pa1 = pa0, pb0 = pa0, pb1 = pa0;
-        const int prow = tile * kBlockM + quarter * 32 + lane;
-        const bool prea = prefetch_residual<FLAGS>(g, prow, n0 + cgroup * 32, pa0, pa1);
-        const bool preb = nsub > 1 && prefetch_residual<FLAGS>(g, prow, n0 + kBlockN + cgroup * 32, pb0, pb1);
-        mbar_wait(&s.acc_full[p], (it >> 1) & 1);
-        tc_fence_after_sync();
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          if (h >= nsub) break;
-          const int c = h * kBlockN + cgroup * 32;
-          const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + p * kBsSlabCols + c;
-          uint32_t v0[16], v1[16];
-          tmem_ld_32x16(taddr, v0);
-          tmem_ld_32x16(taddr + 16, v1);
-          tmem_ld_wait();
-          if (h == nsub - 1) {   // both halves are in registers or done: hand the accumulator back
-            tc_fence_before_sync();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&s.acc_empty[p]);
+        const int row0 = tile * kBlockM + quarter * 32;
+        const uint32_t tq = tmem_base + ((uint32_t)(quarter * 32) << 16) + p * kBsSlabCols;
+        if (kHeavy && !staged) {
+          // 16-column chunks, rolled: small hot loop, next chunk's residual codes prefetched
+          const int nchunks = nsub * 2;
+          uint4 cur = make_uint4(0, 0, 0, 0), nxt = cur;
+          bool cur_ok = prefetch_residual16<FLAGS>(g, row0 + lane, n0 + cgroup * 32, cur), nxt_ok = false;
+          mbar_wait(&s.acc_full[p], (it >> 1) & 1);
+          tc_fence_after_sync();
+#pragma unroll 1
+          for (int ch = 0; ch < nchunks; ++ch) {
+            const int c = (ch >> 1) * kBlockN + cgroup * 32 + (ch & 1) * 16;   // column inside the slab
+            if (ch + 1 < nchunks) {
+              const int cn = ((ch + 1) >> 1) * kBlockN + cgroup * 32 + ((ch + 1) & 1) * 16;
+              nxt_ok = prefetch_residual16<FLAGS>(g, row0 + lane, n0 + cn, nxt);
+            }
+            uint32_t v[16];
+            tmem_ld_32x16(tq + c, v);
+            tmem_ld_wait();
+            if (ch == nchunks - 1) {   // everything is in registers: hand the accumulator back
+              tc_fence_before_sync();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&s.acc_empty[p]);
+            }
+            if (row0 + lane < g.m)
+              epilogue16<FLAGS, kBsSlabCols>(v, s.chan, c, g, row0 + lane, n0 + c, cur_ok ? &cur : nullptr);
+            cur = nxt;
+            cur_ok = nxt_ok;
           }
-          epilogue_block<FLAGS, kBsSlabCols>(v0, v1, s.chan, h * kBlockN, g, tile * kBlockM + quarter * 32,
-                                             n0 + h * kBlockN, quarter, cgroup, lane, s.stage[quarter], staged,
-                                             h == 0 ? (prea ? &pa0 : nullptr) : (preb ? &pb0 : nullptr),
-                                             h == 0 ? (prea ? &pa1 : nullptr) : (preb ? &pb1 : nullptr));
+        } else {
+          mbar_wait(&s.acc_full[p], (it >> 1) & 1);
+          tc_fence_after_sync();
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            if (h >= nsub) break;
+            const int c = h * kBlockN + cgroup * 32;
+            uint32_t v0[16], v1[16];
+            tmem_ld_32x16(tq + c, v0);
+            tmem_ld_32x16(tq + c + 16, v1);
+            tmem_ld_wait();
+            if (h == nsub - 1) {
+              tc_fence_before_sync();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&s.acc_empty[p]);
+            }
+            epilogue_block<FLAGS, kBsSlabCols>(v0, v1, s.chan, h * kBlockN, g, row0, n0 + h * kBlockN, quarter, cgroup,
+                                               lane, s.stage[quarter], staged);
+          }
         }
       }
     }
