@@ -93,24 +93,25 @@ __device__ __forceinline__ uint32_t pack_sat4f(float v0, float v1, float v2, flo
   return r;
 }
 
-// LN code of one element on a power-of-two grid with pre-folded affine (go = gamma/s_out, bo = beta/s_out)
+// LN code of one element on a power-of-two grid with pre-folded affine (go = gamma/s_out, bo = beta/s_out).
+// Same arithmetic as p2v_math.cuh ln_code<true>, with the dyadic exponent handled in the bit domain:
+//   2^N = clamp(2^(7 - e), 1, 2^31),  e = exponent(|A|)   ->  bits(2^(7-e)) = (261 << 23) - (bits(|A|) & 0x7f800000)
 __device__ __forceinline__ float ln_code_folded(float xq, const LnRow& row, float go, float bo) {
   const float A = fmul(row.t, go);
-  const float absA = fabsf(A);
-  int e = (int)((f2u(absA) >> 23) & 0xffu) - 127;
-  int N = 7 - e;
-  N = N < 0 ? 0 : (N > 31 ? 31 : N);
-  const float p2N = pow2i(N);
-  float M = floorf(fmul(absA, p2N));
-  M = fminf(M, 255.f);
+  const uint32_t ab = f2u(A) & 0x7fffffffu;
+  float p2N = u2f(0x82800000u - (ab & 0x7f800000u));          // 2^(7 - e); e = -127 (A == 0 / denormal) clamps below
+  p2N = fminf(fmaxf(p2N, 1.0f), 2147483648.0f);               // N in [0, 31]
+  const float inv2N = u2f(0x7f000000u - f2u(p2N));            // 2^-N
+  const float M = fminf(floorf(fmul(u2f(ab), p2N)), 255.f);
   // sign(A) * M == copysign(M, A): A == 0 forces M == 0, and (-0) * xq + Bq == Bq
   const float sM = u2f(f2u(M) | (f2u(A) & 0x80000000u));
   const float Bq = rne(fmul(fsub(bo, fmul(row.u, go)), p2N));
-  const float y = fadd(fmul(sM, xq), Bq);
-  return rne(fmul(y, pow2i(-N)));
+  // sM * xq is exact (< 2^24), so the fused multiply-add rounds once, like the reference's separate add
+  return rne(fmul(ffma(sM, xq, Bq), inv2N));
 }
 
-template <int G>
+// G = 4-channel groups per lane.  FULL: d == 128 * G (no partial group).  DUMP: also write the unclamped LN codes.
+template <int G, bool FULL, bool DUMP>
 __global__ void __launch_bounds__(256, 3)
 layernorm_int_pot_kernel(const int8_t* __restrict__ in, int64_t in_row_stride, int8_t* __restrict__ out,
                          int32_t* __restrict__ ln_codes, int rows, int d, const p2v_layernorm p) {
@@ -122,7 +123,7 @@ layernorm_int_pot_kernel(const int8_t* __restrict__ in, int64_t in_row_stride, i
 #pragma unroll
   for (int g = 0; g < G; ++g) {
     const int grp = g * 32 + lane;
-    if (grp < groups) {
+    if (FULL || grp < groups) {
       const int c0 = grp * 4;
       const float4 ga = *reinterpret_cast<const float4*>(p.gamma + c0);
       const float4 be = *reinterpret_cast<const float4*>(p.beta + c0);
@@ -133,6 +134,9 @@ layernorm_int_pot_kernel(const int8_t* __restrict__ in, int64_t in_row_stride, i
       bo[g][0] = fmul(be.x, rs.x); bo[g][1] = fmul(be.y, rs.y); bo[g][2] = fmul(be.z, rs.z); bo[g][3] = fmul(be.w, rs.w);
       pm[g][0] = m4.x; pm[g][1] = m4.y; pm[g][2] = m4.z; pm[g][3] = m4.w;
       mk[g][0] = (int)im.x; mk[g][1] = (int)im.y; mk[g][2] = (int)im.z; mk[g][3] = (int)im.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { go[g][j] = 0.f; bo[g][j] = 0.f; pm[g][j] = 0.f; mk[g][j] = 0; }
     }
   }
   // software pipeline: the next row's codes are in flight while this row is normalised
@@ -141,7 +145,7 @@ layernorm_int_pot_kernel(const int8_t* __restrict__ in, int64_t in_row_stride, i
 #pragma unroll
   for (int g = 0; g < G; ++g) {
     const int grp = g * 32 + lane;
-    next_w[g] = (row < rows && grp < groups) ? __ldg(reinterpret_cast<const uint32_t*>(in + (int64_t)row * in_row_stride + grp * 4)) : 0u;
+    next_w[g] = (row < rows && (FULL || grp < groups)) ? __ldg(reinterpret_cast<const uint32_t*>(in + (int64_t)row * in_row_stride + grp * 4)) : 0u;
   }
   for (; row < rows; row += warps_total) {
     uint32_t cur_w[G];
@@ -150,22 +154,18 @@ layernorm_int_pot_kernel(const int8_t* __restrict__ in, int64_t in_row_stride, i
     for (int g = 0; g < G; ++g) {
       const int grp = g * 32 + lane;
       cur_w[g] = next_w[g];
-      next_w[g] = (nrow < rows && grp < groups) ? __ldg(reinterpret_cast<const uint32_t*>(in + (int64_t)nrow * in_row_stride + grp * 4)) : 0u;
+      next_w[g] = (nrow < rows && (FULL || grp < groups)) ? __ldg(reinterpret_cast<const uint32_t*>(in + (int64_t)nrow * in_row_stride + grp * 4)) : 0u;
     }
     float xq[G][4];
-    int sum = 0, sumsq = 0;   // |x| <= 1024, d <= 128 G: per-lane partial sums stay far below 2^31
+    int sum = 0, sumsq = 0;   // |x| <= 1024, d <= 128 G: per-lane partial sums stay far below 2^31; padded groups add 0
 #pragma unroll
     for (int g = 0; g < G; ++g) {
-      const int grp = g * 32 + lane;
-      if (grp < groups) {
-        const uint32_t word = cur_w[g];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int v = (int)(int8_t)((word >> (8 * j)) & 0xff) * mk[g][j];
-          xq[g][j] = (float)v;
-          sum += v;
-          sumsq += v * v;
-        }
+      for (int j = 0; j < 4; ++j) {
+        const int v = (int)(int8_t)((cur_w[g] >> (8 * j)) & 0xff) * mk[g][j];
+        xq[g][j] = (float)v;
+        sum += v;
+        sumsq += v * v;
       }
     }
     long long sumsq64 = sumsq;
@@ -178,13 +178,13 @@ layernorm_int_pot_kernel(const int8_t* __restrict__ in, int64_t in_row_stride, i
 #pragma unroll
     for (int g = 0; g < G; ++g) {
       const int grp = g * 32 + lane;
-      if (grp < groups) {
+      if (FULL || grp < groups) {
         float v[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const float code = ln_code_folded(xq[g][j], st, go[g][j], bo[g][j]);
-          if (ln_codes != nullptr) ln_codes[(int64_t)row * d + grp * 4 + j] = (int)code;
-          v[j] = fadd(fmul(code, pm[g][j]), p.post_zp);
+          if (DUMP) ln_codes[(int64_t)row * d + grp * 4 + j] = (int)code;
+          v[j] = ffma(code, pm[g][j], p.post_zp);   // code * 2^k is exact: one rounding, like mul then add
         }
         *reinterpret_cast<uint32_t*>(out + (int64_t)row * d + grp * 4) = pack_sat4f(v[0], v[1], v[2], v[3]);
       }
@@ -328,9 +328,18 @@ extern "C" int p2v_layernorm_int(const int8_t* in, int64_t in_row_stride, int8_t
     P2V_REQUIRE(p->ln_out_rscale && p->post_mul, "p2v_layernorm_int: pot path needs ln_out_rscale and post_mul");
     const int groups = (d / 4 + 31) / 32;
     const int pgrid = grid < kNumSMs * 3 ? grid : kNumSMs * 3;   // persistent warps (3 resident CTAs per SM): constants stay in registers
-    if (groups == 1) layernorm_int_pot_kernel<1><<<pgrid, warps * 32, 0, st>>>(in, in_row_stride, out, ln_codes, rows, d, *p);
-    else if (groups == 2) layernorm_int_pot_kernel<2><<<pgrid, warps * 32, 0, st>>>(in, in_row_stride, out, ln_codes, rows, d, *p);
-    else if (groups == 3) layernorm_int_pot_kernel<3><<<pgrid, warps * 32, 0, st>>>(in, in_row_stride, out, ln_codes, rows, d, *p);
+#define P2V_LN_LAUNCH(G_)                                                                                          \
+  do {                                                                                                             \
+    const bool full = d == 128 * (G_);                                                                             \
+    if (full && ln_codes) layernorm_int_pot_kernel<G_, true, true><<<pgrid, warps * 32, 0, st>>>(in, in_row_stride, out, ln_codes, rows, d, *p);        \
+    else if (full) layernorm_int_pot_kernel<G_, true, false><<<pgrid, warps * 32, 0, st>>>(in, in_row_stride, out, ln_codes, rows, d, *p);            \
+    else if (ln_codes) layernorm_int_pot_kernel<G_, false, true><<<pgrid, warps * 32, 0, st>>>(in, in_row_stride, out, ln_codes, rows, d, *p);        \
+    else layernorm_int_pot_kernel<G_, false, false><<<pgrid, warps * 32, 0, st>>>(in, in_row_stride, out, ln_codes, rows, d, *p);                     \
+  } while (0)
+    if (groups == 1) P2V_LN_LAUNCH(1);
+    else if (groups == 2) P2V_LN_LAUNCH(2);
+    else if (groups == 3) P2V_LN_LAUNCH(3);
+#undef P2V_LN_LAUNCH
     else layernorm_int_kernel<true><<<grid, warps * 32, 0, st>>>(in, in_row_stride, out, ln_codes, rows, d, *p);
   } else {
     P2V_REQUIRE(p->post_div1, "p2v_layernorm_int: non-pot path needs post_div1");
