@@ -95,7 +95,7 @@ struct AttSmem {
   alignas(16) uint8_t codes[kAttWarps][16 * kVtStride];   // biased score codes in AV key order, per warp
   float lut_f[256];
   float lut_r3[256];
-  unsigned long long lut_i[256];
+  double lut_d[256];   // the integer exp as fp64 (exact): row sums of <= 224 terms < 2^51 stay exact in fp64
 };
 
 // One CTA = one (image, head): K and V are staged once, each of the 7 warps walks 16-row query tiles.
@@ -123,7 +123,7 @@ attention_int_kernel(const int8_t* __restrict__ qkv, int8_t* __restrict__ out, i
     const float e = p.exp_lut[i];
     sm.lut_f[i] = e;
     sm.lut_r3[i] = __fdiv_rn(1.0f, 3.0f * e);   // 3e is exact (<= 24 significant bits)
-    sm.lut_i[i] = (unsigned long long)e;
+    sm.lut_d[i] = (double)e;
   }
   for (int i = tid; i < nkp * 4; i += blockDim.x) {
     const int j = i >> 2, part = i & 3;
@@ -230,9 +230,10 @@ attention_int_kernel(const int8_t* __restrict__ qkv, int8_t* __restrict__ out, i
     __syncwarp();
 
     // ---- exact integer row sums of the integer exp ----------------------------------------------------------
-    unsigned long long sumA = 0, sumB = 0;
-    const unsigned long long* lutA = sm.lut_i + maxA;
-    const unsigned long long* lutB = sm.lut_i + maxB;
+    // fp64 adds run on their own pipe, next to the integer/fp32 work of the other warps
+    double sumA = 0.0, sumB = 0.0;
+    const double* lutA = sm.lut_d + maxA;
+    const double* lutB = sm.lut_d + maxB;
 #pragma unroll 2
     for (int w = 0; w < 2 * full_steps; ++w) {
       const uint32_t wa = *reinterpret_cast<const uint32_t*>(crowA + w * 16);
@@ -257,7 +258,7 @@ attention_int_kernel(const int8_t* __restrict__ qkv, int8_t* __restrict__ out, i
     sumA += __shfl_xor_sync(0xffffffffu, sumA, 2);
     sumB += __shfl_xor_sync(0xffffffffu, sumB, 1);
     sumB += __shfl_xor_sync(0xffffffffu, sumB, 2);
-    const float fsumA = __ull2float_rn(sumA), fsumB = __ull2float_rn(sumB);
+    const float fsumA = __double2float_rn(sumA), fsumB = __double2float_rn(sumB);   // exact integer -> RNE, as u64 -> f32
     const float* lutRA = sm.lut_r3 + maxA;
     const float* lutRB = sm.lut_r3 + maxB;
 
