@@ -161,3 +161,43 @@ def test_gpu_calibration_kernels_reproduce_reference_scales(micro_golden, tiny_g
     bad = _scales_equal(tiny, tiny_golden)
     assert [b for b in bad if '/' not in b] == [], bad           # every activation quantizer matches exactly
     assert len(bad) <= 4, bad                                     # weight exponents: near-tie flips only
+
+
+def test_deit_base_and_mixed_precision_vs_oracle():
+    """D = 768 / 12 heads (DeiT-B, ViT-B): K = 768 takes the operand-streaming GEMM and the generic LayerNorm
+    path.  Calibrated on the GPU, compared with the CPU oracle on the same state for W8 and the published
+    4->8 layer-restore configuration (BASELINE config 4 index set).  Everything up to the first GELU is
+    bit-defined and must be identical; GELU outputs may differ by 1 LSB at rounding ties (device erff vs ATen's
+    CPU erf: the reference itself differs between CPU and GPU there), and such a flip then propagates through the
+    remaining blocks, so later layers and the logits are held to the allowance, not to equality."""
+    import diff_vit_b200 as dv
+    from diff_vit_b200.plan import extract_state
+    torch.manual_seed(0)
+    model = dv.deit_base_patch16_224(pretrained=False, cfg=dv.Config(True, True, 'minmax')).eval().cuda()
+    g = torch.Generator(device='cuda').manual_seed(3)
+    dv.calibrate_model(model, [torch.randn(4, 3, 224, 224, device='cuda', generator=g)])
+    x = torch.randn(3, 3, 224, 224, device='cuda', generator=g)
+    state = extract_state(model)
+    lsb = float(state['act']['act_out'][0])
+    restore = [4] * 50
+    for i in (3, 13, 16, 25):
+        restore[i] = 8
+    eng = model.integer_engine()
+    for bits in ([8] * 50, restore):
+        got, dump = eng.forward_dump(x, bits)
+        want, ref = orc.forward(state, x.cpu(), bits, capture=True)
+        exact = ['act/patch_embed.qact', 'act/qact1', 'ln/blocks.0.norm1', 'act/blocks.0.attn.qact0',
+                 'act/blocks.0.attn.qact1', 'act/blocks.0.attn.qact_attn1', 'softmax/blocks.0.attn.log_int_softmax',
+                 'act/blocks.0.attn.qact2', 'act/blocks.0.attn.qact3', 'act/blocks.0.qact2', 'ln/blocks.0.norm2',
+                 'act/blocks.0.mlp.qact0']
+        for k in exact:
+            r = ref[k].numpy().astype(np.int64)
+            np.testing.assert_array_equal(dump[k].astype(np.int64).reshape(r.shape), r, err_msg=k)
+        r = ref['act/blocks.0.mlp.qact1'].numpy().astype(np.int64)
+        d = np.abs(dump['act/blocks.0.mlp.qact1'].astype(np.int64).reshape(r.shape) - r)
+        assert d.max() <= 1 and (d != 0).mean() <= 1e-3
+        # later layers: a single GELU flip is amplified ~5-10x per stage by the random-init network (the same
+        # happens between the reference's own CPU and GPU runs), so only sanity is checked from here on; the
+        # D = 768 kernels are held to bit-exactness with identical inputs in tests/test_gpu_kernels.py
+        codes = got / lsb
+        assert torch.equal(codes, codes.round()) and codes.abs().max() <= 128 and got.std() > 0
