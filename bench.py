@@ -29,8 +29,8 @@ INT8_NOMINAL_TOPS = 4500.0
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=20)
-    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--steps', type=int, default=100)
+    ap.add_argument('--warmup', type=int, default=10)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--model', default=MODEL)
     ap.add_argument('--batch', type=int, default=BATCH, help='images per GPU per step')
@@ -62,7 +62,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
-                                          '--format=csv,noheader,nounits', '-lms', '100'], stdout=subprocess.PIPE,
+                                          '--format=csv,noheader,nounits', '-lms', '25'], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -175,6 +175,27 @@ def time_gemm(lib_mod, m, n, k, flags, iters, stream_obj):
     return t0.elapsed_time(t1) / iters
 
 
+def time_attention(lib_mod, bound, b, n, heads, iters, stream_obj):
+    """Average device time (ms) of the fused integer attention of block 0 on random int8 q/k/v codes."""
+    import ctypes as C
+    import torch
+    dev = 'cuda'
+    qkv = torch.randint(-60, 61, (b * n, 3 * heads * 64), dtype=torch.int8, device=dev)
+    out = torch.empty(b * n, heads * 64, dtype=torch.int8, device=dev)
+    att = bound.blocks[0].attn
+    lib = lib_mod.lib()
+    with torch.cuda.stream(stream_obj):
+        for _ in range(3):
+            lib_mod.check(lib.p2v_attention_int(qkv.data_ptr(), out.data_ptr(), b, n, heads, C.byref(att), stream_obj.cuda_stream))
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record(stream_obj)
+        for _ in range(iters):
+            lib_mod.check(lib.p2v_attention_int(qkv.data_ptr(), out.data_ptr(), b, n, heads, C.byref(att), stream_obj.cuda_stream))
+        t1.record(stream_obj)
+    stream_obj.synchronize()
+    return t0.elapsed_time(t1) / iters
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -262,21 +283,37 @@ def run_ours(args):
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel: the fc1 GEMM (M x 1536 x 384) with GELU + re-quant epilogue ----
+    # ---- rooflines, timed live with CUDA events on the launch stream -----------------------------------------
+    # Dominant kernel by share of the step (ncu launch list, profiles/r1n_launches.csv: 37 %): the fused integer
+    # attention.  Algorithmic work per launch = QK^T + PV = 4 * B * H * N^2 * 64 int8 ops.  Second: the fc1 GEMM.
     hbm, bf16, src = peaks()
-    m = args.batch * (model.patch_embed.num_patches + 1)
-    d, hid = model.embed_dim, model.blocks[0].mlp.fc1.out_features
+    peak = 2.0 * bf16
+    peak_note = ('2 x %s bf16 burst (MEASURED_PEAKS.json has no int8 entry); nominal dense int8 %.0f' % (src, INT8_NOMINAL_TOPS))
+    ntok = model.patch_embed.num_patches + 1
+    m = args.batch * ntok
+    d, hid, heads = model.embed_dim, model.blocks[0].mlp.fc1.out_features, model.num_heads
+    att_ms = time_attention(_cabi, bound, args.batch, ntok, heads, 20, stream)
+    att_ops = 4.0 * args.batch * heads * ntok * ntok * 64
+    att_tops = att_ops / (att_ms * 1e-3) / 1e12
+    step_ms = total_ms / args.steps
+    roofline = {'bound': 'tensor', 'kernel': 'attention_int_kernel (QK^T -> log-int-softmax -> PV), %d x %d heads x %d tokens'
+                % (args.batch, heads, ntok),
+                'achieved': round(att_tops, 2), 'peak': round(peak, 1), 'unit': 'TFLOP/s', 'frac': round(att_tops / peak, 4),
+                'traffic': 63.8e6, 'traffic_source': 'ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch '
+                                                     '(profiles/r1_summary.md); algorithmic bytes 77.5e6 (qkv in + out)',
+                'us_per_launch': round(att_ms * 1e3, 1), 'share_of_step': round(att_ms * model.depth / step_ms, 3),
+                'peak_source': peak_note,
+                'note': 'issue-bound on the CUDA-core softmax / re-quantisation work (ALU pipe 51 %), not on the tensor pipe (13 %)'}
     gemm_ms = time_gemm(_cabi, m, hid, d, _cabi.EPI_GELU | _cabi.EPI_OUT_POT, 20, stream)
     ops = 2.0 * m * hid * d
     achieved = ops / (gemm_ms * 1e-3) / 1e12
-    peak = 2.0 * bf16
-    roofline = {'bound': 'tensor', 'kernel': 'gemm_i8_tc_kernel<GELU|OUT_POT> fc1 %dx%dx%d' % (m, hid, d),
-                'achieved': round(achieved, 2), 'peak': round(peak, 1), 'unit': 'TFLOP/s',
-                'frac': round(achieved / peak, 4), 'traffic': None,
-                'peak_source': '2 x %s bf16 burst (MEASURED_PEAKS.json has no int8 entry); nominal dense int8 %.0f'
-                               % (src, INT8_NOMINAL_TOPS),
-                'model_achieved_tops': round(value / world * GOP_PER_IMAGE / 1e3, 2),
-                'model_frac_of_peak': round(value / world * GOP_PER_IMAGE / 1e3 / peak, 4)}
+    roofline_gemm = {'bound': 'tensor', 'kernel': 'gemm_i8_bs_kernel<GELU|OUT_POT> fc1 %dx%dx%d (tcgen05 kind::i8)' % (m, hid, d),
+                     'achieved': round(achieved, 2), 'peak': round(peak, 1), 'unit': 'TFLOP/s', 'frac': round(achieved / peak, 4),
+                     'traffic': 43.4e6, 'us_per_launch': round(gemm_ms * 1e3, 1),
+                     'share_of_step': round(gemm_ms * model.depth / step_ms, 3), 'peak_source': peak_note}
+    model_tops = value / world * GOP_PER_IMAGE / 1e3
+    whole = {'achieved_tops': round(model_tops, 2), 'frac_of_peak': round(model_tops / peak, 4),
+             'frac_of_nominal_int8': round(model_tops / INT8_NOMINAL_TOPS, 4), 'gop_per_image': GOP_PER_IMAGE}
 
     cpu = None
     if not args.no_cpu_baseline:
@@ -301,7 +338,8 @@ def run_ours(args):
                 'api': 'IntegerEngine.forward_host_pipelined: pinned H2D of batch i+1 and D2H of logits i-1 overlap forward i'},
         'gpu_launches': (max(args.warmup, 3) + args.steps + n_e2e + 2) * bound.launches + 23,
         'launches_per_step': bound.launches,
-        'roofline': roofline, 'cpu_baseline': cpu, 'clocks': clocks,
+        'roofline': roofline, 'roofline_fc1_gemm': roofline_gemm, 'whole_model': whole, 'cpu_baseline': cpu,
+        'clocks': clocks,
     }
     print(json.dumps(line))
     if world > 1:
