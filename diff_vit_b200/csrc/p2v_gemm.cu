@@ -77,9 +77,14 @@ __device__ __forceinline__ uint32_t pack_sat4(float v0, float v1, float v2, floa
 // is within 1.5 ulp(128) = 2.3e-5 of the exactly divided one, and the guard is 5x that.
 constexpr float kTieGuard = 0.0001220703125f;  // 2^-13
 __device__ __noinline__ float div_round_exact(float y, float s, float zp) { return rintf(fadd(fdiv(y, s), zp)); }
+
+// Round-half-even on the FMA pipe: (t + 1.5 * 2^23) - 1.5 * 2^23 is RNE(t) for |t| < 2^22.  Larger |t| come back
+// as some large value of the same sign, which saturates to the same int8 code as RNE(t) would.  (FRND runs on
+// the conversion unit, which ncu showed ~40 % busy in every GEMM epilogue.)
+__device__ __forceinline__ float rne_small(float t) { return fsub(fadd(t, 12582912.0f), 12582912.0f); }
 __device__ __forceinline__ float div_round(float y, float s, float rs, float zp) {
   const float t = fadd(fmul(y, rs), zp);
-  float r = rintf(t);
+  float r = rne_small(t);
   if (fabsf(fabsf(fsub(t, r)) - 0.5f) < kTieGuard) r = div_round_exact(y, s, zp);   // rare: keeps the hot loop small
   return r;
 }
@@ -92,7 +97,7 @@ __device__ __forceinline__ void div_round4(const float (&y)[4], const float (&s)
 #pragma unroll
   for (int e = 0; e < 4; ++e) {
     const float t = fadd(fmul(y[e], rs[e]), zp);
-    r[e] = rintf(t);
+    r[e] = rne_small(t);
     flags |= (fabsf(fabsf(fsub(t, r[e])) - 0.5f) < kTieGuard) ? (1u << e) : 0u;
   }
   if (flags) {
@@ -160,15 +165,19 @@ __device__ __forceinline__ void epilogue16(const uint32_t (&acc)[16], const floa
     }
     if (kFold) {
 #pragma unroll
-      for (int e = 0; e < 4; ++e) r4[e] = rintf(y4[e]);
+      for (int e = 0; e < 4; ++e) r4[e] = y4[e];                       // the saturating pack rounds half-even
     } else if (FLAGS & EPI_OUT_POT) {
 #pragma unroll
-      for (int e = 0; e < 4; ++e) r4[e] = rintf(fmul(y4[e], rso[e]));
+      for (int e = 0; e < 4; ++e) r4[e] = fmul(y4[e], rso[e]);         // idem
     } else {
       div_round4(y4, so, rso, g.epi.out_zp, r4);
     }
 #pragma unroll
-    for (int e = 0; e < 4; ++e) code[j4 + e] = (FLAGS & EPI_RESIDUAL) ? clamp_code(r4[e]) : r4[e];   // the pack saturates
+    for (int e = 0; e < 4; ++e) {
+      // residual variants need the integral, clamped branch code now; otherwise the saturating pack rounds
+      if ((FLAGS & EPI_RESIDUAL) && (FLAGS & EPI_OUT_POT)) r4[e] = rne_small(r4[e]);
+      code[j4 + e] = (FLAGS & EPI_RESIDUAL) ? clamp_code(r4[e]) : r4[e];
+    }
     if (FLAGS & EPI_RESIDUAL) {
       const float4 SR = *reinterpret_cast<const float4*>(&ch[CH_SR][c + j4]);
       const float4 R2 = *reinterpret_cast<const float4*>(&ch[CH_RSO2][c + j4]);
@@ -201,7 +210,7 @@ __device__ __forceinline__ void epilogue16(const uint32_t (&acc)[16], const floa
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
       if (j < ncols) {
-        const float q = clamp_code(code[j]);
+        const float q = clamp_code(rintf(code[j]));
         g.epi.out_f32[(int64_t)row * g.n + col0 + j] = fmul(fsub(q, g.epi.out_zp), ch[CH_SO][c + j]);
       }
     }
@@ -215,7 +224,7 @@ __device__ __forceinline__ void epilogue16(const uint32_t (&acc)[16], const floa
   } else {
 #pragma unroll
     for (int j = 0; j < 16; ++j)
-      if (j < ncols) g.out[off + j] = (int8_t)clamp_code(code[j]);
+      if (j < ncols) g.out[off + j] = (int8_t)clamp_code(rintf(code[j]));
   }
 }
 
