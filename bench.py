@@ -335,7 +335,7 @@ def run_ours(args):
                    'calibration': 'randn(%d,3,224,224), %.1f s, excluded' % (args.calib_batch, calib_s)},
         'e2e': {'value': round(e2e_value, 1), 'unit': 'images/s', 'h2d_bytes_per_step': in_bytes,
                 'd2h_bytes_per_step': logits_host.numel() * 4, 'steps': n_e2e,
-                'api': 'IntegerEngine.forward_host_pipelined: pinned H2D of batch i+1 and D2H of logits i-1 overlap forward i'},
+                'api': 'IntegerEngine.forward_host_pipelined: pinned H2D of batch i+1 and D2H of logits i-1 overlap forward i (own streams)'},
         'gpu_launches': (max(args.warmup, 3) + args.steps + n_e2e + 2) * bound.launches + 23,
         'launches_per_step': bound.launches,
         'roofline': roofline, 'roofline_fc1_gemm': roofline_gemm, 'whole_model': whole, 'cpu_baseline': cpu,

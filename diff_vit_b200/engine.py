@@ -213,30 +213,35 @@ class IntegerEngine:
         stream, CUDA events).  `batches_host[i]` -> `logits_host[i]`; returns after everything has landed."""
         bp = self.bound(bit_config)
         comp = torch.cuda.current_stream(self.device)
-        if not hasattr(self, '_copy_stream'):
-            self._copy_stream = torch.cuda.Stream(self.device)
-        copy = self._copy_stream
+        if not hasattr(self, '_io_streams'):
+            self._io_streams = (torch.cuda.Stream(self.device), torch.cuda.Stream(self.device))
+        h2d, d2h = self._io_streams        # separate queues: an upload never waits behind a download
         b = batches_host[0].shape[0]
         key = ('xpipe', b)
         if key not in bp._buffers:
             bp._buffers[key] = ([torch.empty(batches_host[0].shape, dtype=torch.float32, device=self.device) for _ in range(2)],
-                                [torch.cuda.Event() for _ in range(2)], [torch.cuda.Event() for _ in range(2)])
-        xdev, ev_in, ev_done = bp._buffers[key]
-        copy.wait_stream(comp)
+                                [[torch.cuda.Event() for _ in range(2)] for _ in range(3)])
+        xdev, (ev_in, ev_done, ev_out) = bp._buffers[key]
+        h2d.wait_stream(comp)
+        d2h.wait_stream(comp)
         for i, xh in enumerate(batches_host):
             slot = i & 1
-            with torch.cuda.stream(copy):
+            with torch.cuda.stream(h2d):
                 if i >= 2:
-                    copy.wait_event(ev_done[slot])          # the forward that read this input buffer has finished
+                    h2d.wait_event(ev_done[slot])           # the forward that read this input buffer has finished
                 xdev[slot].copy_(xh, non_blocking=True)
-                ev_in[slot].record(copy)
+                ev_in[slot].record(h2d)
             comp.wait_event(ev_in[slot])
+            if i >= 2:
+                comp.wait_event(ev_out[slot])               # the logits of batch i-2 have left their buffer
             logits = self.forward_into(xdev[slot], bit_config, slot=slot + 1)
             ev_done[slot].record(comp)
-            with torch.cuda.stream(copy):
-                copy.wait_event(ev_done[slot])
+            with torch.cuda.stream(d2h):
+                d2h.wait_event(ev_done[slot])
                 logits_host[i].copy_(logits, non_blocking=True)
-        copy.synchronize()
+                ev_out[slot].record(d2h)
+        h2d.synchronize()
+        d2h.synchronize()
         comp.synchronize()
         return logits_host
 
