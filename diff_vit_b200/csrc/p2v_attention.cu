@@ -100,7 +100,7 @@ struct AttSmem {
 
 // One CTA = one (image, head): K and V are staged once, each of the 7 warps walks 16-row query tiles.
 #ifndef P2V_ATT_MIN_CTAS
-#define P2V_ATT_MIN_CTAS 2
+#define P2V_ATT_MIN_CTAS 3
 #endif
 template <bool kDump>
 __global__ void __launch_bounds__(kAttWarps * 32, P2V_ATT_MIN_CTAS)
@@ -265,11 +265,15 @@ attention_int_kernel(const int8_t* __restrict__ qkv, int8_t* __restrict__ out, i
     // ---- log2 codes -> two u8 probability planes -> P V ------------------------------------------------------
     int8_t* dsc = kDump ? p.dump_scores + ((int64_t)bh * n) * n : nullptr;
     uint8_t* dsm = kDump ? p.dump_softmax + ((int64_t)bh * n) * n : nullptr;
-    int hi[8][4], lo[8][4];
+    // One accumulator set for both probability planes: the first sweep multiplies the high-byte plane and
+    // parks the low-byte plane in shared memory over the (now consumed) score codes; the accumulators are then
+    // scaled by 2^8 and a second sweep adds the low-byte plane.  32 instead of 64 accumulator registers per
+    // thread lets three CTAs share an SM.
+    int acc[8][4];
 #pragma unroll
     for (int jn = 0; jn < 8; ++jn)
 #pragma unroll
-      for (int e = 0; e < 4; ++e) { hi[jn][e] = 0; lo[jn][e] = 0; }
+      for (int e = 0; e < 4; ++e) acc[jn][e] = 0;
 
 #pragma unroll 1
     for (int s = 0; s < nsteps; ++s) {
@@ -322,8 +326,28 @@ attention_int_kernel(const int8_t* __restrict__ qkv, int8_t* __restrict__ out, i
       for (int jn = 0; jn < 8; ++jn) {
         const uint8_t* vp = sm.Vt + (jn * 8 + g) * kVtStride + s * 32 + t * 4;
         const uint32_t b0 = *reinterpret_cast<const uint32_t*>(vp), b1 = *reinterpret_cast<const uint32_t*>(vp + 16);
-        mma_u8s8(hi[jn], pa_hi[0], pa_hi[1], pa_hi[2], pa_hi[3], b0, b1);
-        mma_u8s8(lo[jn], pa_lo[0], pa_lo[1], pa_lo[2], pa_lo[3], b0, b1);
+        mma_u8s8(acc[jn], pa_hi[0], pa_hi[1], pa_hi[2], pa_hi[3], b0, b1);
+      }
+      // this thread wrote these four code words and is their only reader: overwrite them with the low plane
+      *reinterpret_cast<uint32_t*>(crowA + (2 * s) * 16) = pa_lo[0];
+      *reinterpret_cast<uint32_t*>(crowB + (2 * s) * 16) = pa_lo[1];
+      *reinterpret_cast<uint32_t*>(crowA + (2 * s + 1) * 16) = pa_lo[2];
+      *reinterpret_cast<uint32_t*>(crowB + (2 * s + 1) * 16) = pa_lo[3];
+    }
+#pragma unroll
+    for (int jn = 0; jn < 8; ++jn)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[jn][e] <<= 8;
+#pragma unroll 1
+    for (int s = 0; s < nsteps; ++s) {
+      const uint32_t l0 = *reinterpret_cast<const uint32_t*>(crowA + (2 * s) * 16);
+      const uint32_t l1 = *reinterpret_cast<const uint32_t*>(crowB + (2 * s) * 16);
+      const uint32_t l2 = *reinterpret_cast<const uint32_t*>(crowA + (2 * s + 1) * 16);
+      const uint32_t l3 = *reinterpret_cast<const uint32_t*>(crowB + (2 * s + 1) * 16);
+#pragma unroll
+      for (int jn = 0; jn < 8; ++jn) {
+        const uint8_t* vp = sm.Vt + (jn * 8 + g) * kVtStride + s * 32 + t * 4;
+        mma_u8s8(acc[jn], l0, l1, l2, l3, *reinterpret_cast<const uint32_t*>(vp), *reinterpret_cast<const uint32_t*>(vp + 16));
       }
     }
 
@@ -333,13 +357,13 @@ attention_int_kernel(const int8_t* __restrict__ qkv, int8_t* __restrict__ out, i
       int q[4];
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        const int acc = hi[jn][e] * 256 + lo[jn][e];
+        const int a = acc[jn][e];
         if (out_shift > 0) {
           // RNE(acc / 2^sh) in integers: add half minus one plus the parity of the truncated result
-          const int r = (acc + ((1 << (out_shift - 1)) - 1) + ((acc >> out_shift) & 1)) >> out_shift;
+          const int r = (a + ((1 << (out_shift - 1)) - 1) + ((a >> out_shift) & 1)) >> out_shift;
           q[e] = min(max(r + izp, -128), 127);
         } else {
-          const double v = rint((double)acc * p.out_mul) + (double)p.out_zp;
+          const double v = rint((double)a * p.out_mul) + (double)p.out_zp;
           q[e] = (int)fmin(fmax(v, -128.0), 127.0);
         }
       }
