@@ -11,7 +11,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libp2vit_b200.so')
-SOURCES = ['p2v_engine.cu', 'p2v_gemm.cu', 'p2v_rowops.cu', 'p2v_attention.cu', 'p2v_observe.cu']
+SOURCES = ['p2v_engine.cu', 'p2v_gemm.cu', 'p2v_rowops.cu', 'p2v_attention.cu', 'p2v_observe.cu',
+           'p2v_modules.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '--expt-relaxed-constexpr', '-Xcompiler', '-fPIC', '-Xptxas', '-v']
 

@@ -44,6 +44,12 @@ def reduce_min_(t):
     return t
 
 
+def reduce_sum_(t):
+    if is_active():
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=_GROUP)
+    return t
+
+
 def global_mean(sq_err, dims=None):
     """Mean of `sq_err` over `dims` (all dims when None) across every rank: SUM all-reduce of the local
     sums (accumulated in fp64 so that the arg-min over candidate scales agrees with the single-process

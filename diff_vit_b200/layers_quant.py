@@ -58,6 +58,16 @@ class SmoothQuantState:
     the candidate losses it computes therefore never influence the result and are not evaluated here.
     """
 
+    FIELDS = ('channel_scale', 'best_scale', 'best_act_scale', 'best_act_zp', 'best_weight_scale', 'best_weight_zp')
+
+    @staticmethod
+    def move(owner, fn):
+        """Carry the owner's SmoothQuant state through a Module._apply (model.cuda(), model.to(...))."""
+        from .ptq.quantizer.core import map_state
+        for name in SmoothQuantState.FIELDS:
+            if getattr(owner, name, None) is not None:
+                setattr(owner, name, map_state(fn, getattr(owner, name)))
+
     @staticmethod
     def channel_scale(x, weight, alpha):
         """PoT-rounded max|x|_c^alpha / max|W|_c^(1-alpha) (per input channel)."""
@@ -137,6 +147,11 @@ class Mlp(nn.Module):
         self.drop = nn.Dropout(drop)
         self.channel_scale = None
         self.fc1_output = None
+
+    def _apply(self, fn, *args, **kwargs):
+        super()._apply(fn, *args, **kwargs)
+        SmoothQuantState.move(self, fn)
+        return self
 
     def forward(self, x, FLOPs, global_distance, ffn_bit_config, plot=False, quant=True, smoothquant=True,
                 activation=[], hessian_statistic=False):

@@ -4,6 +4,7 @@ import numpy as np
 import torch
 
 from ... import dist as _dist
+from . import gpu_stats
 from .base import BaseObserver
 
 
@@ -59,19 +60,24 @@ class PercentileObserver(BaseObserver):
 
     def update(self, v):
         assert self.calibration_mode == 'layer_wise'
-        if _dist.is_active():
-            raise NotImplementedError('data-parallel percentile calibration needs an exact distributed order '
-                                      'statistic (all-gather of the tail candidates); calibrate on one rank')
         flat = self.reshape_tensor(v).reshape(-1)
-        try:
-            cur_max = torch.quantile(flat, self.percentile_alpha)
-            cur_min = torch.quantile(flat, 1.0 - self.percentile_alpha)
-        except RuntimeError:  # torch.quantile refuses > 16M elements
-            host = flat.cpu()
-            cur_max = torch.tensor(np.percentile(host, self.percentile_alpha * 100),
-                                   device=v.device, dtype=torch.float32)
-            cur_min = torch.tensor(np.percentile(host, (1 - self.percentile_alpha) * 100),
-                                   device=v.device, dtype=torch.float32)
+        if _dist.is_active() or gpu_stats.usable(flat):
+            # exact radix select in the sm_100a histogram kernel (summed over ranks when calibrating
+            # data-parallel) instead of a full sort; same interpolation as the reference's call
+            total = flat.numel()
+            if _dist.is_active():
+                total = int(_dist.reduce_sum_(torch.tensor([total], dtype=torch.int64, device=flat.device)))
+            cur_max, cur_min = gpu_stats.quantile_pair(flat, self.percentile_alpha, total)
+        else:
+            try:
+                cur_max = torch.quantile(flat, self.percentile_alpha)
+                cur_min = torch.quantile(flat, 1.0 - self.percentile_alpha)
+            except RuntimeError:  # torch.quantile refuses > 16M elements
+                host = flat.cpu()
+                cur_max = torch.tensor(np.percentile(host, self.percentile_alpha * 100),
+                                       device=v.device, dtype=torch.float32)
+                cur_min = torch.tensor(np.percentile(host, (1 - self.percentile_alpha) * 100),
+                                       device=v.device, dtype=torch.float32)
         if self.max_val is None:
             self.max_val, self.min_val = cur_max, cur_min
         else:

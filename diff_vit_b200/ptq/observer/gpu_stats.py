@@ -69,3 +69,81 @@ def first_argmin_mean(sums, count):
         best = torch.where(better, score[k], best)
         choice = torch.where(better, torch.full_like(choice, float(k)), choice)
     return choice
+
+
+# ---- exact order statistics (percentile observer) -------------------------------------------------------
+_SELECT_PASSES = (21, 10, 0)   # 11-bit digits of the 32-bit order-preserving key, most significant first
+_SELECT_BINS = 2048
+
+
+def _digit_histogram(flat, prefix, mask, shift):
+    """int64[2048] histogram of key bits [shift, shift+11) over the elements matching prefix under mask."""
+    if flat.is_cuda:
+        from ... import _cabi
+        hist = torch.zeros(_SELECT_BINS, dtype=torch.int64, device=flat.device)
+        _cabi.check(_cabi.lib().p2v_select_histogram(flat.data_ptr(), flat.numel(), prefix, mask, shift,
+                                                    hist.data_ptr(), _stream()))
+        return hist
+    # CPU tensors (gloo runs, unit tests): the same digit histogram with torch ops
+    bits = flat.view(torch.int32).to(torch.int64) & 0xffffffff
+    key = torch.where(bits >= 0x80000000, bits ^ 0xffffffff, bits | 0x80000000)
+    sel = key[(key & mask) == prefix]
+    return torch.bincount((sel >> shift) & (_SELECT_BINS - 1), minlength=_SELECT_BINS)
+
+
+def order_statistics(x, ranks):
+    """Exact ascending order statistics x_(r), r 0-based, of a fp32 tensor; under data-parallel calibration
+    the ranks refer to the union of every process's shard (digit histograms are summed over the group).
+    Three streaming passes per requested rank; replaces the full sort behind torch.quantile / np.percentile
+    (models/ptq/observer/percentile.py:27-38)."""
+    from ... import dist as _dist
+    flat = x.detach().contiguous().reshape(-1).float()
+    out = []
+    for r in ranks:
+        prefix = mask = 0
+        remaining = int(r)
+        for shift in _SELECT_PASSES:
+            hist = _digit_histogram(flat, prefix, mask, shift)
+            if _dist.is_active():
+                import torch.distributed as tdist
+                tdist.all_reduce(hist, op=tdist.ReduceOp.SUM, group=_dist._GROUP)
+            cum = torch.cumsum(hist.cpu(), 0)
+            b = int(torch.searchsorted(cum, torch.tensor(remaining), right=True))
+            if b >= _SELECT_BINS:
+                raise IndexError('order statistic %d is beyond the %d elements observed' % (r, int(cum[-1])))
+            if b > 0:
+                remaining -= int(cum[b - 1])
+            prefix |= b << shift
+            mask |= ((_SELECT_BINS - 1) << shift) & 0xffffffff
+        bits = prefix ^ 0x80000000 if prefix & 0x80000000 else prefix ^ 0xffffffff
+        out.append(torch.tensor([bits], dtype=torch.int64).to(torch.int32).view(torch.float32)[0])
+    return torch.stack(out).to(x.device)
+
+
+def quantile_pair(x, alpha, total):
+    """(quantile(alpha), quantile(1 - alpha)) over `total` elements (all ranks) with the interpolation rules of
+    the call the reference would have made: torch.quantile up to 16M elements, np.percentile beyond
+    (percentile.py:27-38).  Only the two neighbouring order statistics of each are ever materialised."""
+    import numpy as np
+    res = []
+    for q in (alpha, 1.0 - alpha):
+        if total <= 16_000_000:
+            # ATen quantile: ranks = q * (n - 1) in the tensor dtype, lerp(below, above, frac)
+            pos = torch.tensor(q, dtype=torch.float32) * (total - 1)
+            lo, hi = int(pos.floor()), int(pos.ceil())
+            v = order_statistics(x, [lo, hi])
+            res.append(torch.lerp(v[0], v[1], (pos - pos.floor()).to(v.device)))
+        else:
+            # numpy 'linear' method on a float32 array: the quantile and the virtual index follow numpy's promotion
+            qq = np.asanyarray(np.true_divide(q * 100, np.float32(100)))
+            vi = np.asanyarray((total - 1) * qq)
+            lo = int(np.floor(vi))
+            hi = min(lo + 1, total - 1)
+            v = order_statistics(x, [lo, hi]).cpu().numpy()
+            gamma = np.asanyarray(vi - lo, dtype=vi.dtype)
+            diff = np.subtract(v[1], v[0])
+            val = np.add(v[0], diff * gamma)
+            if gamma >= 0.5:
+                val = np.subtract(v[1], diff * (1 - gamma))
+            res.append(torch.tensor(val, device=x.device, dtype=torch.float32))
+    return res[0], res[1]

@@ -18,6 +18,19 @@ _PARAM_SHAPE = {
 }
 
 
+def map_state(fn, value):
+    """Apply a Module._apply function (device / dtype move) to calibration state held as plain tensors,
+    or as lists / dicts of them.  Integer tensors (zero points) only change device."""
+    if isinstance(value, torch.Tensor):
+        moved = fn(value)
+        return moved if value.is_floating_point() else value.to(moved.device)
+    if isinstance(value, list):
+        return [map_state(fn, v) for v in value]
+    if isinstance(value, dict):
+        return {k: map_state(fn, v) for k, v in value.items()}
+    return value
+
+
 class BaseQuantizer(nn.Module):
 
     def __init__(self, bit_type, observer, module_type):
@@ -55,6 +68,13 @@ class UniformQuantizer(BaseQuantizer):
     @property
     def _is_act(self):
         return self.module_type == 'activation'
+
+    def _apply(self, fn, *args, **kwargs):
+        """The calibrated pairs are plain attributes (as in the reference); make them follow .cuda()/.to()."""
+        super()._apply(fn, *args, **kwargs)
+        for name in ('scale', 'zero_point', 'dic_scale', 'dic_zero_point'):
+            setattr(self, name, map_state(fn, getattr(self, name)))
+        return self
 
     def update_quantization_params(self, *args, **kwargs):
         scale, zero_point = self.observer.get_quantization_params(*args, **kwargs)

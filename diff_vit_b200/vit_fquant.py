@@ -12,6 +12,7 @@ from functools import partial
 
 import torch
 from torch import nn
+from torch.nn.modules import module as _module_globals
 
 from .layers_quant import DropPath, Mlp, PatchEmbed, SmoothQuantState, trunc_normal_
 from .ptq import QAct, QConv2d, QIntLayerNorm, QIntSoftmax, QLinear
@@ -62,6 +63,11 @@ class Attention(nn.Module):
                                            observer_str=cfg.OBSERVER_S, quantizer_str=cfg.QUANTIZER_S)
         self.channel_scale = None
         self.qkv_output = None
+
+    def _apply(self, fn, *args, **kwargs):
+        super()._apply(fn, *args, **kwargs)
+        SmoothQuantState.move(self, fn)
+        return self
 
     def forward(self, x, FLOPs, global_distance, atten_bit_config, plot=False, quant=False, smoothquant=True,
                 hessian_statistic=False):
@@ -189,6 +195,8 @@ class VisionTransformer(nn.Module):
         trunc_normal_(self.cls_token, std=0.02)
         self.apply(self._init_weights)
         self._engine = None
+        self._submodules = None
+        self.per_module = False   # True: run every Q-module's own forward even when the fused engine could
 
     def _init_weights(self, m):
         if isinstance(m, nn.Linear):
@@ -280,8 +288,20 @@ class VisionTransformer(nn.Module):
             self._engine = IntegerEngine(self)
         return self._engine
 
+    def _hooked(self):
+        """True when somebody listens on a submodule (forward hooks of cka_utility.py:39-66 /
+        modeldiff_p2.py:50-82) or asked for per-module execution: those callers need every Q-module's own
+        forward to run, which the fused engine skips."""
+        if self.per_module:
+            return True
+        if self._submodules is None:
+            self._submodules = [m for m in self.modules() if m is not self]
+        if _module_globals._global_forward_hooks or _module_globals._global_forward_pre_hooks:
+            return True
+        return any(m._forward_hooks or m._forward_pre_hooks for m in self._submodules)
+
     def forward(self, x, bit_config=None, plot=False, hessian_statistic=False):
-        if self.quant and not hessian_statistic and self._integer_path(bit_config):
+        if self.quant and not hessian_statistic and self._integer_path(bit_config) and not self._hooked():
             logits = self.integer_engine().forward(x, bit_config)
             return logits, self.flops(), []
         FLOPs, global_distance = [], []

@@ -137,6 +137,31 @@ int p2v_attention_int(const int8_t* qkv, int8_t* out, int b, int n, int heads, c
 int p2v_fake_quant_f32(const float* x, float* out, int8_t* codes, int64_t outer, int channels, int64_t inner,
                        const float* scale, const float* zero_point, int qmin, int qmax, void* stream);
 
+/* ---- the operators on their own, fp32 in / fp32 out (module-level use) -------------------------------- */
+/* QIntLayerNorm.forward in mode 'int' (models/ptq/layers.py:255-289) on dequantized fp32 rows x [rows, d]:
+ * x_q = RNE(x / in_scale[c]) * in_mask[c] with in_mask = RNE(in_scale / in_scale1), in_scale1 = min(in_scale);
+ * integer row statistics; dyadic (M, N) affine; out = code * out_scale[c].  *overflow_flag (device int, pre-set
+ * to 0) becomes 1 if some |x_q| >= 2^20, i.e. the input was not on the in_scale grid. */
+int p2v_layernorm_int_f32(const float* x, float* out, int64_t rows, int d, const float* in_scale,
+                          const float* in_mask, float in_scale1, const float* gamma, const float* beta,
+                          const float* out_scale, int* overflow_flag, void* stream);
+/* QIntSoftmax.forward with log_i_softmax (models/ptq/layers.py:323-376) over the last dimension of x [rows, n]:
+ * I-BERT integer exp with the constants (x0_int, b_int, c_int) of layers.py:334-352 and n = exp_bits, exact row
+ * sum, k = log_round(RNE(sum / exp)).  out (optional) = 2^-k, 0 where k >= levels; codes (optional) = min(k, levels). */
+int p2v_softmax_log_int_f32(const float* x, float* out, uint8_t* codes, int64_t rows, int n, float scale,
+                            float x0_int, float b_int, float c_int, int exp_bits, int levels, void* stream);
+/* QAct applied to a sum of code tensors (the residual adds of models/vit_fquant.py:449,466):
+ * out = clamp(RNE((a * a_scale[c] + b * b_scale[c]) / out_scale[c] + out_zp), -128, 127); b may be NULL (re-quantize a). */
+int p2v_requant_eltwise(const int8_t* a, const int8_t* b, int8_t* out, int64_t rows, int d, const float* a_scale,
+                        const float* b_scale, const float* out_scale, float out_zp, void* stream);
+/* One pass of an exact radix select over fp32 data (the order statistics behind torch.quantile / np.percentile in
+ * models/ptq/observer/percentile.py:27-38): hist[2048] (device, uint64, ACCUMULATED) counts bits
+ * [shift, shift + 11) of the order-preserving key of every element whose key matches prefix under prefix_mask.
+ * key(v) = bits(v) ^ (v < 0 ? 0xffffffff : 0x80000000).  Histograms from several ranks add up, which makes the
+ * select exact across a data-parallel calibration batch. */
+int p2v_select_histogram(const float* x, int64_t total, uint32_t prefix, uint32_t prefix_mask, int shift,
+                         unsigned long long* hist, void* stream);
+
 /* ---- calibration statistics ------------------------------------------------------- */
 /* Running range of an activation: x is fp32 [rows, channels]; per_channel = 0 reduces the whole tensor to
  * out_min[0] / out_max[0], per_channel = 1 gives one pair per (contiguous, innermost) channel.  The outputs are

@@ -54,7 +54,19 @@ def _worker(rank, world, port, ret):
                 return data, [], []
         top1, top5, n = dvd.validate(Fake(), [(mine, dvd.shard(target))], [8])
         ref1, ref5 = dvd.accuracy(logits, target, topk=(1, 5))
-        ret[rank] = (len(scales), bad, ok_gather, abs(top1 - float(ref1)) < 1e-9 and abs(top5 - float(ref5)) < 1e-9, n)
+        # percentile observer: the exact distributed order statistic equals torch.quantile on the whole batch
+        from diff_vit_b200.ptq.observer import build_observer
+        from diff_vit_b200.ptq.bit_type import BIT_TYPE_DICT
+        act = torch.randn(6, 50, 128, generator=g) * 3
+        whole = build_observer('percentile', 'activation', BIT_TYPE_DICT['int8'], 'layer_wise')
+        whole.update(act)
+        with dvd.calibration_group():
+            part = build_observer('percentile', 'activation', BIT_TYPE_DICT['int8'], 'layer_wise')
+            part.update(dvd.shard(act))
+        ok_pct = (float(part.max_val) == float(whole.max_val) and float(part.min_val) == float(whole.min_val)
+                  and float(whole.max_val) == float(torch.quantile(act.reshape(-1), 0.99999)))
+        ret[rank] = (len(scales), bad, ok_gather, abs(top1 - float(ref1)) < 1e-9 and abs(top5 - float(ref5)) < 1e-9, n,
+                     ok_pct)
     finally:
         dist.destroy_process_group()
 
@@ -66,10 +78,26 @@ def test_two_rank_calibration_matches_single_process_and_reference():
     ret = mgr.dict()
     mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
     for rank in range(world):
-        count, bad, ok_gather, ok_acc, n = ret[rank]
+        count, bad, ok_gather, ok_acc, n, ok_pct = ret[rank]
+        assert ok_pct, 'sharded percentile calibration differs from the single-process quantile'
         assert count == 71
         assert bad == [], 'rank %d: parameters differ from the single-process reference calibration: %s' % (rank, bad[:5])
         assert ok_gather and ok_acc and n == 8
+
+
+def test_order_statistics_exact_on_cpu():
+    """The radix select behind the percentile observer (torch path of the digit histogram)."""
+    from diff_vit_b200.ptq.observer import gpu_stats
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(100003, generator=g) * 5
+    x[:4] = torch.tensor([0.0, -0.0, 1e-30, -1e-30])
+    ref = torch.sort(x).values
+    ranks = [0, 1, 2, 50001, 100002, 100001]
+    assert torch.equal(gpu_stats.order_statistics(x, ranks), ref[ranks])
+    hi, lo = gpu_stats.quantile_pair(x, 0.99999, x.numel())
+    assert float(hi) == float(torch.quantile(x, 0.99999)) and float(lo) == float(torch.quantile(x, 1 - 0.99999))
+    with pytest.raises(IndexError):
+        gpu_stats.order_statistics(x, [x.numel()])
 
 
 def test_shard_covers_batch():
