@@ -29,7 +29,7 @@ constexpr int kAttWarps = 7;
 constexpr int kAttRows = kAttWarps * 16;  // 112 query rows per CTA
 constexpr int kMaxKeys = 224;      // keys padded to a multiple of 32
 constexpr int kMaxTiles = kMaxKeys / 8;
-constexpr int kQKStride = 80;      // bytes per Q/K row in smem (64 + pad, conflict-free fragment loads)
+constexpr int kKStride = 64;       // bytes per K row in smem; the 16 words of a row are stored t-major (see stage K)
 constexpr int kVtStride = 240;     // bytes per V^T row in smem (224 + pad)
 
 __device__ __forceinline__ void mma_s8s8(int (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
@@ -37,6 +37,25 @@ __device__ __forceinline__ void mma_s8s8(int (&c)[4], const uint32_t (&a)[4], ui
       "mma.sync.aligned.m16n8k32.row.col.s32.s8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
       : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// D = A B + C with C a broadcast constant kept in its own registers (the scores start from a bias, see below)
+__device__ __forceinline__ void mma_s8s8_init(int (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1, int c) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k32.row.col.s32.s8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
+      : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1), "r"(c));
+}
+// RNE + unsigned saturation of two floats into bytes 0 and 1, `upper`'s low half into bytes 2 and 3
+__device__ __forceinline__ uint32_t pack2_u8(float lo, float hi, uint32_t upper) {
+  uint32_t r;
+  const int a = __float2int_rn(hi), b = __float2int_rn(lo);
+  asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(upper));
+  return r;
+}
+__device__ __forceinline__ uint32_t pack2_s8(int lo, int hi) {
+  uint32_t r;
+  asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(hi), "r"(lo), "r"(0));
+  return r;
 }
 __device__ __forceinline__ void mma_u8s8(int (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
                                          uint32_t b0, uint32_t b1) {
@@ -75,13 +94,13 @@ __device__ __forceinline__ bool code_guarded(uint32_t bits) {
 }
 
 // four keys of one packed code word -> four 16-bit probabilities; returns true if any element needs the
-// exact path.  lutR = lut_r3 + rowmax (biased), so the table is addressed by the code byte directly.
-__device__ __forceinline__ bool prob16x4(uint32_t w, const float* lutR, float fsum, uint32_t (&v)[4], uint32_t (&bits)[4]) {
+// exact path.  revR = rev_r3 + (255 - rowmax) (biased), so the table is addressed by the code byte directly.
+__device__ __forceinline__ bool prob16x4(uint32_t w, const float* revR, float fsum, uint32_t (&v)[4], uint32_t (&bits)[4]) {
   bool any = false;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const uint32_t byte = __byte_perm(w, 0, 0x4440 + i);
-    bits[i] = __float_as_uint(__fmaf_rn(fsum, *(lutR - (int)byte), 0.16666667f));
+    bits[i] = __float_as_uint(__fmaf_rn(fsum, revR[byte], 0.16666667f));
     any |= code_guarded(bits[i]);
     // 1 << (15 - k), k = E - 125: shift counts >= 32 (k >= 16, or the wrapped negative) give 0
     asm("shl.b32 %0, %1, %2;" : "=r"(v[i]) : "r"(1u), "r"(140u - (bits[i] >> 23)));
@@ -90,19 +109,23 @@ __device__ __forceinline__ bool prob16x4(uint32_t w, const float* lutR, float fs
 }
 
 struct AttSmem {
-  alignas(16) uint8_t Ks[kMaxKeys * kQKStride];
+  alignas(16) uint8_t Ks[kMaxKeys * kKStride];
   alignas(16) uint8_t Vt[kHd * kVtStride];
   alignas(16) uint8_t codes[kAttWarps][16 * kVtStride];   // biased score codes in AV key order, per warp
-  float lut_f[256];
-  float lut_r3[256];
-  double lut_d[256];   // the integer exp as fp64 (exact): row sums of <= 224 terms < 2^51 stay exact in fp64
+  float lut_f[256];    // e(d), d = rowmax - code (exact path)
+  // the two tables of the hot loops are stored reversed (entry 255 - d), so that with the per-row base
+  // rev + (255 - rowmax) they are addressed by the biased code byte itself: one LEA per lookup
+  float rev_r3[256];   // 1 / (3 e(d))
+  double rev_d[256];   // e(d) as fp64 (exact): row sums of <= 224 terms < 2^51 stay exact in fp64
 };
 
 // One CTA = one (image, head): K and V are staged once, each of the 7 warps walks 16-row query tiles.
 #ifndef P2V_ATT_MIN_CTAS
 #define P2V_ATT_MIN_CTAS 3
 #endif
-template <bool kDump>
+// kPot: the score multiplier is a power of two (every minmax-calibrated model), which lets the int32 -> fp32
+// conversion of the scores ride on the accumulator (see the score loop).
+template <bool kDump, bool kPot>
 __global__ void __launch_bounds__(kAttWarps * 32, P2V_ATT_MIN_CTAS)
 attention_int_kernel(const int8_t* __restrict__ qkv, int8_t* __restrict__ out, int n, int heads,
                      const p2v_attention p, int out_shift) {
@@ -122,14 +145,20 @@ attention_int_kernel(const int8_t* __restrict__ qkv, int8_t* __restrict__ out, i
   for (int i = tid; i < 256; i += blockDim.x) {
     const float e = p.exp_lut[i];
     sm.lut_f[i] = e;
-    sm.lut_r3[i] = __fdiv_rn(1.0f, 3.0f * e);   // 3e is exact (<= 24 significant bits)
-    sm.lut_d[i] = (double)e;
+    sm.rev_r3[255 - i] = __fdiv_rn(1.0f, 3.0f * e);   // 3e is exact (<= 24 significant bits)
+    sm.rev_d[255 - i] = (double)e;
   }
+  // K rows with their 16 words stored t-major: word w (columns 4w .. 4w+3) goes to slot (w & 3) * 4 + (w >> 2), so
+  // the four B-fragment words of lane t (columns 4t, 16 + 4t, 32 + 4t, 48 + 4t) are one 16-byte load
   for (int i = tid; i < nkp * 4; i += blockDim.x) {
     const int j = i >> 2, part = i & 3;
     uint4 v = make_uint4(0, 0, 0, 0);
     if (j < n) v = __ldg(reinterpret_cast<const uint4*>(base + j * row_stride + (heads + head) * kHd) + part);
-    *reinterpret_cast<uint4*>(sm.Ks + j * kQKStride + part * 16) = v;
+    uint32_t* dst = reinterpret_cast<uint32_t*>(sm.Ks + j * kKStride) + part;
+    dst[0] = v.x;
+    dst[4] = v.y;
+    dst[8] = v.z;
+    dst[12] = v.w;
   }
   // V^T with the key permutation of the AV product: 4 consecutive positions kappa = 16h + 4t + {0,1,2,3}
   // hold keys {j0, j0+1, j0+8, j0+9}, j0 = 32s + 16h + 2t.  One thread transposes a 4-key x 4-channel
@@ -166,8 +195,11 @@ attention_int_kernel(const int8_t* __restrict__ qkv, int8_t* __restrict__ out, i
   const int nsteps = ntiles >> 2;           // 32-key steps
   const int full_steps = n >> 5;            // steps whose 32 keys are all < n
   const float zp_biased = p.score_zp + 128.f;
+  const int cinit = kPot ? 0x4B400000 : 0;   // 1.5 * 2^23 as an accumulator bias (see the score loop)
+  const float zq = kPot ? (float)((double)zp_biased - 12582912.0 * (double)p.score_mul) : zp_biased;
   const int64_t out_stride = (int64_t)heads * kHd;
   const int izp = (int)p.out_zp;
+  const int half_m1 = out_shift > 0 ? (1 << (out_shift - 1)) - 1 : 0;
 
   for (int r0 = warp * 16; r0 < n; r0 += kAttWarps * 16) {
     const int rowA = r0 + g, rowB = r0 + g + 8;
@@ -188,41 +220,58 @@ attention_int_kernel(const int8_t* __restrict__ qkv, int8_t* __restrict__ out, i
     // ---- S = Q K^T -> biased int8 score codes: clamp(RNE(acc * mul + zp), -128, 127) + 128 ----------------
     // acc * mul is exact for the power-of-two multiplier and adding the integer zp + 128 keeps it exact,
     // so one fma followed by an unsigned saturating RNE conversion is the reference's round-then-clamp.
-    int maxA = 0, maxB = 0;   // biased maxima
+    // kPot: the accumulators start from 0x4B400000, the bit pattern of 1.5 * 2^23, so that the int32 result
+    // re-read as fp32 IS 1.5 * 2^23 + acc (|acc| <= 2^20 keeps it in the binade with ulp 1); the constant is
+    // taken out again inside the fma's addend, which stays exactly representable.  No int -> float converts.
+    // The row maximum is taken on the fp32 values (the conversion is monotone) and converted once.
+    float fmaxA = -INFINITY, fmaxB = -INFINITY;
+    auto score_tile = [&](int j, float (&f)[4]) {
+      const uint4 kf = *reinterpret_cast<const uint4*>(sm.Ks + (j * 8 + g) * kKStride + t * 16);
+      int c[4];
+      mma_s8s8_init(c, qa[0], kf.x, kf.y, cinit);
+      mma_s8s8(c, qa[1], kf.z, kf.w);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) f[e] = __fmaf_rn(kPot ? __int_as_float(c[e]) : (float)c[e], p.score_mul, zq);
+    };
 #pragma unroll 1
-    for (int s = 0; s < nsteps; ++s) {
-      const bool full = s < full_steps;
+    for (int s = 0; s < full_steps; ++s) {
 #pragma unroll
-      for (int jj = 0; jj < 4; ++jj) {
-        const int j = s * 4 + jj;
-        if (!full && j * 8 >= n) {   // a tile of padded keys only: code 0, no MMA
-          const int pos0 = (s << 5) + ((jj >> 1) << 4) + ((jj & 1) << 1);
-          *reinterpret_cast<uint16_t*>(crowA + pos0) = 0;
-          *reinterpret_cast<uint16_t*>(crowB + pos0) = 0;
-          continue;
-        }
-        int c[4] = {0, 0, 0, 0};
-#pragma unroll
-        for (int ks = 0; ks < 2; ++ks) {
-          const uint8_t* kp = sm.Ks + (j * 8 + g) * kQKStride + ks * 32 + t * 4;
-          mma_s8s8(c, qa[ks], *reinterpret_cast<const uint32_t*>(kp), *reinterpret_cast<const uint32_t*>(kp + 16));
-        }
-        uint32_t sc[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e)
-          asm("cvt.rni.sat.u8.f32 %0, %1;" : "=r"(sc[e]) : "f"(__fmaf_rn((float)c[e], p.score_mul, zp_biased)));
-        if (!full) {   // padded keys: code 0 is never above a real (biased) code
-          const int col = j * 8 + t * 2;
-          if (col >= n) { sc[0] = 0; sc[2] = 0; }
-          if (col + 1 >= n) { sc[1] = 0; sc[3] = 0; }
-        }
-        maxA = max(maxA, (int)max(sc[0], sc[1]));
-        maxB = max(maxB, (int)max(sc[2], sc[3]));
-        const int pos = (s << 5) + ((jj >> 1) << 4) + ((jj & 1) << 1);
-        *reinterpret_cast<uint16_t*>(crowA + pos) = (uint16_t)(sc[0] | (sc[1] << 8));
-        *reinterpret_cast<uint16_t*>(crowB + pos) = (uint16_t)(sc[2] | (sc[3] << 8));
+      for (int jp = 0; jp < 2; ++jp) {     // a pair of 8-key tiles = one 32-bit word of codes per row
+        float f0[4], f1[4];
+        score_tile(s * 4 + jp * 2, f0);
+        score_tile(s * 4 + jp * 2 + 1, f1);
+        fmaxA = fmaxf(fmaxf(fmaxA, f0[0]), f0[1]);
+        fmaxB = fmaxf(fmaxf(fmaxB, f0[2]), f0[3]);
+        fmaxA = fmaxf(fmaxf(fmaxA, f1[0]), f1[1]);
+        fmaxB = fmaxf(fmaxf(fmaxB, f1[2]), f1[3]);
+        *reinterpret_cast<uint32_t*>(crowA + (s << 5) + (jp << 4)) = pack2_u8(f0[0], f0[1], pack2_u8(f1[0], f1[1], 0u));
+        *reinterpret_cast<uint32_t*>(crowB + (s << 5) + (jp << 4)) = pack2_u8(f0[2], f0[3], pack2_u8(f1[2], f1[3], 0u));
       }
     }
+    if (full_steps < nsteps) {   // the ragged last step: padded keys get code 0 (never above a real biased code)
+      const int s = full_steps;
+#pragma unroll 1
+      for (int jj = 0; jj < 4; ++jj) {
+        const int j = s * 4 + jj;
+        uint32_t pa = 0, pb = 0;
+        if (j * 8 < n) {
+          float f[4];
+          score_tile(j, f);
+          const int col = j * 8 + t * 2;
+          const bool ok0 = col < n, ok1 = col + 1 < n;
+          if (ok0) { fmaxA = fmaxf(fmaxA, f[0]); fmaxB = fmaxf(fmaxB, f[2]); }
+          if (ok1) { fmaxA = fmaxf(fmaxA, f[1]); fmaxB = fmaxf(fmaxB, f[3]); }
+          pa = pack2_u8(f[0], f[1], 0u) & (ok1 ? 0xffffu : (ok0 ? 0xffu : 0u));
+          pb = pack2_u8(f[2], f[3], 0u) & (ok1 ? 0xffffu : (ok0 ? 0xffu : 0u));
+        }
+        const int pos = (s << 5) + ((jj >> 1) << 4) + ((jj & 1) << 1);
+        *reinterpret_cast<uint16_t*>(crowA + pos) = (uint16_t)pa;
+        *reinterpret_cast<uint16_t*>(crowB + pos) = (uint16_t)pb;
+      }
+    }
+    int maxA, maxB;   // biased maxima
+    asm("cvt.rni.sat.u8.f32 %0, %1;" : "=r"(maxA) : "f"(fmaxA));
+    asm("cvt.rni.sat.u8.f32 %0, %1;" : "=r"(maxB) : "f"(fmaxB));
     maxA = max(maxA, __shfl_xor_sync(0xffffffffu, maxA, 1));
     maxA = max(maxA, __shfl_xor_sync(0xffffffffu, maxA, 2));
     maxB = max(maxB, __shfl_xor_sync(0xffffffffu, maxB, 1));
@@ -232,16 +281,16 @@ attention_int_kernel(const int8_t* __restrict__ qkv, int8_t* __restrict__ out, i
     // ---- exact integer row sums of the integer exp ----------------------------------------------------------
     // fp64 adds run on their own pipe, next to the integer/fp32 work of the other warps
     double sumA = 0.0, sumB = 0.0;
-    const double* lutA = sm.lut_d + maxA;
-    const double* lutB = sm.lut_d + maxB;
+    const double* revA = sm.rev_d + (255 - maxA);
+    const double* revB = sm.rev_d + (255 - maxB);
 #pragma unroll 2
     for (int w = 0; w < 2 * full_steps; ++w) {
       const uint32_t wa = *reinterpret_cast<const uint32_t*>(crowA + w * 16);
       const uint32_t wb = *reinterpret_cast<const uint32_t*>(crowB + w * 16);
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        sumA += *(lutA - (int)__byte_perm(wa, 0, 0x4440 + i));
-        sumB += *(lutB - (int)__byte_perm(wb, 0, 0x4440 + i));
+        sumA += revA[__byte_perm(wa, 0, 0x4440 + i)];
+        sumB += revB[__byte_perm(wb, 0, 0x4440 + i)];
       }
     }
     for (int w = 2 * full_steps; w < 2 * nsteps; ++w) {
@@ -249,8 +298,8 @@ attention_int_kernel(const int8_t* __restrict__ qkv, int8_t* __restrict__ out, i
       const uint32_t wb = *reinterpret_cast<const uint32_t*>(crowB + w * 16);
       for (int i = 0; i < 4; ++i) {
         if (key_of(w, i) < n) {
-          sumA += *(lutA - (int)((wa >> (8 * i)) & 0xff));
-          sumB += *(lutB - (int)((wb >> (8 * i)) & 0xff));
+          sumA += revA[(wa >> (8 * i)) & 0xff];
+          sumB += revB[(wb >> (8 * i)) & 0xff];
         }
       }
     }
@@ -259,8 +308,8 @@ attention_int_kernel(const int8_t* __restrict__ qkv, int8_t* __restrict__ out, i
     sumB += __shfl_xor_sync(0xffffffffu, sumB, 1);
     sumB += __shfl_xor_sync(0xffffffffu, sumB, 2);
     const float fsumA = __double2float_rn(sumA), fsumB = __double2float_rn(sumB);   // exact integer -> RNE, as u64 -> f32
-    const float* lutRA = sm.lut_r3 + maxA;
-    const float* lutRB = sm.lut_r3 + maxB;
+    const float* lutRA = sm.rev_r3 + (255 - maxA);
+    const float* lutRB = sm.rev_r3 + (255 - maxB);
 
     // ---- log2 codes -> two u8 probability planes -> P V ------------------------------------------------------
     int8_t* dsc = kDump ? p.dump_scores + ((int64_t)bh * n) * n : nullptr;
@@ -282,6 +331,10 @@ attention_int_kernel(const int8_t* __restrict__ qkv, int8_t* __restrict__ out, i
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {        // hh = 0: keys of a0/a1; hh = 1: keys of a2/a3
         const int w = 2 * s + hh;
+        if (!full && w * 16 >= n) {   // sixteen padded keys: probability 0 in both planes
+          pa_hi[2 * hh] = pa_hi[2 * hh + 1] = pa_lo[2 * hh] = pa_lo[2 * hh + 1] = 0u;
+          continue;
+        }
         const uint32_t wa = *reinterpret_cast<const uint32_t*>(crowA + w * 16);
         const uint32_t wb = *reinterpret_cast<const uint32_t*>(crowB + w * 16);
         uint32_t va[4], vb[4], ba[4], bb[4];
@@ -360,35 +413,35 @@ attention_int_kernel(const int8_t* __restrict__ qkv, int8_t* __restrict__ out, i
         const int a = acc[jn][e];
         if (out_shift > 0) {
           // RNE(acc / 2^sh) in integers: add half minus one plus the parity of the truncated result
-          const int r = (a + ((1 << (out_shift - 1)) - 1) + ((a >> out_shift) & 1)) >> out_shift;
-          q[e] = min(max(r + izp, -128), 127);
+          q[e] = ((a + half_m1 + ((a >> out_shift) & 1)) >> out_shift) + izp;
         } else {
           const double v = rint((double)a * p.out_mul) + (double)p.out_zp;
           q[e] = (int)fmin(fmax(v, -128.0), 127.0);
         }
       }
       const int col = head * kHd + jn * 8 + t * 2;
-      if (rowA < n)
-        *reinterpret_cast<uint16_t*>(out + ((int64_t)img * n + rowA) * out_stride + col) =
-            (uint16_t)((q[0] & 0xff) | ((q[1] & 0xff) << 8));
-      if (rowB < n)
-        *reinterpret_cast<uint16_t*>(out + ((int64_t)img * n + rowB) * out_stride + col) =
-            (uint16_t)((q[2] & 0xff) | ((q[3] & 0xff) << 8));
+      if (rowA < n) *reinterpret_cast<uint16_t*>(out + ((int64_t)img * n + rowA) * out_stride + col) = (uint16_t)pack2_s8(q[0], q[1]);
+      if (rowB < n) *reinterpret_cast<uint16_t*>(out + ((int64_t)img * n + rowB) * out_stride + col) = (uint16_t)pack2_s8(q[2], q[3]);
     }
     __syncwarp();   // the next row tile overwrites this warp's code buffer
   }
 }
 
+template <bool kDump, bool kPot>
+static int attention_configure_one() {
+  P2V_CHECK_CUDA(cudaFuncSetAttribute(attention_int_kernel<kDump, kPot>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)sizeof(AttSmem)));
+  // three CTAs per SM need the full shared-memory carveout
+  P2V_CHECK_CUDA(cudaFuncSetAttribute(attention_int_kernel<kDump, kPot>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  return P2V_OK;
+}
 static int attention_configure() {
   static int state = 1;
   if (state == 1) {
-    P2V_CHECK_CUDA(cudaFuncSetAttribute(attention_int_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)sizeof(AttSmem)));
-    P2V_CHECK_CUDA(cudaFuncSetAttribute(attention_int_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)sizeof(AttSmem)));
-    // three CTAs per SM need the full shared-memory carveout
-    P2V_CHECK_CUDA(cudaFuncSetAttribute(attention_int_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    P2V_CHECK_CUDA(cudaFuncSetAttribute(attention_int_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    int rc;
+    if ((rc = attention_configure_one<false, false>()) || (rc = attention_configure_one<false, true>()) ||
+        (rc = attention_configure_one<true, false>()) || (rc = attention_configure_one<true, true>()))
+      return rc;
     state = 0;
   }
   return P2V_OK;
@@ -414,10 +467,18 @@ extern "C" int p2v_attention_int(const int8_t* qkv, int8_t* out, int b, int n, i
   int rc = attention_configure_once();
   if (rc) return rc;
   const size_t smem = sizeof(AttSmem);
-  if (p->dump_scores != nullptr)
-    attention_int_kernel<true><<<grid, kAttWarps * 32, smem, (cudaStream_t)stream>>>(qkv, out, n, heads, *p, out_shift);
-  else
-    attention_int_kernel<false><<<grid, kAttWarps * 32, smem, (cudaStream_t)stream>>>(qkv, out, n, heads, *p, out_shift);
+  // power-of-two score multiplier 2^-sh, sh >= 0, and an integer zero point: the biased-accumulator conversion
+  int ex2 = 0;
+  const bool pot = p->score_mul > 0.f && frexpf(p->score_mul, &ex2) == 0.5f && ex2 <= 1 && ex2 >= -30 &&
+                   p->score_zp == (float)(int)p->score_zp;
+  const bool dump = p->dump_scores != nullptr;
+  const cudaStream_t st = (cudaStream_t)stream;
+#define P2V_ATT_LAUNCH(D, P) attention_int_kernel<D, P><<<grid, kAttWarps * 32, smem, st>>>(qkv, out, n, heads, *p, out_shift)
+  if (dump && pot) P2V_ATT_LAUNCH(true, true);
+  else if (dump) P2V_ATT_LAUNCH(true, false);
+  else if (pot) P2V_ATT_LAUNCH(false, true);
+  else P2V_ATT_LAUNCH(false, false);
+#undef P2V_ATT_LAUNCH
   P2V_CHECK_CUDA(cudaGetLastError());
   return P2V_OK;
 }
