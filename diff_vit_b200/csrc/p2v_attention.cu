@@ -65,6 +65,14 @@ __device__ __forceinline__ void mma_u8s8(int (&c)[4], uint32_t a0, uint32_t a1, 
       : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
+// Table lookups of the hot loops through 32-bit shared-window addresses: base + (byte << k) is a single LEA,
+// where indexing a generic pointer costs a subtract, a scaled add and the window base.
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+  float v;
+  asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+
 // position of key j inside the permuted K dimension of the AV product (see file header)
 __device__ __forceinline__ int av_perm(int j) {
   const int s = j >> 5, jj = j & 31;
@@ -95,12 +103,12 @@ __device__ __forceinline__ bool code_guarded(uint32_t bits) {
 
 // four keys of one packed code word -> four 16-bit probabilities; returns true if any element needs the
 // exact path.  revR = rev_r3 + (255 - rowmax) (biased), so the table is addressed by the code byte directly.
-__device__ __forceinline__ bool prob16x4(uint32_t w, const float* revR, float fsum, uint32_t (&v)[4], uint32_t (&bits)[4]) {
+__device__ __forceinline__ bool prob16x4(uint32_t w, uint32_t revR, float fsum, uint32_t (&v)[4], uint32_t (&bits)[4]) {
   bool any = false;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const uint32_t byte = __byte_perm(w, 0, 0x4440 + i);
-    bits[i] = __float_as_uint(__fmaf_rn(fsum, revR[byte], 0.16666667f));
+    bits[i] = __float_as_uint(__fmaf_rn(fsum, lds_f32(revR + (byte << 2)), 0.16666667f));
     any |= code_guarded(bits[i]);
     // 1 << (15 - k), k = E - 125: shift counts >= 32 (k >= 16, or the wrapped negative) give 0
     asm("shl.b32 %0, %1, %2;" : "=r"(v[i]) : "r"(1u), "r"(140u - (bits[i] >> 23)));
@@ -116,7 +124,8 @@ struct AttSmem {
   // the two tables of the hot loops are stored reversed (entry 255 - d), so that with the per-row base
   // rev + (255 - rowmax) they are addressed by the biased code byte itself: one LEA per lookup
   float rev_r3[256];   // 1 / (3 e(d))
-  double rev_d[256];   // e(d) as fp64 (exact): row sums of <= 224 terms < 2^51 stay exact in fp64
+  float rev_e[256];    // e(d): an integer of <= 24 significant bits, exact in fp32 (4-byte entries: a 32-lane lookup
+                       // spreads over all 32 banks, where fp64 entries left 16 bank pairs and twice the conflicts)
 };
 
 // One CTA = one (image, head): K and V are staged once, each of the 7 warps walks 16-row query tiles.
@@ -146,7 +155,7 @@ attention_int_kernel(const int8_t* __restrict__ qkv, int8_t* __restrict__ out, i
     const float e = p.exp_lut[i];
     sm.lut_f[i] = e;
     sm.rev_r3[255 - i] = __fdiv_rn(1.0f, 3.0f * e);   // 3e is exact (<= 24 significant bits)
-    sm.rev_d[255 - i] = (double)e;
+    sm.rev_e[255 - i] = e;
   }
   // K rows with their 16 words stored t-major: word w (columns 4w .. 4w+3) goes to slot (w & 3) * 4 + (w >> 2), so
   // the four B-fragment words of lane t (columns 4t, 16 + 4t, 32 + 4t, 48 + 4t) are one 16-byte load
@@ -195,6 +204,8 @@ attention_int_kernel(const int8_t* __restrict__ qkv, int8_t* __restrict__ out, i
   const int nsteps = ntiles >> 2;           // 32-key steps
   const int full_steps = n >> 5;            // steps whose 32 keys are all < n
   const float zp_biased = p.score_zp + 128.f;
+  const uint32_t rev_e_saddr = (uint32_t)__cvta_generic_to_shared(sm.rev_e);
+  const uint32_t rev_r3_saddr = (uint32_t)__cvta_generic_to_shared(sm.rev_r3);
   const int cinit = kPot ? 0x4B400000 : 0;   // 1.5 * 2^23 as an accumulator bias (see the score loop)
   const float zq = kPot ? (float)((double)zp_biased - 12582912.0 * (double)p.score_mul) : zp_biased;
   const int64_t out_stride = (int64_t)heads * kHd;
@@ -279,27 +290,33 @@ attention_int_kernel(const int8_t* __restrict__ qkv, int8_t* __restrict__ out, i
     __syncwarp();
 
     // ---- exact integer row sums of the integer exp ----------------------------------------------------------
-    // fp64 adds run on their own pipe, next to the integer/fp32 work of the other warps
+    // the fp32 table values are widened and added in fp64 (exact: < 2^51), on the fp64 pipe next to the integer/fp32
+    // work of the other warps
     double sumA = 0.0, sumB = 0.0;
-    const double* revA = sm.rev_d + (255 - maxA);
-    const double* revB = sm.rev_d + (255 - maxB);
+    const uint32_t revA = rev_e_saddr + ((255 - maxA) << 2);
+    const uint32_t revB = rev_e_saddr + ((255 - maxB) << 2);
+    {
+      double pa[4] = {0.0, 0.0, 0.0, 0.0}, pb[4] = {0.0, 0.0, 0.0, 0.0};   // independent chains: the adds are exact
 #pragma unroll 2
-    for (int w = 0; w < 2 * full_steps; ++w) {
-      const uint32_t wa = *reinterpret_cast<const uint32_t*>(crowA + w * 16);
-      const uint32_t wb = *reinterpret_cast<const uint32_t*>(crowB + w * 16);
+      for (int w = 0; w < 2 * full_steps; ++w) {
+        const uint32_t wa = *reinterpret_cast<const uint32_t*>(crowA + w * 16);
+        const uint32_t wb = *reinterpret_cast<const uint32_t*>(crowB + w * 16);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        sumA += revA[__byte_perm(wa, 0, 0x4440 + i)];
-        sumB += revB[__byte_perm(wb, 0, 0x4440 + i)];
+        for (int i = 0; i < 4; ++i) {
+          pa[i] += (double)lds_f32(revA + (__byte_perm(wa, 0, 0x4440 + i) << 2));
+          pb[i] += (double)lds_f32(revB + (__byte_perm(wb, 0, 0x4440 + i) << 2));
+        }
       }
+      sumA = (pa[0] + pa[1]) + (pa[2] + pa[3]);
+      sumB = (pb[0] + pb[1]) + (pb[2] + pb[3]);
     }
     for (int w = 2 * full_steps; w < 2 * nsteps; ++w) {
       const uint32_t wa = *reinterpret_cast<const uint32_t*>(crowA + w * 16);
       const uint32_t wb = *reinterpret_cast<const uint32_t*>(crowB + w * 16);
       for (int i = 0; i < 4; ++i) {
         if (key_of(w, i) < n) {
-          sumA += revA[(wa >> (8 * i)) & 0xff];
-          sumB += revB[(wb >> (8 * i)) & 0xff];
+          sumA += (double)lds_f32(revA + (((wa >> (8 * i)) & 0xff) << 2));
+          sumB += (double)lds_f32(revB + (((wb >> (8 * i)) & 0xff) << 2));
         }
       }
     }
@@ -308,8 +325,8 @@ attention_int_kernel(const int8_t* __restrict__ qkv, int8_t* __restrict__ out, i
     sumB += __shfl_xor_sync(0xffffffffu, sumB, 1);
     sumB += __shfl_xor_sync(0xffffffffu, sumB, 2);
     const float fsumA = __double2float_rn(sumA), fsumB = __double2float_rn(sumB);   // exact integer -> RNE, as u64 -> f32
-    const float* lutRA = sm.rev_r3 + (255 - maxA);
-    const float* lutRB = sm.rev_r3 + (255 - maxB);
+    const uint32_t lutRA = rev_r3_saddr + ((255 - maxA) << 2);
+    const uint32_t lutRB = rev_r3_saddr + ((255 - maxB) << 2);
 
     // ---- log2 codes -> two u8 probability planes -> P V ------------------------------------------------------
     int8_t* dsc = kDump ? p.dump_scores + ((int64_t)bh * n) * n : nullptr;
