@@ -11,6 +11,16 @@ __device__ __forceinline__ uint32_t pack4i(int q0, int q1, int q2, int q3) {
          ((uint32_t)(q3 & 0xff) << 24);
 }
 
+// RNE(x / s + zp) clamped to int8 without an IEEE division per element: t = x * fl(1/s) + zp is within a few ulp of
+// the exactly divided operand, so the rounding can differ only within 2^-13 of a tie; those rare elements are
+// redone with the exact division (same guard as the GEMM epilogue, p2v_gemm.cu div_round).
+__device__ __forceinline__ int quant_div_guarded(float x, float s, float rs, float zp) {
+  const float t = fadd(fmul(x, rs), zp);
+  float r = rintf(t);
+  if (fabsf(fabsf(fsub(t, r)) - 0.5f) < 0.0001220703125f) r = rintf(fadd(fdiv(x, s), zp));
+  return clamp_i(r, -128, 127);
+}
+
 // ---- input quantizer + patchify ------------------------------------------------------------------
 // One thread converts 16 consecutive pixels of one image row (64 B fp32 in, 16 B codes out).  With
 // p % 16 == 0 those 16 pixels are 16 consecutive K entries of one patch row: K = (c*p + kh)*p + kw.
@@ -19,6 +29,7 @@ __global__ void quant_patchify_kernel(const float* __restrict__ x, int8_t* __res
   const int gw = w / p, gh = h / p;
   const int k = c * p * p;
   const int w16 = w / 16;
+  const float rs = __frcp_rn(scale);
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total16;
        i += (int64_t)gridDim.x * blockDim.x) {
     const int xs = (int)(i % w16);
@@ -34,8 +45,8 @@ __global__ void quant_patchify_kernel(const float* __restrict__ x, int8_t* __res
     uint32_t o[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      o[j] = pack4i(quant_div(v[j].x, scale, zp, -128, 127), quant_div(v[j].y, scale, zp, -128, 127),
-                    quant_div(v[j].z, scale, zp, -128, 127), quant_div(v[j].w, scale, zp, -128, 127));
+      o[j] = pack4i(quant_div_guarded(v[j].x, scale, rs, zp), quant_div_guarded(v[j].y, scale, rs, zp),
+                    quant_div_guarded(v[j].z, scale, rs, zp), quant_div_guarded(v[j].w, scale, rs, zp));
     }
     const int px = xs * 16;
     const int pw = px / p, kw = px % p, ph = y / p, kh = y % p;
@@ -46,32 +57,43 @@ __global__ void quant_patchify_kernel(const float* __restrict__ x, int8_t* __res
 
 // ---- token assembly ------------------------------------------------------------------------------------
 // x = qact_embed(cat(cls, patches)) + qact_pos(pos_embed); out = qact1(x)   (models/vit_fquant.py:718-733)
-__global__ void embed_assemble_kernel(const int8_t* __restrict__ pe, int8_t* __restrict__ out, int b, int np,
-                                      int d, float pe_scale, float pe_zp, float embed_scale, float embed_zp,
-                                      const float* __restrict__ cls_value, const float* __restrict__ pos_value,
-                                      const float* __restrict__ out_scale, int64_t total4) {
+// One thread owns one 4-channel group (blockDim.x is a multiple of d / 4) and walks tokens grid-stride, so the
+// per-channel constants and reciprocals are set up once per thread.
+__global__ void __launch_bounds__(256)
+embed_assemble_kernel(const int8_t* __restrict__ pe, int8_t* __restrict__ out, int b, int np,
+                      int d, float pe_scale, float pe_zp, float embed_scale, float embed_zp,
+                      const float* __restrict__ cls_value, const float* __restrict__ pos_value,
+                      const float* __restrict__ out_scale) {
   const int d4 = d / 4;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total4;
-       i += (int64_t)gridDim.x * blockDim.x) {
-    const int c0 = (int)(i % d4) * 4;
-    const int64_t tok = i / d4;
+  const int c0 = (threadIdx.x % d4) * 4;
+  const int tok_per_block = blockDim.x / d4;
+  const int64_t tokens = (int64_t)b * (np + 1);
+  const float4 so4 = *reinterpret_cast<const float4*>(out_scale + c0);
+  const float so[4] = {so4.x, so4.y, so4.z, so4.w};
+  const float rso[4] = {__frcp_rn(so4.x), __frcp_rn(so4.y), __frcp_rn(so4.z), __frcp_rn(so4.w)};
+  const float4 cl4 = *reinterpret_cast<const float4*>(cls_value + c0);
+  const float cls[4] = {cl4.x, cl4.y, cl4.z, cl4.w};
+  const float embed_rs = __frcp_rn(embed_scale);
+  for (int64_t tok = (int64_t)blockIdx.x * tok_per_block + threadIdx.x / d4; tok < tokens;
+       tok += (int64_t)gridDim.x * tok_per_block) {
     const int t = (int)(tok % (np + 1));
     const int img = (int)(tok / (np + 1));
     int q[4];
     uint32_t word = 0;
-    if (t > 0) word = *reinterpret_cast<const uint32_t*>(pe + ((int64_t)img * np + (t - 1)) * d + c0);
+    if (t > 0) word = __ldg(reinterpret_cast<const uint32_t*>(pe + ((int64_t)img * np + (t - 1)) * d + c0));
+    const float4 ps4 = __ldg(reinterpret_cast<const float4*>(pos_value + (int64_t)t * d + c0));
+    const float pos[4] = {ps4.x, ps4.y, ps4.z, ps4.w};
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       float xe;
       if (t == 0) {
-        xe = cls_value[c0 + j];
+        xe = cls[j];
       } else {
         const float pv = fmul(fsub((float)(int8_t)((word >> (8 * j)) & 0xff), pe_zp), pe_scale);
-        const int qe = quant_div(pv, embed_scale, embed_zp, -128, 127);
+        const int qe = quant_div_guarded(pv, embed_scale, embed_rs, embed_zp);
         xe = fmul(fsub((float)qe, embed_zp), embed_scale);
       }
-      const float xv = fadd(xe, pos_value[(int64_t)t * d + c0 + j]);
-      q[j] = quant_div(xv, out_scale[c0 + j], 0.f, -128, 127);
+      q[j] = quant_div_guarded(fadd(xe, pos[j]), so[j], rso[j], 0.f);
     }
     *reinterpret_cast<uint32_t*>(out + tok * d + c0) = pack4i(q[0], q[1], q[2], q[3]);
   }
@@ -307,9 +329,12 @@ extern "C" int p2v_embed_assemble(const int8_t* pe, int8_t* out, int b, int np, 
                                   const float* out_scale, void* stream) {
   P2V_REQUIRE(pe && out && cls_value && pos_value && out_scale, "p2v_embed_assemble: null pointer");
   P2V_REQUIRE(b > 0 && np > 0 && d > 0 && d % 4 == 0, "p2v_embed_assemble: bad shape b=%d np=%d d=%d", b, np, d);
-  const int64_t total4 = (int64_t)b * (np + 1) * (d / 4);
-  embed_assemble_kernel<<<grid_for(total4, 256), 256, 0, (cudaStream_t)stream>>>(
-      pe, out, b, np, d, pe_scale, pe_zp, embed_scale, embed_zp, cls_value, pos_value, out_scale, total4);
+  const int d4 = d / 4;
+  P2V_REQUIRE(d4 <= 256, "p2v_embed_assemble: d=%d exceeds 1024 channels", d);
+  const int block = (256 / d4) * d4;   // a whole number of tokens per block
+  const int64_t tokens = (int64_t)b * (np + 1);
+  embed_assemble_kernel<<<grid_for(tokens, block / d4), block, 0, (cudaStream_t)stream>>>(
+      pe, out, b, np, d, pe_scale, pe_zp, embed_scale, embed_zp, cls_value, pos_value, out_scale);
   P2V_CHECK_CUDA(cudaGetLastError());
   return P2V_OK;
 }
