@@ -132,6 +132,27 @@ __device__ __forceinline__ float ln_code_folded(float xq, const LnRow& row, floa
   return rne(fmul(ffma(sM, xq, Bq), inv2N));
 }
 
+// The same code with every step on the integer / FMA pipes (ncu: the three FRND per element of ln_code_folded kept
+// the conversion unit 58 % busy).  For exponent(|A|) in [-24, 7], i.e. N = 7 - e in [0, 31] without clamping:
+//   M = floor(|A| 2^N) is the leading 8 bits of |A|'s significand: bits(sign(A) M) = (bits(A) & 0x807f0000) | 0x43000000
+//   2^N and 2^-N are exponent arithmetic, and both roundings are done with the 1.5 * 2^23 constant:
+//   RNE(x) = (x + 1.5 * 2^23) - 1.5 * 2^23 for |x| < 2^22, the scaling by the power of two folded into the add.
+// ok is cleared when A is out of that range or |Bq| > 2^21 (then |code| <= |Bq| + 255 * 1016 could reach 2^22);
+// the caller redoes such elements with ln_code_folded.  Both paths give identical codes where both apply.
+__device__ __forceinline__ float ln_code_fast(float xq, const LnRow& row, float go, float bo, bool& ok) {
+  constexpr float kMagic = 12582912.0f;   // 1.5 * 2^23
+  const float A = fmul(row.t, go);
+  const uint32_t fa = f2u(A);
+  const uint32_t ex = fa & 0x7f800000u;
+  const uint32_t p2n = 0x82800000u - ex;                      // bits of 2^(7 - e)
+  const float sM = u2f((fa & 0x807f0000u) | 0x43000000u);
+  const float b = fsub(bo, fmul(row.u, go));
+  const float Bq = fsub(ffma(b, u2f(p2n), kMagic), kMagic);   // RNE(b 2^N): b 2^N is exact, one rounding in the fma
+  ok = ok && (ex - 0x33800000u < 0x10000000u) && (fabsf(Bq) <= 2097152.0f);
+  const float y = ffma(sM, xq, Bq);                            // exact product (< 2^18) + integer: one rounding
+  return fsub(ffma(y, u2f(0x7f000000u - p2n), kMagic), kMagic);   // RNE(y 2^-N)
+}
+
 // G = 4-channel groups per lane.  FULL: d == 128 * G (no partial group).  DUMP: also write the unclamped LN codes.
 template <int G, bool FULL, bool DUMP>
 __global__ void __launch_bounds__(256, 3)
@@ -201,12 +222,18 @@ layernorm_int_pot_kernel(const int8_t* __restrict__ in, int64_t in_row_stride, i
     for (int g = 0; g < G; ++g) {
       const int grp = g * 32 + lane;
       if (FULL || grp < groups) {
-        float v[4];
+        float v[4], code[4];
+        bool ok = true;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) code[j] = ln_code_fast(xq[g][j], st, go[g][j], bo[g][j], ok);
+        if (!ok) {   // rare: a dyadic exponent outside [0, 31] before clamping, or a huge offset
+#pragma unroll
+          for (int j = 0; j < 4; ++j) code[j] = ln_code_folded(xq[g][j], st, go[g][j], bo[g][j]);
+        }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const float code = ln_code_folded(xq[g][j], st, go[g][j], bo[g][j]);
-          if (DUMP) ln_codes[(int64_t)row * d + grp * 4 + j] = (int)code;
-          v[j] = ffma(code, pm[g][j], p.post_zp);   // code * 2^k is exact: one rounding, like mul then add
+          if (DUMP) ln_codes[(int64_t)row * d + grp * 4 + j] = (int)code[j];
+          v[j] = ffma(code[j], pm[g][j], p.post_zp);   // code * 2^k is exact: one rounding, like mul then add
         }
         *reinterpret_cast<uint32_t*>(out + (int64_t)row * d + grp * 4) = pack_sat4f(v[0], v[1], v[2], v[3]);
       }
