@@ -299,11 +299,12 @@ def run_ours(args):
     roofline = {'bound': 'tensor', 'kernel': 'attention_int_kernel (QK^T -> log-int-softmax -> PV), %d x %d heads x %d tokens'
                 % (args.batch, heads, ntok),
                 'achieved': round(att_tops, 2), 'peak': round(peak, 1), 'unit': 'TFLOP/s', 'frac': round(att_tops / peak, 4),
-                'traffic': 63.8e6, 'traffic_source': 'ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch '
+                'traffic': 61.1e6, 'traffic_source': 'ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch '
                                                      '(profiles/r1_summary.md); algorithmic bytes 77.5e6 (qkv in + out)',
                 'us_per_launch': round(att_ms * 1e3, 1), 'share_of_step': round(att_ms * model.depth / step_ms, 3),
                 'peak_source': peak_note,
-                'note': 'issue-bound on the CUDA-core softmax / re-quantisation work (ALU pipe 51 %), not on the tensor pipe (13 %)'}
+                'note': 'bound by CUDA-core issue (51 % active, 48 lane instructions per score element) and shared-memory '
+                        'wavefronts of the softmax table lookups, not by the tensor pipe (15 %) or DRAM (4 %); ncu r1q'}
     gemm_ms = time_gemm(_cabi, m, hid, d, _cabi.EPI_GELU | _cabi.EPI_OUT_POT, 20, stream)
     ops = 2.0 * m * hid * d
     achieved = ops / (gemm_ms * 1e-3) / 1e12
