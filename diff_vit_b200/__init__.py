@@ -37,7 +37,8 @@ def calibrate_model(model, batches):
             for i, x in enumerate(batches):
                 if i == len(batches) - 1:
                     model.model_open_last_calibrate()
-                model(x, plot=False)
+                _, _, distance = model(x, plot=False)
+                model.global_distance = distance   # per-layer weight distances of the last pass (search.omega)
     finally:
         torch.backends.cudnn.allow_tf32 = tf32
     model.model_close_calibrate()

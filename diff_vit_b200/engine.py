@@ -144,12 +144,21 @@ class IntegerEngine:
         for plan in plans:
             self._plans[tuple(int(b) for b in plan.bit_config)] = _BoundPlan(plan, self.device)
 
+    max_plans = 8   # device-resident plans kept per engine (a mixed-precision search walks hundreds of configs)
+
     def bound(self, bit_config):
+        """The device-resident plan of a bit_config: re-selected from the calibrated state (no re-calibration),
+        cached, least recently used evicted beyond `max_plans`."""
         key = tuple(int(b) for b in bit_config)
-        if key not in self._plans:
-            if self.state is None:
-                raise KeyError('no plan for bit_config %s and no calibrated state to build one from' % (key,))
-            self._plans[key] = _BoundPlan(build_plan(self.state, key), self.device)
+        if key in self._plans:
+            self._plans[key] = self._plans.pop(key)          # most recently used last
+            return self._plans[key]
+        if self.state is None:
+            raise KeyError('no plan for bit_config %s and no calibrated state to build one from' % (key,))
+        while len(self._plans) >= self.max_plans:
+            torch.cuda.synchronize(self.device)              # nothing in flight may still read the evicted buffers
+            self._plans.pop(next(iter(self._plans))).close()
+        self._plans[key] = _BoundPlan(build_plan(self.state, key), self.device)
         return self._plans[key]
 
     def _check_input(self, x, arch):

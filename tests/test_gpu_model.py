@@ -247,3 +247,36 @@ def test_vit_base_percentile_config3_vs_oracle():
     lsb = float(state['act']['act_out'][0])
     codes = got / lsb
     assert torch.allclose(codes, codes.round(), atol=1e-3) and got.std() > 0
+
+
+def test_mixed_precision_search_reuses_one_calibration(micro_model, micro_golden):
+    """The search driver (test_quant.py:253-408) on the engine: dozens of bit_configs evaluated from one calibrated
+    state; plans are re-selected, cached (LRU) and evicted, and a re-built plan gives the same logits."""
+    import random
+    from diff_vit_b200 import search
+    z = micro_golden
+    x = torch.from_numpy(z['x_eval']).cuda()
+    labels = torch.from_numpy(z['w8/logits']).argmax(1)          # "ground truth": the all-8-bit prediction
+    eng = micro_model.integer_engine()
+    eng.max_plans = 4
+    first = eng.forward(x, [int(v) for v in z['mixed/bit_config']]).clone()
+    calls = []
+    fit = search.evolutionary_search
+    flops = micro_model.flops()
+    rng = random.Random(0)
+    init = search.candidate_configs(flops, rng, limit=12, ratio=1.6)
+    ranked = search.rank_by_omega(init, micro_model.global_distance)
+    assert ranked[0][1] <= ranked[-1][1]
+
+    def fitness(cfg):
+        calls.append(tuple(cfg))
+        return dvd.validate(micro_model, [(x, labels)], cfg)[0]
+    from diff_vit_b200 import dist as dvd
+    pop, seen = fit([c for c, _ in ranked], fitness, flops, rng, pop_size=6, iterations=2, mutate_size=4,
+                    crossover_size=4, ratio=1.6)
+    assert len(seen) >= 12 and len(eng._plans) <= 4               # far more configs than resident plans
+    assert pop[0][1] >= pop[-1][1] and 0.0 <= pop[-1][1] <= 100.0
+    assert all(len(c) == len(flops) for c, _ in pop)
+    again = eng.forward(x, [int(v) for v in z['mixed/bit_config']])   # evicted meanwhile: rebuilt from the state
+    assert torch.equal(again, first)
+    eng.max_plans = 8
