@@ -196,6 +196,24 @@ def time_attention(lib_mod, bound, b, n, heads, iters, stream_obj):
     return t0.elapsed_time(t1) / iters
 
 
+def bind_to_gpu_numa_node(local):
+    """One process per GPU: run (and first-touch the pinned staging buffers) on the CPUs NVML reports as local to
+    this GPU, so that eight ranks do not pull their 154 MB batches across the socket interconnect.  Best effort."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        handle = pynvml.nvmlDeviceGetHandleByIndex(local)
+        words = pynvml.nvmlDeviceGetCpuAffinity(handle, (os.cpu_count() + 63) // 64)
+        cpus = [64 * i + b for i, w in enumerate(words) for b in range(64) if (w >> b) & 1]
+        cpus = [c for c in cpus if c in os.sched_getaffinity(0)]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return 'cpus %d-%d' % (min(cpus), max(cpus))
+    except Exception as exc:   # no NVML / restricted container: keep the inherited affinity
+        return 'unchanged (%s)' % type(exc).__name__
+    return 'unchanged'
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -210,6 +228,7 @@ def run_ours(args):
                          '(use --impl reference for the CPU baseline)')
     torch.cuda.set_device(local)
     device = torch.device('cuda', local)
+    numa_note = bind_to_gpu_numa_node(local) if world > 1 else None
     if world > 1:
         os.environ.pop('NCCL_DEBUG', None)     # NCCL's version banner would land on stdout next to the JSON line
         dist.init_process_group('nccl', device_id=device)
@@ -336,7 +355,8 @@ def run_ours(args):
                    'calibration': 'randn(%d,3,224,224), %.1f s, excluded' % (args.calib_batch, calib_s)},
         'e2e': {'value': round(e2e_value, 1), 'unit': 'images/s', 'h2d_bytes_per_step': in_bytes,
                 'd2h_bytes_per_step': logits_host.numel() * 4, 'steps': n_e2e,
-                'api': 'IntegerEngine.forward_host_pipelined: pinned H2D of batch i+1 and D2H of logits i-1 overlap forward i (own streams)'},
+                'api': 'IntegerEngine.forward_host_pipelined: pinned H2D of batch i+1 and D2H of logits i-1 overlap forward i (own streams)',
+                'host_affinity': numa_note},
         'gpu_launches': (max(args.warmup, 3) + args.steps + n_e2e + 2) * bound.launches + 23,
         'launches_per_step': bound.launches,
         'roofline': roofline, 'roofline_fc1_gemm': roofline_gemm, 'whole_model': whole, 'cpu_baseline': cpu,

@@ -124,6 +124,7 @@ struct AttSmem {
   // the two tables of the hot loops are stored reversed (entry 255 - d), so that with the per-row base
   // rev + (255 - rowmax) they are addressed by the biased code byte itself: one LEA per lookup
   float rev_r3[256];   // 1 / (3 e(d))
+  int zks[kMaxKeys];   // kZp: z * sum_d k[j][d] per key (asymmetric q/k/v codes)
   float rev_e[256];    // e(d): an integer of <= 24 significant bits, exact in fp32 (4-byte entries: a 32-lane lookup
                        // spreads over all 32 banks, where fp64 entries left 16 bank pairs and twice the conflicts)
 };
@@ -134,7 +135,10 @@ struct AttSmem {
 #endif
 // kPot: the score multiplier is a power of two (every minmax-calibrated model), which lets the int32 -> fp32
 // conversion of the scores ride on the accumulator (see the score loop).
-template <bool kDump, bool kPot>
+// kZp: the q/k/v codes carry a zero point z (asymmetric observers).  The MMAs still multiply the raw codes;
+//   sum (q - z)(k - z) = acc - z (sum q + sum k) + 64 z^2   and   sum p (v - z) = acc2 - z sum p
+// are completed with per-row / per-key sums (kZp implies !kPot: the corrected sum can reach 2^22).
+template <bool kDump, bool kPot, bool kZp>
 __global__ void __launch_bounds__(kAttWarps * 32, P2V_ATT_MIN_CTAS)
 attention_int_kernel(const int8_t* __restrict__ qkv, int8_t* __restrict__ out, int n, int heads,
                      const p2v_attention p, int out_shift) {
@@ -149,6 +153,7 @@ attention_int_kernel(const int8_t* __restrict__ qkv, int8_t* __restrict__ out, i
   const int ntiles = nkp >> 3;
   const int64_t row_stride = (int64_t)3 * heads * kHd;
   const int8_t* base = qkv + (int64_t)img * n * row_stride;
+  const int iz = kZp ? (int)p.in_zp : 0;
 
   // ---- stage K (row-major, padded stride) and V (transposed + permuted) in shared memory ---------------
   for (int i = tid; i < 256; i += blockDim.x) {
@@ -168,6 +173,13 @@ attention_int_kernel(const int8_t* __restrict__ qkv, int8_t* __restrict__ out, i
     dst[4] = v.y;
     dst[8] = v.z;
     dst[12] = v.w;
+    if (kZp) {   // the four lanes of a key add their 16-byte partial sums
+      int ks = __dp4a((int)v.x, 0x01010101, __dp4a((int)v.y, 0x01010101, __dp4a((int)v.z, 0x01010101, __dp4a((int)v.w, 0x01010101, 0))));
+      const uint32_t mask = __activemask();
+      ks += __shfl_xor_sync(mask, ks, 1);
+      ks += __shfl_xor_sync(mask, ks, 2);
+      if (part == 0) sm.zks[j] = iz * ks;
+    }
   }
   // V^T with the key permutation of the AV product: 4 consecutive positions kappa = 16h + 4t + {0,1,2,3}
   // hold keys {j0, j0+1, j0+8, j0+9}, j0 = 32s + 16h + 2t.  One thread transposes a 4-key x 4-channel
@@ -228,6 +240,22 @@ attention_int_kernel(const int8_t* __restrict__ qkv, int8_t* __restrict__ out, i
       }
     }
 
+    int rcA = 0, rcB = 0;   // kZp: z * sum_d q[row][d] - 64 z^2, subtracted from every raw score of the row
+    if (kZp) {
+      int qsA = 0, qsB = 0;
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) {
+        qsA = __dp4a((int)qa[ks][0], 0x01010101, __dp4a((int)qa[ks][2], 0x01010101, qsA));
+        qsB = __dp4a((int)qa[ks][1], 0x01010101, __dp4a((int)qa[ks][3], 0x01010101, qsB));
+      }
+      qsA += __shfl_xor_sync(0xffffffffu, qsA, 1);
+      qsA += __shfl_xor_sync(0xffffffffu, qsA, 2);
+      qsB += __shfl_xor_sync(0xffffffffu, qsB, 1);
+      qsB += __shfl_xor_sync(0xffffffffu, qsB, 2);
+      rcA = iz * qsA - kHd * iz * iz;
+      rcB = iz * qsB - kHd * iz * iz;
+    }
+
     // ---- S = Q K^T -> biased int8 score codes: clamp(RNE(acc * mul + zp), -128, 127) + 128 ----------------
     // acc * mul is exact for the power-of-two multiplier and adding the integer zp + 128 keeps it exact,
     // so one fma followed by an unsigned saturating RNE conversion is the reference's round-then-clamp.
@@ -241,6 +269,10 @@ attention_int_kernel(const int8_t* __restrict__ qkv, int8_t* __restrict__ out, i
       int c[4];
       mma_s8s8_init(c, qa[0], kf.x, kf.y, cinit);
       mma_s8s8(c, qa[1], kf.z, kf.w);
+      if (kZp) {
+        const int2 zk = *reinterpret_cast<const int2*>(&sm.zks[j * 8 + t * 2]);
+        c[0] -= rcA + zk.x; c[1] -= rcA + zk.y; c[2] -= rcB + zk.x; c[3] -= rcB + zk.y;
+      }
 #pragma unroll
       for (int e = 0; e < 4; ++e) f[e] = __fmaf_rn(kPot ? __int_as_float(c[e]) : (float)c[e], p.score_mul, zq);
     };
@@ -340,6 +372,7 @@ attention_int_kernel(const int8_t* __restrict__ qkv, int8_t* __restrict__ out, i
     for (int jn = 0; jn < 8; ++jn)
 #pragma unroll
       for (int e = 0; e < 4; ++e) acc[jn][e] = 0;
+    int psA = 0, psB = 0;   // kZp: sum of the 16-bit probabilities of the row (this lane's keys)
 
 #pragma unroll 1
     for (int s = 0; s < nsteps; ++s) {
@@ -384,6 +417,10 @@ attention_int_kernel(const int8_t* __restrict__ qkv, int8_t* __restrict__ out, i
             }
           }
         }
+        if (kZp) {
+          psA += (int)(va[0] + va[1] + va[2] + va[3]);
+          psB += (int)(vb[0] + vb[1] + vb[2] + vb[3]);
+        }
         // 16-bit probabilities -> low-byte plane and high-byte plane, 4 keys per register
         const uint32_t a01 = va[0] | (va[1] << 16), a23 = va[2] | (va[3] << 16);
         const uint32_t b01 = vb[0] | (vb[1] << 16), b23 = vb[2] | (vb[3] << 16);
@@ -422,12 +459,20 @@ attention_int_kernel(const int8_t* __restrict__ qkv, int8_t* __restrict__ out, i
     }
 
     // ---- re-quantize and store ----------------------------------------------------------------------------
+    if (kZp) {
+      psA += __shfl_xor_sync(0xffffffffu, psA, 1);
+      psA += __shfl_xor_sync(0xffffffffu, psA, 2);
+      psB += __shfl_xor_sync(0xffffffffu, psB, 1);
+      psB += __shfl_xor_sync(0xffffffffu, psB, 2);
+      psA *= iz;
+      psB *= iz;
+    }
 #pragma unroll
     for (int jn = 0; jn < 8; ++jn) {
       int q[4];
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        const int a = acc[jn][e];
+        const int a = acc[jn][e] - (kZp ? (e < 2 ? psA : psB) : 0);
         if (out_shift > 0) {
           // RNE(acc / 2^sh) in integers: add half minus one plus the parity of the truncated result
           q[e] = ((a + half_m1 + ((a >> out_shift) & 1)) >> out_shift) + izp;
@@ -444,20 +489,21 @@ attention_int_kernel(const int8_t* __restrict__ qkv, int8_t* __restrict__ out, i
   }
 }
 
-template <bool kDump, bool kPot>
+template <bool kDump, bool kPot, bool kZp>
 static int attention_configure_one() {
-  P2V_CHECK_CUDA(cudaFuncSetAttribute(attention_int_kernel<kDump, kPot>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  P2V_CHECK_CUDA(cudaFuncSetAttribute(attention_int_kernel<kDump, kPot, kZp>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)sizeof(AttSmem)));
   // three CTAs per SM need the full shared-memory carveout
-  P2V_CHECK_CUDA(cudaFuncSetAttribute(attention_int_kernel<kDump, kPot>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  P2V_CHECK_CUDA(cudaFuncSetAttribute(attention_int_kernel<kDump, kPot, kZp>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
   return P2V_OK;
 }
 static int attention_configure() {
   static int state = 1;
   if (state == 1) {
     int rc;
-    if ((rc = attention_configure_one<false, false>()) || (rc = attention_configure_one<false, true>()) ||
-        (rc = attention_configure_one<true, false>()) || (rc = attention_configure_one<true, true>()))
+    if ((rc = attention_configure_one<false, false, false>()) || (rc = attention_configure_one<false, true, false>()) ||
+        (rc = attention_configure_one<true, false, false>()) || (rc = attention_configure_one<true, true, false>()) ||
+        (rc = attention_configure_one<false, false, true>()) || (rc = attention_configure_one<true, false, true>()))
       return rc;
     state = 0;
   }
@@ -486,15 +532,19 @@ extern "C" int p2v_attention_int(const int8_t* qkv, int8_t* out, int b, int n, i
   const size_t smem = sizeof(AttSmem);
   // power-of-two score multiplier 2^-sh, sh >= 0, and an integer zero point: the biased-accumulator conversion
   int ex2 = 0;
-  const bool pot = p->score_mul > 0.f && frexpf(p->score_mul, &ex2) == 0.5f && ex2 <= 1 && ex2 >= -30 &&
+  const bool zp = p->in_zp != 0.f;
+  P2V_REQUIRE(p->in_zp == (float)(int)p->in_zp && fabsf(p->in_zp) <= 128.f, "p2v_attention_int: in_zp must be an int8 code");
+  const bool pot = !zp && p->score_mul > 0.f && frexpf(p->score_mul, &ex2) == 0.5f && ex2 <= 1 && ex2 >= -30 &&
                    p->score_zp == (float)(int)p->score_zp;
   const bool dump = p->dump_scores != nullptr;
   const cudaStream_t st = (cudaStream_t)stream;
-#define P2V_ATT_LAUNCH(D, P) attention_int_kernel<D, P><<<grid, kAttWarps * 32, smem, st>>>(qkv, out, n, heads, *p, out_shift)
-  if (dump && pot) P2V_ATT_LAUNCH(true, true);
-  else if (dump) P2V_ATT_LAUNCH(true, false);
-  else if (pot) P2V_ATT_LAUNCH(false, true);
-  else P2V_ATT_LAUNCH(false, false);
+#define P2V_ATT_LAUNCH(D, P, Z) attention_int_kernel<D, P, Z><<<grid, kAttWarps * 32, smem, st>>>(qkv, out, n, heads, *p, out_shift)
+  if (zp && dump) P2V_ATT_LAUNCH(true, false, true);
+  else if (zp) P2V_ATT_LAUNCH(false, false, true);
+  else if (dump && pot) P2V_ATT_LAUNCH(true, true, false);
+  else if (dump) P2V_ATT_LAUNCH(true, false, false);
+  else if (pot) P2V_ATT_LAUNCH(false, true, false);
+  else P2V_ATT_LAUNCH(false, false, false);
 #undef P2V_ATT_LAUNCH
   P2V_CHECK_CUDA(cudaGetLastError());
   return P2V_OK;

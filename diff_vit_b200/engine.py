@@ -85,6 +85,7 @@ class _BoundPlan:
         d = _cabi.Attention()
         d.score_mul, d.score_zp, d.out_mul, d.out_zp = p.score_mul, p.score_zp, p.out_mul, p.out_zp
         d.softmax_levels = p.levels
+        d.in_zp = getattr(p, 'in_zp', 0.0)
         d.exp_lut = self._p(p.exp_lut)
         return d
 

@@ -104,6 +104,7 @@ class AttentionPlan:
     out_zp: float
     levels: int
     exp_lut: torch.Tensor      # fp32 [256]
+    in_zp: float = 0.0         # zero point of the q/k/v codes (asymmetric observers)
 
 
 @dataclass
@@ -206,15 +207,19 @@ class _Builder:
             raise NotImplementedError('%s: asymmetric weight quantizers are not produced by the minmax observer' % name)
         in_scale, in_zp, _, _ = self.act(in_act)
         in_scale = _scalar(in_scale, in_act)
-        if float(_scalar(in_zp, in_act)) != 0.0:
-            raise NotImplementedError('%s: non-zero input zero point (omse observer) is not supported by the '
-                                      'integer GEMM yet' % in_act)
+        in_zp = float(_scalar(in_zp, in_act))
         out_scale, out_zp, _, _ = self.act(out_act)
         out_vec = _expand(out_scale, n)
         pot = is_pot(out_vec) and float(torch.as_tensor(out_zp).reshape(-1)[0]) == 0.0
         flags = (1 if gelu else 0) | (4 if pot else 0)
-        plan = LinearPlan(w=codes.to(torch.int8).contiguous(), acc_scale=_expand(in_scale * w_scale.reshape(-1), n),
-                          bias=self.P[name + '.bias'].clone(), out_scale=out_vec, out_rscale=1.0 / out_vec,
+        acc_scale = _expand(in_scale * w_scale.reshape(-1), n)
+        bias = self.P[name + '.bias'].clone()
+        if in_zp != 0.0:
+            # asymmetric input (omse observer): sum_k (q_k - z) w_nk = acc_n - z * sum_k w_nk; the second term is a
+            # per-channel constant and joins the bias, so the GEMM itself still multiplies raw int8 codes
+            bias = (bias.double() - in_zp * acc_scale.double() * codes.double().sum(1)).float()
+        plan = LinearPlan(w=codes.to(torch.int8).contiguous(), acc_scale=acc_scale,
+                          bias=bias, out_scale=out_vec, out_rscale=1.0 / out_vec,
                           out_zp=float(torch.as_tensor(out_zp).reshape(-1)[0]), flags=flags)
         if residual is not None:
             res_act, out2_act = residual
@@ -246,13 +251,12 @@ class _Builder:
         sa, za, _, _ = self.act(pre + '.qact_attn1')
         s2, z2, _, _ = self.act(pre + '.qact2')
         s1, sa, s2 = (float(_scalar(v, pre)) for v in (s1, sa, s2))
-        if float(_scalar(z1, pre)) != 0.0:
-            raise NotImplementedError('%s.qact1: non-zero zero point' % pre)
         score_mul = s1 * s1 * self.arch['attn_scale'] / sa
         return AttentionPlan(score_mul=float(torch.tensor(score_mul, dtype=torch.float32)),
                              score_zp=float(_scalar(za, pre)), out_mul=(2.0 ** -15) * s1 / s2,
                              out_zp=float(_scalar(z2, pre)), levels=2 ** self.arch['softmax_bits'],
-                             exp_lut=softmax_exp_lut(_scalar(self.act(pre + '.qact_attn1')[0], pre)))
+                             exp_lut=softmax_exp_lut(_scalar(self.act(pre + '.qact_attn1')[0], pre)),
+                             in_zp=float(_scalar(z1, pre)))
 
     def build(self):
         P, arch, bits = self.P, self.arch, self.bits

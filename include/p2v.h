@@ -128,6 +128,9 @@ typedef struct p2v_attention {
   const float* exp_lut; /* [256] fp32 view of the integer exp (exact: < 2^24 significant bits) */
   int8_t* dump_scores;
   uint8_t* dump_softmax;
+  float in_zp;        /* zero point of the q/k/v codes (qact1); non-zero only with asymmetric observers (omse):
+                         S = sum (q - z)(k - z) and O = sum p (v - z) are formed from the raw int8 products plus row /
+                         key sums, so the tensor-core operands stay int8 */
 } p2v_attention;
 int p2v_attention_int(const int8_t* qkv, int8_t* out, int b, int n, int heads, const p2v_attention* p,
                       void* stream);

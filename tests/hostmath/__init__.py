@@ -65,7 +65,8 @@ def attention(qkv, b, n, heads, p):
     sm = np.empty((b, heads, n, n), np.uint8)
     lut = _f(p.exp_lut)
     lib().hm_attention(_p(qkv), _p(out), b, n, heads, C.c_float(p.score_mul), C.c_float(p.score_zp),
-                       C.c_double(p.out_mul), C.c_float(p.out_zp), p.levels, _p(lut), _p(sc), _p(sm))
+                       C.c_double(p.out_mul), C.c_float(p.out_zp), p.levels, _p(lut), _p(sc), _p(sm),
+                       C.c_float(getattr(p, 'in_zp', 0.0)))
     return out, sc, sm
 
 

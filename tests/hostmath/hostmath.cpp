@@ -65,7 +65,9 @@ void hm_layernorm(const int8_t* in, int64_t in_row_stride, int8_t* out, int32_t*
 
 // qkv [b, n, 3, heads, 64] -> out [b, n, heads*64]; scores/softmax dumps [b, heads, n, n]
 void hm_attention(const int8_t* qkv, int8_t* out, int b, int n, int heads, float score_mul, float score_zp,
-                  double out_mul, float out_zp, int levels, const float* lut, int8_t* scores, uint8_t* softmax) {
+                  double out_mul, float out_zp, int levels, const float* lut, int8_t* scores, uint8_t* softmax,
+                  float in_zp) {
+  const int z = (int)in_zp;
   const int hd = 64;
   const int64_t rs = 3 * heads * hd;
   std::vector<int> sc(n);
@@ -78,7 +80,7 @@ void hm_attention(const int8_t* qkv, int8_t* out, int b, int n, int heads, float
         for (int j = 0; j < n; ++j) {
           const int8_t* k = qkv + ((int64_t)img * n + j) * rs + (heads + h) * hd;
           int acc = 0;
-          for (int d = 0; d < hd; ++d) acc += (int)q[d] * (int)k[d];
+          for (int d = 0; d < hd; ++d) acc += ((int)q[d] - z) * ((int)k[d] - z);
           sc[j] = clamp_i(rne(fadd(fmul((float)acc, score_mul), score_zp)), -128, 127);
           mx = sc[j] > mx ? sc[j] : mx;
         }
@@ -98,7 +100,7 @@ void hm_attention(const int8_t* qkv, int8_t* out, int b, int n, int heads, float
           for (int j = 0; j < n; ++j) {
             if (kk[j] >= levels) continue;
             const int8_t* v = qkv + ((int64_t)img * n + j) * rs + (2 * heads + h) * hd;
-            acc += (long long)v[d] << (15 - kk[j]);
+            acc += (long long)((int)v[d] - z) * (1LL << (15 - kk[j]));
           }
           double v = rint((double)acc * out_mul) + (double)out_zp;
           v = v < -128.0 ? -128.0 : (v > 127.0 ? 127.0 : v);

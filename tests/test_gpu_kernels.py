@@ -155,17 +155,22 @@ def test_layernorm_int_matches_host_arithmetic(cabi, rows, d, stride_rows, pot):
 
 @pytest.mark.parametrize('b,n,heads', [(2, 197, 3), (3, 10, 2), (1, 224, 1), (2, 33, 6), (1, 1, 1)])
 @pytest.mark.parametrize('spread', [1, 6])
-def test_attention_int_matches_host_arithmetic(cabi, b, n, heads, spread):
+@pytest.mark.parametrize('in_zp', [0, 7, -11])
+def test_attention_int_matches_host_arithmetic(cabi, b, n, heads, spread, in_zp):
+    """in_zp != 0: asymmetric q/k/v codes (omse observer); the kernel completes the raw int8 products with row / key
+    sums and must equal the direct sum over (q - z)(k - z) and p (v - z) of the host arithmetic, with non-zero
+    score and output zero points as well."""
     from diff_vit_b200.plan import AttentionPlan, softmax_exp_lut
     rng = np.random.default_rng(b * 100 + n + heads + spread)
-    qkv = _rand_i8(rng, b * n, 3 * heads * 64, lo=-20 * spread, hi=20 * spread)
+    qkv = _rand_i8(rng, b * n, 3 * heads * 64, lo=max(-128, -20 * spread + in_zp), hi=min(127, 20 * spread + in_zp))
     s_att = torch.tensor([2.0 ** -4])
-    p = AttentionPlan(score_mul=float(2.0 ** -7), score_zp=0.0, out_mul=2.0 ** -15 * 2.0 ** -1, out_zp=0.0, levels=16,
-                      exp_lut=softmax_exp_lut(s_att))
+    p = AttentionPlan(score_mul=float(2.0 ** -7), score_zp=3.0 if in_zp else 0.0, out_mul=2.0 ** -15 * 2.0 ** -1,
+                      out_zp=-5.0 if in_zp else 0.0, levels=16, exp_lut=softmax_exp_lut(s_att), in_zp=float(in_zp))
     want, want_sc, want_sm = hostmath.attention(qkv, b, n, heads, p)
     lut = p.exp_lut.cuda()
     c = cabi.Attention()
-    c.score_mul, c.score_zp, c.out_mul, c.out_zp, c.softmax_levels = p.score_mul, 0.0, p.out_mul, 0.0, 16
+    c.score_mul, c.score_zp, c.out_mul, c.out_zp, c.softmax_levels = p.score_mul, p.score_zp, p.out_mul, p.out_zp, 16
+    c.in_zp = p.in_zp
     c.exp_lut = lut.data_ptr()
     sc = torch.zeros(b, heads, n, n, dtype=torch.int8, device='cuda')
     sm = torch.zeros(b, heads, n, n, dtype=torch.uint8, device='cuda')

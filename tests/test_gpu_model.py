@@ -280,3 +280,41 @@ def test_mixed_precision_search_reuses_one_calibration(micro_model, micro_golden
     again = eng.forward(x, [int(v) for v in z['mixed/bit_config']])   # evicted meanwhile: rebuilt from the state
     assert torch.equal(again, first)
     eng.max_plans = 8
+
+
+def test_omse_zero_points_through_the_engine(micro_golden):
+    """Asymmetric activation quantizers (omse, the second observer of BASELINE config 3) on the GPU: the engine
+    must agree with the host arithmetic of the same plan bit for bit, and with the CPU oracle within the
+    allowance of the non power-of-two scales."""
+    import functools
+    import hostmath
+    import diff_vit_b200 as dv
+    from conftest import build_micro
+    from diff_vit_b200.plan import build_plan, extract_state
+    z = micro_golden
+    model = build_micro(z)
+    fresh = dv.VisionTransformer(img_size=48, patch_size=16, embed_dim=128, depth=2, num_heads=2, mlp_ratio=4,
+                                 qkv_bias=True, norm_layer=functools.partial(dv.QIntLayerNorm, eps=1e-6),
+                                 input_quant=True, cfg=dv.Config(True, True, 'omse'), num_classes=16).eval()
+    fresh.load_state_dict(model.state_dict())
+    dv.calibrate_model(fresh, [torch.from_numpy(z['x_calib'])])
+    state = extract_state(fresh)
+    plan = build_plan(state, [8] * 10)
+    assert plan.blocks[0].attn.in_zp != 0.0
+    x = torch.from_numpy(z['x_eval'])
+    logits, dump = fresh.integer_engine().forward_dump(x.cuda(), [8] * 10)
+    host_logits, host = hostmath.run_plan(plan, z['x_eval'])
+    total = bad = 0
+    for k, v in host.items():
+        if k not in dump:
+            continue
+        d = np.abs(dump[k].astype(np.int64).reshape(v.shape) - v.astype(np.int64))
+        total += d.size
+        bad += int((d != 0).sum())
+    assert total > 100000 and bad <= 5e-3 * total, '%d of %d codes differ from the host arithmetic' % (bad, total)
+    for k in ('act/blocks.0.attn.qact1', 'act/blocks.0.attn.qact_attn1', 'softmax/blocks.0.attn.log_int_softmax',
+              'act/blocks.0.attn.qact2'):    # everything up to the first GELU is bit-defined
+        np.testing.assert_array_equal(dump[k].astype(np.int64).reshape(host[k].shape), host[k].astype(np.int64), err_msg=k)
+    ref_logits, _ = orc.forward(state, x, [8] * 10, capture=False)
+    lsb = float(state['act']['act_out'][0])
+    assert np.abs(ref_logits.numpy() - logits.cpu().numpy()).max() <= 8 * lsb
