@@ -196,6 +196,28 @@ def time_attention(lib_mod, bound, b, n, heads, iters, stream_obj):
     return t0.elapsed_time(t1) / iters
 
 
+def time_layernorm(lib_mod, bound, rows, d, iters, stream_obj):
+    """Average device time (ms) of block 0's integer LayerNorm (norm1) on random int8 residual codes."""
+    import ctypes as C
+    import torch
+    x = torch.randint(-128, 128, (rows, d), dtype=torch.int8, device='cuda')
+    out = torch.empty_like(x)
+    ln = bound.blocks[0].norm1
+    lib = lib_mod.lib()
+    call = lambda: lib_mod.check(lib.p2v_layernorm_int(x.data_ptr(), d, out.data_ptr(), None, rows, d, C.byref(ln),
+                                                       stream_obj.cuda_stream))
+    with torch.cuda.stream(stream_obj):
+        for _ in range(3):
+            call()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record(stream_obj)
+        for _ in range(iters):
+            call()
+        t1.record(stream_obj)
+    stream_obj.synchronize()
+    return t0.elapsed_time(t1) / iters
+
+
 def bind_to_gpu_numa_node(local):
     """One process per GPU: run (and first-touch the pinned staging buffers) on the CPUs NVML reports as local to
     this GPU, so that eight ranks do not pull their 154 MB batches across the socket interconnect.  Best effort."""
@@ -324,6 +346,15 @@ def run_ours(args):
                 'peak_source': peak_note,
                 'note': 'bound by CUDA-core issue (51 % active, 48 lane instructions per score element) and shared-memory '
                         'wavefronts of the softmax table lookups, not by the tensor pipe (15 %) or DRAM (4 %); ncu r1q'}
+    ln_ms = time_layernorm(_cabi, bound, m, d, 20, stream)
+    hbm_peak = float(hbm)
+    ln_gbs = 2.0 * m * d / (ln_ms * 1e-3) / 1e9
+    roofline_ln = {'bound': 'hbm', 'kernel': 'layernorm_int_pot_kernel %d rows x %d (int8 in, int8 out)' % (m, d),
+                   'achieved': round(ln_gbs, 1), 'peak': round(hbm_peak, 1), 'unit': 'GB/s', 'peak_source': '%s HBM copy bandwidth' % src,
+                   'frac': round(ln_gbs / hbm_peak, 4), 'traffic': 19.4e6,
+                   'traffic_source': 'ncu r1q: dram read 19.4 MB, write-back deferred (the 19.4 MB output stays in the 126 MB L2)',
+                   'us_per_launch': round(ln_ms * 1e3, 1), 'share_of_step': round(ln_ms * (2 * model.depth + 1) / step_ms, 3),
+                   'note': 'latency / issue bound (36 lane instructions per element, per-row serial chain), not HBM bound'}
     gemm_ms = time_gemm(_cabi, m, hid, d, _cabi.EPI_GELU | _cabi.EPI_OUT_POT, 20, stream)
     ops = 2.0 * m * hid * d
     achieved = ops / (gemm_ms * 1e-3) / 1e12
@@ -359,7 +390,7 @@ def run_ours(args):
                 'host_affinity': numa_note},
         'gpu_launches': (max(args.warmup, 3) + args.steps + n_e2e + 2) * bound.launches + 23,
         'launches_per_step': bound.launches,
-        'roofline': roofline, 'roofline_fc1_gemm': roofline_gemm, 'whole_model': whole, 'cpu_baseline': cpu,
+        'roofline': roofline, 'roofline_fc1_gemm': roofline_gemm, 'roofline_layernorm': roofline_ln, 'whole_model': whole, 'cpu_baseline': cpu,
         'clocks': clocks,
     }
     print(json.dumps(line))

@@ -109,6 +109,39 @@ __device__ __forceinline__ void div_round4(const float (&y)[4], const float (&s)
 
 __device__ __forceinline__ float clamp_code(float r) { return fminf(fmaxf(r, -128.f), 127.f); }
 
+// ---- erf-GELU straight to the output grid -----------------------------------------------------------------------
+// libdevice's erff selects between two polynomial sets per element (9 FSEL + 10 FMA-pipe ops + MUFU): with the
+// surrounding arithmetic 32 instructions per output of the fc1 epilogue, which is issue-bound (ncu: 80 %).
+// Here erf(x) = sign(x) (1 - 2^(t Q(t))), t = min(|x|, 4), Q a degree-6 minimax fit of log2(erfc(t)) / t weighted by
+// erfc(t): |error| < 5e-7 absolute including MUFU.EX2, one polynomial, no selects.  The result on the output grid
+//   tq = (0.5 y rso) (1 + erf(y / sqrt 2))
+// is accepted only if it lies further than 1.5e-6 |0.5 y rso| from a rounding boundary - more than the difference
+// to the reference expression gelu_erf(y) * rso (approximation error plus a few ulp of association) - so accepted
+// elements round to the same int8 code as the reference expression; the others (~2e-4) are redone with gelu_erf.
+// p2v_test_gelu_fast sweeps all 2^32 inputs on the device and counts accepted elements whose codes differ: zero.
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float gelu_code_fast(float y, float half_rso, bool& ok) {
+  const float x = fmul(y, 0.70710678118654752440f);
+  const float t = fminf(fabsf(x), 4.0f);
+  float q = 1.0022142669185996e-4f;
+  q = ffma(q, t, -4.6157639008015394e-4f);
+  q = ffma(q, t, -2.3022270761430264e-3f);
+  q = ffma(q, t, 2.9452499002218246e-2f);
+  q = ffma(q, t, -1.4896366000175476e-1f);
+  q = ffma(q, t, -9.183286428451538e-1f);
+  q = ffma(q, t, -1.6279137134552002f);
+  const float erfv = copysignf(fsub(1.0f, ex2_approx(fmul(t, q))), x);
+  const float hr = fmul(y, half_rso);
+  const float tq = ffma(hr, erfv, hr);
+  const float rr = fsub(fadd(tq, 12582912.0f), 12582912.0f);          // RNE(tq) for |tq| < 2^22 (beyond: saturates anyway)
+  ok = ok && (fabsf(fabsf(fsub(tq, rr)) - 0.5f) >= fmul(fabsf(hr), 1.5e-6f));
+  return tq;
+}
+
 // Epilogue of 16 consecutive columns of one output row (one thread).  ch: this accumulator stage's
 // channel constants, c: column offset inside the tile.
 // Staged mode (res_staged / out_staged non-null): the residual codes of these 16 columns were brought in, and the
@@ -158,12 +191,21 @@ __device__ __forceinline__ void epilogue16(const uint32_t (&acc)[16], const floa
       so[0] = S.x; so[1] = S.y; so[2] = S.z; so[3] = S.w;
     }
     float y4[4], r4[4];
+    constexpr bool kGeluPot = (FLAGS & EPI_GELU) && (FLAGS & EPI_OUT_POT);
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       y4[e] = ffma((float)(int)acc[j4 + e], a4[e], b4[e]);   // kFold: already on the output grid
-      if (FLAGS & EPI_GELU) y4[e] = gelu_erf(y4[e]);
+      if ((FLAGS & EPI_GELU) && !kGeluPot) y4[e] = gelu_erf(y4[e]);
     }
-    if (kFold) {
+    if (kGeluPot) {
+      bool ok = true;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) r4[e] = gelu_code_fast(y4[e], rso[e], ok);   // rso[] holds rso / 2 here
+      if (!ok) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) r4[e] = fmul(gelu_erf(y4[e]), fmul(rso[e], 2.0f));
+      }
+    } else if (kFold) {
 #pragma unroll
       for (int e = 0; e < 4; ++e) r4[e] = y4[e];                       // the saturating pack rounds half-even
     } else if (FLAGS & EPI_OUT_POT) {
@@ -246,6 +288,7 @@ __device__ __forceinline__ void load_channels(float (*ch)[CW], const p2v_epilogu
         A = fmul(A, RSO);
         B = fmul(B, RSO);
       }
+      if ((FLAGS & EPI_GELU) && (FLAGS & EPI_OUT_POT)) RSO = fmul(RSO, 0.5f);   // gelu_code_fast takes rso / 2 (exact)
       if (FLAGS & EPI_RESIDUAL) {
         SR = e.res_scale[col];
         SO2 = e.out2_scale[col];
@@ -693,6 +736,31 @@ gemm_i8_bs_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   if (warp == 2) tmem_dealloc<512>(tmem_base);
 }
 
+// ---- exhaustive check of gelu_code_fast (test hook) ---------------------------------------------------------------
+// All 2^32 fp32 bit patterns: counts[0] = accepted elements whose int8 code differs from the reference expression,
+// counts[1] = rejected (guard) among |y| < 8, counts[2] = finite inputs with |y| < 8.
+__global__ void gelu_fast_sweep_kernel(float rso, unsigned long long* __restrict__ counts) {
+  unsigned long long bad = 0, rejected = 0, total = 0;
+  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < (1ull << 32); i += stride) {
+    const float y = __uint_as_float((uint32_t)i);
+    if (!isfinite(y)) continue;
+    bool ok = true;
+    const float tq = gelu_code_fast(y, 0.5f * rso, ok);
+    const float ref = fmul(gelu_erf(y), rso);
+    const int cf = max(-128, min(127, __float2int_rn(fminf(fmaxf(tq, -1e6f), 1e6f))));
+    const int cr = max(-128, min(127, __float2int_rn(fminf(fmaxf(ref, -1e6f), 1e6f))));
+    if (ok && cf != cr) ++bad;
+    if (fabsf(y) < 8.f) {
+      ++total;
+      if (!ok) ++rejected;
+    }
+  }
+  atomicAdd(&counts[0], bad);
+  atomicAdd(&counts[1], rejected);
+  atomicAdd(&counts[2], total);
+}
+
 // ---- CUDA-core cross-check (dp4a) -----------------------------------------------------------------------
 template <uint32_t FLAGS>
 __global__ void gemm_i8_simt_kernel(const int8_t* __restrict__ a, int64_t lda, const int8_t* __restrict__ w,
@@ -897,6 +965,13 @@ extern "C" int p2v_gemm_i8(const int8_t* a, int64_t lda, const int8_t* w, int8_t
   if ((rc = make_tmap_kmajor(&ta, a, m, k, lda))) return rc;
   if ((rc = make_tmap_kmajor(&tb, w, n, k, k))) return rc;
   return gemm_i8_tc(ta, tb, out, ld_out, m, n, k, *epi, (cudaStream_t)stream);
+}
+
+extern "C" int p2v_test_gelu_fast(float out_rscale, unsigned long long* counts, void* stream) {
+  P2V_REQUIRE(counts != nullptr && out_rscale > 0.f, "p2v_test_gelu_fast: bad arguments");
+  gelu_fast_sweep_kernel<<<kNumSMs * 8, 256, 0, (cudaStream_t)stream>>>(out_rscale, counts);
+  P2V_CHECK_CUDA(cudaGetLastError());
+  return P2V_OK;
 }
 
 extern "C" int p2v_gemm_set_mode(int mode) {

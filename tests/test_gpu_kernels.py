@@ -228,3 +228,15 @@ def test_error_reporting(cabi):
     assert rc == -1 and b'null' in cabi.lib().p2v_last_error()
     with pytest.raises(cabi.P2VError):
         cabi.check(cabi.lib().p2v_quant_patchify(1, 1, 1, 3, 30, 30, 16, 1.0, 0.0, None))
+
+
+def test_fast_gelu_reproduces_the_erf_codes_for_every_input(cabi):
+    """The fc1 epilogue evaluates erf-GELU with one polynomial + ex2 and a guard band; whenever the guard accepts,
+    the int8 code must equal RNE(gelu_erf(y) / s_out).  Swept over ALL 2^32 fp32 inputs for every power-of-two
+    output grid from 2^0 to 2^-12."""
+    for e in range(0, 13):
+        counts = torch.zeros(3, dtype=torch.int64, device='cuda')
+        cabi.check(cabi.lib().p2v_test_gelu_fast(float(2.0 ** e), counts.data_ptr(), _stream()))
+        bad, rejected, total = (int(v) for v in counts.cpu())
+        assert bad == 0, 'grid 2^-%d: %d accepted inputs round to a different code' % (e, bad)
+        assert total > 2_000_000_000 and rejected <= 2e-3 * total, (e, rejected, total)
