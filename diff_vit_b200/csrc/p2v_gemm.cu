@@ -138,7 +138,7 @@ __device__ __forceinline__ float gelu_code_fast(float y, float half_rso, bool& o
   const float hr = fmul(y, half_rso);
   const float tq = ffma(hr, erfv, hr);
   const float rr = fsub(fadd(tq, 12582912.0f), 12582912.0f);          // RNE(tq) for |tq| < 2^22 (beyond: saturates anyway)
-  ok = ok && (fabsf(fabsf(fsub(tq, rr)) - 0.5f) >= fmul(fabsf(hr), 1.5e-6f));
+  ok = ok & (fabsf(fabsf(fsub(tq, rr)) - 0.5f) >= fmul(fabsf(hr), 1.5e-6f));   // no short circuit: branch-free
   return tq;
 }
 

@@ -148,7 +148,7 @@ __device__ __forceinline__ float ln_code_fast(float xq, const LnRow& row, float 
   const float sM = u2f((fa & 0x807f0000u) | 0x43000000u);
   const float b = fsub(bo, fmul(row.u, go));
   const float Bq = fsub(ffma(b, u2f(p2n), kMagic), kMagic);   // RNE(b 2^N): b 2^N is exact, one rounding in the fma
-  ok = ok && (ex - 0x33800000u < 0x10000000u) && (fabsf(Bq) <= 2097152.0f);
+  ok = ok & (ex - 0x33800000u < 0x10000000u) & (fabsf(Bq) <= 2097152.0f);   // no short circuit: branch-free
   const float y = ffma(sM, xq, Bq);                            // exact product (< 2^18) + integer: one rounding
   return fsub(ffma(y, u2f(0x7f000000u - p2n), kMagic), kMagic);   // RNE(y 2^-N)
 }
