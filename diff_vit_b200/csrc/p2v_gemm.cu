@@ -408,7 +408,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                   const GemmArgs g) {
   extern __shared__ uint8_t smem_raw[];
-  GemmSmem& s = *reinterpret_cast<GemmSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // align by pointer arithmetic, not through an integer: the compiler then still knows these are shared-memory
+  // addresses (LDS / STS instead of generic LD / ST plus window-base arithmetic on every epilogue constant load)
+  GemmSmem& s = *reinterpret_cast<GemmSmem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int tiles_m = (g.m + kBlockM - 1) / kBlockM;
@@ -589,7 +591,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_i8_bs_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                   const GemmArgs g, const BsPlan plan) {
   extern __shared__ uint8_t smem_raw[];
-  BsSmem& s = *reinterpret_cast<BsSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  BsSmem& s = *reinterpret_cast<BsSmem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int tiles_m = (g.m + kBlockM - 1) / kBlockM;
