@@ -74,10 +74,12 @@ embed_assemble_kernel(const int8_t* __restrict__ pe, int8_t* __restrict__ out, i
   const float4 cl4 = *reinterpret_cast<const float4*>(cls_value + c0);
   const float cls[4] = {cl4.x, cl4.y, cl4.z, cl4.w};
   const float embed_rs = __frcp_rn(embed_scale);
-  for (int64_t tok = (int64_t)blockIdx.x * tok_per_block + threadIdx.x / d4; tok < tokens;
-       tok += (int64_t)gridDim.x * tok_per_block) {
-    const int t = (int)(tok % (np + 1));
-    const int img = (int)(tok / (np + 1));
+  // 32-bit token arithmetic (b * (np + 1) < 2^31 is checked at launch): a 64-bit modulo per token costs more than
+  // the whole element math
+  const int ntok = (int)tokens, np1 = np + 1;
+  for (int tok = blockIdx.x * tok_per_block + threadIdx.x / d4; tok < ntok; tok += gridDim.x * tok_per_block) {
+    const int img = tok / np1;
+    const int t = tok - img * np1;
     int q[4];
     uint32_t word = 0;
     if (t > 0) word = __ldg(reinterpret_cast<const uint32_t*>(pe + ((int64_t)img * np + (t - 1)) * d + c0));
@@ -95,7 +97,7 @@ embed_assemble_kernel(const int8_t* __restrict__ pe, int8_t* __restrict__ out, i
       }
       q[j] = quant_div_guarded(fadd(xe, pos[j]), so[j], rso[j], 0.f);
     }
-    *reinterpret_cast<uint32_t*>(out + tok * d + c0) = pack4i(q[0], q[1], q[2], q[3]);
+    *reinterpret_cast<uint32_t*>(out + (int64_t)tok * d + c0) = pack4i(q[0], q[1], q[2], q[3]);
   }
 }
 
@@ -358,6 +360,7 @@ extern "C" int p2v_embed_assemble(const int8_t* pe, int8_t* out, int b, int np, 
   P2V_REQUIRE(b > 0 && np > 0 && d > 0 && d % 4 == 0, "p2v_embed_assemble: bad shape b=%d np=%d d=%d", b, np, d);
   const int d4 = d / 4;
   P2V_REQUIRE(d4 <= 256, "p2v_embed_assemble: d=%d exceeds 1024 channels", d);
+  P2V_REQUIRE((int64_t)b * (np + 1) < (1ll << 31), "p2v_embed_assemble: too many tokens");
   const int block = (256 / d4) * d4;   // a whole number of tokens per block
   const int64_t tokens = (int64_t)b * (np + 1);
   embed_assemble_kernel<<<grid_for(tokens, block / d4), block, 0, (cudaStream_t)stream>>>(
