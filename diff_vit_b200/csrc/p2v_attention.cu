@@ -67,6 +67,11 @@ __device__ __forceinline__ void mma_u8s8(int (&c)[4], uint32_t a0, uint32_t a1, 
 
 // Table lookups of the hot loops through 32-bit shared-window addresses: base + (byte << k) is a single LEA,
 // where indexing a generic pointer costs a subtract, a scaled add and the window base.
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+  uint32_t v;
+  asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
 __device__ __forceinline__ float lds_f32(uint32_t addr) {
   float v;
   asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
@@ -125,6 +130,9 @@ struct AttSmem {
   // rev + (255 - rowmax) they are addressed by the biased code byte itself: one LEA per lookup
   float rev_r3[256];   // 1 / (3 e(d))
   int zks[kMaxKeys];   // kZp: z * sum_d k[j][d] per key (asymmetric q/k/v codes)
+  uint32_t rev_ehi[256];   // high word of (double)e(d) when its low word is zero (e has <= 21 significant bits: it is
+                           // z * 2^(32-q) with z a 10..20-bit integer), so the row sums need no fp32 -> fp64 convert
+  int wide;                // some entry has more significant bits: the sums convert rev_e instead
   float rev_e[256];    // e(d): an integer of <= 24 significant bits, exact in fp32 (4-byte entries: a 32-lane lookup
                        // spreads over all 32 banks, where fp64 entries left 16 bank pairs and twice the conflicts)
 };
@@ -156,11 +164,15 @@ attention_int_kernel(const int8_t* __restrict__ qkv, int8_t* __restrict__ out, i
   const int iz = kZp ? (int)p.in_zp : 0;
 
   // ---- stage K (row-major, padded stride) and V (transposed + permuted) in shared memory ---------------
+  if (tid == 0) sm.wide = 0;
+  __syncthreads();
   for (int i = tid; i < 256; i += blockDim.x) {
     const float e = p.exp_lut[i];
     sm.lut_f[i] = e;
     sm.rev_r3[255 - i] = __fdiv_rn(1.0f, 3.0f * e);   // 3e is exact (<= 24 significant bits)
     sm.rev_e[255 - i] = e;
+    sm.rev_ehi[255 - i] = (uint32_t)__double2hiint((double)e);
+    if (__double2loint((double)e) != 0) sm.wide = 1;
   }
   // K rows with their 16 words stored t-major: word w (columns 4w .. 4w+3) goes to slot (w & 3) * 4 + (w >> 2), so
   // the four B-fragment words of lane t (columns 4t, 16 + 4t, 32 + 4t, 48 + 4t) are one 16-byte load
@@ -217,6 +229,8 @@ attention_int_kernel(const int8_t* __restrict__ qkv, int8_t* __restrict__ out, i
   const int full_steps = n >> 5;            // steps whose 32 keys are all < n
   const float zp_biased = p.score_zp + 128.f;
   const uint32_t rev_e_saddr = (uint32_t)__cvta_generic_to_shared(sm.rev_e);
+  const uint32_t rev_ehi_saddr = (uint32_t)__cvta_generic_to_shared(sm.rev_ehi);
+  const bool wide = sm.wide != 0;
   const uint32_t rev_r3_saddr = (uint32_t)__cvta_generic_to_shared(sm.rev_r3);
   const int cinit = kPot ? 0x4B400000 : 0;   // 1.5 * 2^23 as an accumulator bias (see the score loop)
   const float zq = kPot ? (float)((double)zp_biased - 12582912.0 * (double)p.score_mul) : zp_biased;
@@ -329,6 +343,19 @@ attention_int_kernel(const int8_t* __restrict__ qkv, int8_t* __restrict__ out, i
     const uint32_t revB = rev_e_saddr + ((255 - maxB) << 2);
     {
       double pa[4] = {0.0, 0.0, 0.0, 0.0}, pb[4] = {0.0, 0.0, 0.0, 0.0};   // independent chains: the adds are exact
+      if (!wide) {   // the table word IS the high half of the double: no conversion instruction
+        const uint32_t hiA = rev_ehi_saddr + ((255 - maxA) << 2), hiB = rev_ehi_saddr + ((255 - maxB) << 2);
+#pragma unroll 2
+        for (int w = 0; w < 2 * full_steps; ++w) {
+          const uint32_t wa = *reinterpret_cast<const uint32_t*>(crowA + w * 16);
+          const uint32_t wb = *reinterpret_cast<const uint32_t*>(crowB + w * 16);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            pa[i] += __hiloint2double((int)lds_u32(hiA + (__byte_perm(wa, 0, 0x4440 + i) << 2)), 0);
+            pb[i] += __hiloint2double((int)lds_u32(hiB + (__byte_perm(wb, 0, 0x4440 + i) << 2)), 0);
+          }
+        }
+      } else
 #pragma unroll 2
       for (int w = 0; w < 2 * full_steps; ++w) {
         const uint32_t wa = *reinterpret_cast<const uint32_t*>(crowA + w * 16);
