@@ -106,19 +106,22 @@ __device__ __forceinline__ bool code_guarded(uint32_t bits) {
   return (((bits + kCodeGuard) & 0x7fffffu) < 2 * kCodeGuard) || bits < 0x3f800000u;
 }
 
-// four keys of one packed code word -> four 16-bit probabilities; returns true if any element needs the
-// exact path.  revR = rev_r3 + (255 - rowmax) (biased), so the table is addressed by the code byte directly.
-__device__ __forceinline__ bool prob16x4(uint32_t w, uint32_t revR, float fsum, uint32_t (&v)[4], uint32_t (&bits)[4]) {
-  bool any = false;
+// four keys of one packed code word -> four 16-bit probabilities.  Returns the minimum over the four elements of
+//   (int)((bits - 0x3f800000 + kCodeGuard) & 0x807fff80):  <= 0 exactly when code_guarded() holds for one of them
+// (negative: u < 1; zero: within kCodeGuard ulps of a power of two), so the caller tests one number per word pair.
+// revR = rev_r3 + (255 - rowmax) (biased), so the table is addressed by the code byte directly.
+__device__ __forceinline__ int prob16x4(uint32_t w, uint32_t revR, float fsum, uint32_t (&v)[4], uint32_t (&bits)[4]) {
+  static_assert(kCodeGuard == 64, "the mask below encodes a 64-ulp guard");
+  int worst = 0x7fffffff;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const uint32_t byte = __byte_perm(w, 0, 0x4440 + i);
     bits[i] = __float_as_uint(__fmaf_rn(fsum, lds_f32(revR + (byte << 2)), 0.16666667f));
-    any |= code_guarded(bits[i]);
+    worst = min(worst, (int)((bits[i] - 0x3f7fffc0u) & 0x807fff80u));
     // 1 << (15 - k), k = E - 125: shift counts >= 32 (k >= 16, or the wrapped negative) give 0
     asm("shl.b32 %0, %1, %2;" : "=r"(v[i]) : "r"(1u), "r"(140u - (bits[i] >> 23)));
   }
-  return any;
+  return worst;
 }
 
 struct AttSmem {
@@ -415,9 +418,9 @@ attention_int_kernel(const int8_t* __restrict__ qkv, int8_t* __restrict__ out, i
         const uint32_t wa = *reinterpret_cast<const uint32_t*>(crowA + w * 16);
         const uint32_t wb = *reinterpret_cast<const uint32_t*>(crowB + w * 16);
         uint32_t va[4], vb[4], ba[4], bb[4];
-        const bool fa = prob16x4(wa, lutRA, fsumA, va, ba);
-        const bool fb = prob16x4(wb, lutRB, fsumB, vb, bb);
-        if (fa | fb) {   // rare: a value next to a step of the code function, or a dominant key
+        const int fa = prob16x4(wa, lutRA, fsumA, va, ba);
+        const int fb = prob16x4(wb, lutRB, fsumB, vb, bb);
+        if (min(fa, fb) <= 0) {   // rare: a value next to a step of the code function, or a dominant key
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             if (code_guarded(ba[i])) va[i] = exact_prob16(fsumA, sm.lut_f[maxA - (int)((wa >> (8 * i)) & 0xff)], p.softmax_levels);
