@@ -446,7 +446,7 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int m0 = (tile / tiles_n) * kBlockM, n0 = (tile % tiles_n) * kBlockN;
         for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&s.empty[stage], phase ^ 1);
+          mbar_wait_relaxed(&s.empty[stage], phase ^ 1);
           mbar_expect_tx(&s.full[stage], 2 * kTileBytes);
           tma_load_2d(s.a[stage], &tmap_a, &s.full[stage], kb * kBlockK, m0);
           tma_load_2d(s.b[stage], &tmap_b, &s.full[stage], kb * kBlockK, n0);
@@ -459,7 +459,7 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       constexpr uint32_t idesc = umma_idesc_i8(kBlockM, kBlockN);
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        mbar_wait(&s.acc_empty[acc], acc_phase ^ 1);  // epilogue drained this accumulator
+        mbar_wait_relaxed(&s.acc_empty[acc], acc_phase ^ 1);  // epilogue drained this accumulator
         tc_fence_after_sync();
         const uint32_t tmem_d = tmem_base + acc * kBlockN;
         for (int kb = 0; kb < num_kb; ++kb) {
@@ -639,7 +639,7 @@ gemm_i8_bs_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         uint32_t stage = 0, phase = 0;
         for (int tile = local; tile < tiles_m; tile += cnt) {
           for (int kb = 0; kb < num_kb; ++kb) {
-            mbar_wait(&s.empty[stage], phase ^ 1);
+            mbar_wait_relaxed(&s.empty[stage], phase ^ 1);
             mbar_expect_tx(&s.full[stage], kTileBytes);
             tma_load_2d(s.a[stage], &tmap_a, &s.full[stage], kb * kBlockK, tile * kBlockM);
             if (++stage == kBsStagesA) { stage = 0; phase ^= 1; }
@@ -653,7 +653,7 @@ gemm_i8_bs_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         uint32_t stage = 0, phase = 0, it = 0;
         for (int tile = local; tile < tiles_m; tile += cnt, ++it) {
           const uint32_t p = it & 1;
-          mbar_wait(&s.acc_empty[p], ((it >> 1) & 1) ^ 1);
+          mbar_wait_relaxed(&s.acc_empty[p], ((it >> 1) & 1) ^ 1);
           tc_fence_after_sync();
           const uint32_t tmem_d = tmem_base + p * kBsSlabCols;
           for (int kb = 0; kb < num_kb; ++kb) {
