@@ -75,6 +75,7 @@ SYMBOLS = {
     'p2v_softmax_log_int_f32': (C.c_int, [_vp, _vp, _vp, C.c_int64, C.c_int, C.c_float, C.c_float, C.c_float,
                                           C.c_float, C.c_int, C.c_int, _vp]),
     'p2v_requant_eltwise': (C.c_int, [_vp, _vp, _vp, C.c_int64, C.c_int, _vp, _vp, _vp, C.c_float, _vp]),
+    'p2v_unpack_int4': (C.c_int, [_vp, _vp, C.c_int64, _vp]),
     'p2v_select_histogram': (C.c_int, [_vp, C.c_int64, C.c_uint32, C.c_uint32, C.c_int, _vp, _vp]),
     'p2v_observe_minmax': (C.c_int, [_vp, C.c_int64, C.c_int, C.c_int, _vp, _vp, _vp]),
     'p2v_observe_scale_sse': (C.c_int, [_vp, C.c_int64, C.c_int, C.c_int, _fp, C.c_int, C.c_float, C.c_float, _vp, _vp]),

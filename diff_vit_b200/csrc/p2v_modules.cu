@@ -143,6 +143,36 @@ select_histogram_kernel(const float* __restrict__ x, int64_t total, uint32_t pre
     if (local[i]) atomicAdd(&hist[i], (unsigned long long)local[i]);
 }
 
+// ---- int4-packed weights -> int8 codes ---------------------------------------------------------------------------
+// byte i holds code 2i in its low nibble and code 2i + 1 in its high nibble, both two's complement in [-8, 7].
+// 16 packed bytes in, 32 codes out per thread and step.
+__global__ void __launch_bounds__(256)
+unpack_int4_kernel(const uint8_t* __restrict__ packed, int8_t* __restrict__ out, int64_t nbytes) {
+  const int64_t n16 = nbytes >> 4;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n16; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(packed) + i);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    uint32_t o[8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      // spread the eight nibbles of w[k] over two words, then sign-extend every byte: (x ^ 8) - 8 per nibble
+      const uint32_t lo = w[k] & 0x0f0f0f0fu, hi = (w[k] >> 4) & 0x0f0f0f0fu;
+      const uint32_t a = __byte_perm(lo, hi, 0x5140), b = __byte_perm(lo, hi, 0x7362);   // bytes: l0 h0 l1 h1 | l2 h2 l3 h3
+      o[2 * k] = __vsub4(a ^ 0x08080808u, 0x08080808u);
+      o[2 * k + 1] = __vsub4(b ^ 0x08080808u, 0x08080808u);
+    }
+    uint4* dst = reinterpret_cast<uint4*>(out) + 2 * i;
+    dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+    dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (nbytes & 15)) {   // tail bytes
+    const int64_t i = (n16 << 4) + threadIdx.x;
+    const int b = packed[i];
+    out[2 * i] = (int8_t)(((b & 15) ^ 8) - 8);
+    out[2 * i + 1] = (int8_t)((((b >> 4) & 15) ^ 8) - 8);
+  }
+}
+
 }  // namespace p2v
 
 using namespace p2v;
@@ -188,6 +218,15 @@ extern "C" int p2v_requant_eltwise(const int8_t* a, const int8_t* b, int8_t* out
   P2V_REQUIRE(rows > 0 && d > 0, "p2v_requant_eltwise: bad shape");
   requant_eltwise_kernel<<<grid_cap((rows * d + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
       a, b, out, rows, d, a_scale, b_scale, out_scale, out_zp);
+  P2V_CHECK_CUDA(cudaGetLastError());
+  return P2V_OK;
+}
+
+extern "C" int p2v_unpack_int4(const uint8_t* packed, int8_t* out, int64_t nbytes, void* stream) {
+  P2V_REQUIRE(packed && out && nbytes > 0, "p2v_unpack_int4: bad arguments");
+  P2V_REQUIRE((reinterpret_cast<uintptr_t>(packed) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
+              "p2v_unpack_int4: buffers must be 16-byte aligned");
+  unpack_int4_kernel<<<grid_cap((nbytes / 16 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(packed, out, nbytes);
   P2V_CHECK_CUDA(cudaGetLastError());
   return P2V_OK;
 }

@@ -64,8 +64,19 @@ class _BoundPlan:
 
     def _linear(self, lp):
         d = _cabi.LinearDesc()
-        d.w = self._p(lp.w)
-        d.n, d.k = lp.w.shape
+        if lp.w is not None:
+            d.w = self._p(lp.w)
+            d.n, d.k = lp.w.shape
+        else:   # int4-packed layer of a serialised plan: nibbles are expanded to int8 codes on the device
+            packed = _dev(lp.w4, self.device)
+            n, k = lp.w4.shape[0], lp.w4.shape[1] * 2
+            codes = torch.empty((n, k), dtype=torch.int8, device=self.device)
+            _cabi.check(_cabi.lib().p2v_unpack_int4(packed.data_ptr(), codes.data_ptr(), packed.numel(),
+                                                    _cabi.current_stream()))
+            torch.cuda.current_stream(self.device).synchronize()
+            self.keep.append(codes)
+            d.w = codes.data_ptr()
+            d.n, d.k = n, k
         e = d.epi
         e.acc_scale, e.bias = self._p(lp.acc_scale), self._p(lp.bias)
         e.out_scale, e.out_rscale = self._p(lp.out_scale), self._p(lp.out_rscale)

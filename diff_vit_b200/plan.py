@@ -79,6 +79,36 @@ class LinearPlan:
     flags: int
     res_scale: Optional[torch.Tensor] = None
     out2_scale: Optional[torch.Tensor] = None
+    bits: int = 8                             # weight width of this layer (4: codes in [-8, 7])
+    w4: Optional[torch.Tensor] = None         # uint8 [n, k / 2]: the int4 codes two per byte (even k in the low nibble);
+                                              # serialised plans carry 4-bit layers this way and leave `w` empty
+
+    def codes(self):
+        """int8 [n, k] weight codes, unpacking the nibbles of a packed 4-bit layer (host side)."""
+        if self.w is not None:
+            return self.w
+        return unpack_int4(self.w4)
+
+    def pack(self):
+        """Move a 4-bit layer to its packed form (in place); 8-bit layers are left alone."""
+        if self.bits == 4 and self.w is not None and self.w.shape[1] % 2 == 0:
+            self.w4, self.w = pack_int4(self.w), None
+        return self
+
+
+def pack_int4(w):
+    """int8 codes in [-8, 7], [n, k] with k even -> uint8 [n, k / 2], element 2i in the low nibble of byte i."""
+    w = w.to(torch.int16)
+    if int(w.min()) < -8 or int(w.max()) > 7:
+        raise ValueError('pack_int4: codes outside [-8, 7]')
+    return ((w[:, 0::2] & 0xF) | ((w[:, 1::2] & 0xF) << 4)).to(torch.uint8).contiguous()
+
+
+def unpack_int4(packed):
+    p = packed.to(torch.int16)
+    lo, hi = p & 0xF, (p >> 4) & 0xF
+    out = torch.stack((lo, hi), dim=-1).reshape(packed.shape[0], -1)
+    return torch.where(out > 7, out - 16, out).to(torch.int8).contiguous()
 
 
 @dataclass
@@ -218,7 +248,7 @@ class _Builder:
             # asymmetric input (omse observer): sum_k (q_k - z) w_nk = acc_n - z * sum_k w_nk; the second term is a
             # per-channel constant and joins the bias, so the GEMM itself still multiplies raw int8 codes
             bias = (bias.double() - in_zp * acc_scale.double() * codes.double().sum(1)).float()
-        plan = LinearPlan(w=codes.to(torch.int8).contiguous(), acc_scale=acc_scale,
+        plan = LinearPlan(w=codes.to(torch.int8).contiguous(), acc_scale=acc_scale, bits=int(bits),
                           bias=bias, out_scale=out_vec, out_rscale=1.0 / out_vec,
                           out_zp=float(torch.as_tensor(out_zp).reshape(-1)[0]), flags=flags)
         if residual is not None:
@@ -336,9 +366,24 @@ def _flatten(obj, prefix, out):
         out[prefix] = obj
 
 
-def save_plan(plan, path):
-    """Write a VitPlan to a compressed .npz file."""
+def _linear_plans(plan):
+    yield plan.patch_embed
+    for blk in plan.blocks:
+        yield from (blk.qkv, blk.proj, blk.fc1, blk.fc2)
+    yield plan.head
+
+
+def save_plan(plan, path, pack4=True):
+    """Write a VitPlan to a compressed .npz file.  4-bit layers are stored int4-packed (two codes per byte);
+    the engine unpacks them on the device when the plan is bound (`p2v_unpack_int4`)."""
+    import copy
     import numpy as np
+    if pack4:
+        plan = copy.copy(plan)
+        plan.patch_embed, plan.head = copy.copy(plan.patch_embed).pack(), copy.copy(plan.head).pack()
+        plan.blocks = [copy.copy(b) for b in plan.blocks]
+        for b in plan.blocks:
+            b.qkv, b.proj, b.fc1, b.fc2 = (copy.copy(l).pack() for l in (b.qkv, b.proj, b.fc1, b.fc2))
     flat = {}
     _flatten(plan, 'plan', flat)
     np.savez_compressed(path, **{k: np.asarray(v) for k, v in flat.items()})

@@ -161,6 +161,10 @@ int p2v_softmax_log_int_f32(const float* x, float* out, uint8_t* codes, int64_t 
  * out = clamp(RNE((a * a_scale[c] + b * b_scale[c]) / out_scale[c] + out_zp), -128, 127); b may be NULL (re-quantize a). */
 int p2v_requant_eltwise(const int8_t* a, const int8_t* b, int8_t* out, int64_t rows, int d, const float* a_scale,
                         const float* b_scale, const float* out_scale, float out_zp, void* stream);
+/* int4-packed weight codes (the storage form of 4-bit layers in serialised plans, BASELINE config 4) -> the int8
+ * codes the tensor-core GEMM consumes (tcgen05 has no int4 kind): byte i holds code 2i in its low nibble and code
+ * 2i + 1 in its high nibble, two's complement in [-8, 7].  out has 2 * nbytes entries. */
+int p2v_unpack_int4(const uint8_t* packed, int8_t* out, int64_t nbytes, void* stream);
 /* One pass of an exact radix select over fp32 data (the order statistics behind torch.quantile / np.percentile in
  * models/ptq/observer/percentile.py:27-38): hist[2048] (device, uint64, ACCUMULATED) counts bits
  * [shift, shift + 11) of the order-preserving key of every element whose key matches prefix under prefix_mask.

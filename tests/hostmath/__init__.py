@@ -35,7 +35,7 @@ def _f(t):
 
 def gemm_epilogue(a, lp, residual=None, want_f32=False):
     """a int8 [m,k]; lp LinearPlan -> (codes, aux, f32)"""
-    w = lp.w.numpy().astype(np.int64)
+    w = lp.codes().numpy().astype(np.int64)
     acc = (a.astype(np.int64) @ w.T).astype(np.int32)
     m, n = acc.shape
     out = np.empty((m, n), np.int8)

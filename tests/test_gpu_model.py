@@ -318,3 +318,29 @@ def test_omse_zero_points_through_the_engine(micro_golden):
     ref_logits, _ = orc.forward(state, x, [8] * 10, capture=False)
     lsb = float(state['act']['act_out'][0])
     assert np.abs(ref_logits.numpy() - logits.cpu().numpy()).max() <= 8 * lsb
+
+
+def test_int4_packed_plan_runs_on_the_engine(micro_model, micro_state, micro_golden, tmp_path):
+    """BASELINE config 4 storage: a serialised mixed-precision plan carries its 4-bit layers int4-packed; the engine
+    expands them on the device (p2v_unpack_int4) and must give the logits of the in-memory plan bit for bit."""
+    from diff_vit_b200 import _cabi
+    from diff_vit_b200.engine import IntegerEngine
+    from diff_vit_b200.plan import build_plan, load_plan, save_plan, unpack_int4
+    z = micro_golden
+    bc = [int(v) for v in z['mixed/bit_config']]
+    x = torch.from_numpy(z['x_eval']).cuda()
+    want = micro_model.integer_engine().forward(x, bc)
+    path = str(tmp_path / 'mixed.npz')
+    save_plan(build_plan(micro_state, bc), path)
+    plan = load_plan(path)
+    assert any(l.w is None and l.w4 is not None for b in plan.blocks for l in (b.qkv, b.proj, b.fc1, b.fc2))
+    got = IntegerEngine(plans=[plan]).forward(x, bc)
+    assert torch.equal(got, want)
+    # the kernel on its own, including a length that is not a multiple of 16 bytes
+    g = torch.Generator().manual_seed(9)
+    for nbytes in (16 * 1000, 16 * 37 + 5):
+        packed = torch.randint(0, 256, (1, nbytes), dtype=torch.uint8, generator=g)
+        out = torch.empty(2 * nbytes, dtype=torch.int8, device='cuda')
+        pd = packed.cuda()
+        _cabi.check(_cabi.lib().p2v_unpack_int4(pd.data_ptr(), out.data_ptr(), nbytes, _cabi.current_stream()))
+        assert torch.equal(out.cpu().reshape(1, -1), unpack_int4(packed))

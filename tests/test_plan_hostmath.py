@@ -101,11 +101,24 @@ def test_plan_round_trips_through_npz(micro_state, micro_golden, tmp_path):
     from diff_vit_b200.plan import load_plan, save_plan
     plan = build_plan(micro_state, [int(v) for v in micro_golden['mixed/bit_config']])
     path = str(tmp_path / 'plan.npz')
-    save_plan(plan, path)
+    save_plan(plan, path, pack4=False)
     back = load_plan(path)
     assert back.bit_config == plan.bit_config and back.arch == plan.arch
     a, b = list(plan.tensors()), list(back.tensors())
     assert len(a) == len(b) > 50 and all(x.dtype == y.dtype and torch.equal(x, y) for x, y in zip(a, b))
+    # default: 4-bit layers travel int4-packed (two codes per byte) and are expanded again when used
+    from diff_vit_b200.plan import _linear_plans, pack_int4, unpack_int4
+    save_plan(plan, path)
+    back = load_plan(path)
+    packed = [(o, l) for o, l in zip(_linear_plans(plan), _linear_plans(back)) if o.bits == 4]
+    assert len(packed) >= 2 and all(l.w is None and l.w4.dtype == torch.uint8 and l.w4.shape[1] * 2 == o.w.shape[1]
+                                    and torch.equal(l.codes(), o.w) for o, l in packed)
+    assert all(l.w4 is None and torch.equal(l.w, o.w) for o, l in zip(_linear_plans(plan), _linear_plans(back)) if o.bits == 8)
+    assert all(o.w is not None for o in _linear_plans(plan))                       # the caller's plan is untouched
+    edge = torch.tensor([[-8, 7, -1, 0], [3, -4, 5, -6]], dtype=torch.int8)
+    assert torch.equal(unpack_int4(pack_int4(edge)), edge) and pack_int4(edge).tolist() == [[0x78, 0x0F], [0xC3, 0xA5]]
+    with pytest.raises(ValueError):
+        pack_int4(torch.tensor([[8, 0]], dtype=torch.int8))
     assert back.blocks[1].attn.out_mul == plan.blocks[1].attn.out_mul and back.blocks[0].norm2.pot == plan.blocks[0].norm2.pot
     logits, _ = hostmath.run_plan(back, micro_golden['x_eval'])
     np.testing.assert_array_equal(logits, micro_golden['mixed/logits'])
