@@ -213,12 +213,12 @@ layernorm_int_pot_kernel(const int8_t* __restrict__ in, int64_t in_row_stride, i
         sumsq += v * v;
       }
     }
-    long long sumsq64 = sumsq;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      sum += __shfl_xor_sync(0xffffffffu, sum, o);
-      sumsq64 += __shfl_xor_sync(0xffffffffu, sumsq64, o);
-    }
+    // warp totals with the REDUX unit (one instruction per 32-bit value instead of five shuffle / add rounds); the
+    // sum of squares can pass 2^32 for large masks, so its two 16-bit halves are reduced separately
+    sum = __reduce_add_sync(0xffffffffu, sum);
+    const unsigned sq_lo = __reduce_add_sync(0xffffffffu, (unsigned)sumsq & 0xffffu);
+    const unsigned sq_hi = __reduce_add_sync(0xffffffffu, (unsigned)sumsq >> 16);
+    const long long sumsq64 = ((long long)sq_hi << 16) + (long long)sq_lo;
     const LnRow st = ln_row_stats((long long)sum, sumsq64, d, p.in_scale1);
 #pragma unroll
     for (int g = 0; g < G; ++g) {
