@@ -132,15 +132,19 @@ struct LnRow {
 };
 
 // sum, sumsq: exact integer sums of x_q * mask over the row.  C: channel count.
-P2V_HD LnRow ln_row_stats(long long sum, long long sumsq, int C, float in_scale1) {
+// scale_over_c = fl(in_scale1 / C), the row-independent factor of the standard deviation
+P2V_HD LnRow ln_row_stats(long long sum, long long sumsq, int C, float in_scale1, float scale_over_c) {
   float fs = (float)sum, fq = (float)sumsq, fc = (float)C;
   float mean = fmul(fdiv(fs, fc), in_scale1);                       // x_q.mean(-1) * in_scale1
   float var = fsub(fmul(fc, fq), fmul(fs, fs));                     // C*sum(x^2) - sum(x)^2
-  float stdv = fmul(fdiv(in_scale1, fc), fsqrt(var));               // (in_scale1 / C) * sqrt(.)
+  float stdv = fmul(scale_over_c, fsqrt(var));                      // (in_scale1 / C) * sqrt(.)
   LnRow r;
   r.t = fdiv(in_scale1, stdv);
   r.u = fdiv(mean, stdv);
   return r;
+}
+P2V_HD LnRow ln_row_stats(long long sum, long long sumsq, int C, float in_scale1) {
+  return ln_row_stats(sum, sumsq, C, in_scale1, fdiv(in_scale1, (float)C));
 }
 
 // One element: xq = code * mask (integer-valued), gamma/beta the LN affine, out_scale the LN output

@@ -155,6 +155,15 @@ __device__ __forceinline__ float ln_code_fast(float xq, const LnRow& row, float 
   return fsub(ffma(y, u2f(0x7f000000u - p2n), kMagic), kMagic);   // RNE(y 2^-N)
 }
 
+// byte J of w, sign-extended, in one PRMT (selector nibble 8 | J replicates the byte's msb; __byte_perm would mask
+// that bit away, hence the PTX)
+__device__ __forceinline__ int sext_byte(uint32_t w, int j) {
+  const uint32_t sel = j == 0 ? 0x8880u : (j == 1 ? 0x9991u : (j == 2 ? 0xaaa2u : 0xbbb3u));   // constant after unrolling
+  int v;
+  asm("prmt.b32 %0, %1, 0, %2;" : "=r"(v) : "r"(w), "r"(sel));
+  return v;
+}
+
 // G = 4-channel groups per lane.  FULL: d == 128 * G (no partial group).  DUMP: also write the unclamped LN codes.
 template <int G, bool FULL, bool DUMP>
 __global__ void __launch_bounds__(256, 3)
@@ -184,6 +193,7 @@ layernorm_int_pot_kernel(const int8_t* __restrict__ in, int64_t in_row_stride, i
       for (int j = 0; j < 4; ++j) { go[g][j] = 0.f; bo[g][j] = 0.f; pm[g][j] = 0.f; mk[g][j] = 0; }
     }
   }
+  const float scale_over_c = fdiv(p.in_scale1, (float)d);   // row-independent part of ln_row_stats
   // software pipeline: the next row's codes are in flight while this row is normalised
   uint32_t next_w[G];
   int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -207,7 +217,8 @@ layernorm_int_pot_kernel(const int8_t* __restrict__ in, int64_t in_row_stride, i
     for (int g = 0; g < G; ++g) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const int v = (int)(int8_t)((cur_w[g] >> (8 * j)) & 0xff) * mk[g][j];
+        // one PRMT sign-extends byte j (selector nibble 8 | j replicates its msb)
+        const int v = sext_byte(cur_w[g], j) * mk[g][j];
         xq[g][j] = (float)v;
         sum += v;
         sumsq += v * v;
@@ -219,7 +230,7 @@ layernorm_int_pot_kernel(const int8_t* __restrict__ in, int64_t in_row_stride, i
     const unsigned sq_lo = __reduce_add_sync(0xffffffffu, (unsigned)sumsq & 0xffffu);
     const unsigned sq_hi = __reduce_add_sync(0xffffffffu, (unsigned)sumsq >> 16);
     const long long sumsq64 = ((long long)sq_hi << 16) + (long long)sq_lo;
-    const LnRow st = ln_row_stats((long long)sum, sumsq64, d, p.in_scale1);
+    const LnRow st = ln_row_stats((long long)sum, sumsq64, d, p.in_scale1, scale_over_c);
 #pragma unroll
     for (int g = 0; g < G; ++g) {
       const int grp = g * 32 + lane;
