@@ -7,16 +7,18 @@
 // Integer formulation (probed bit-exact against the reference):
 //   score code   sc = clamp(RNE(acc * 2^(2 e_qkv - 3 - e_score)))          acc = sum_d q*k   (|acc| < 2^20)
 //   integer exp  e(d) for d = rowmax - sc in [0, 255]: a 256-entry table built on the host with the
-//                reference's own expressions; row sum exact in 64-bit integers
+//                reference's own expressions; the row sum is exact (integers < 2^51 accumulated in fp64)
 //   log2 code    k = log_round(RNE(sum / e)) in [0, 15], 16 = probability 0
 //   AV           acc2 = sum_j v_j * 2^(15 - k_j)  (int32), out = clamp(RNE(acc2 * 2^(e_qkv - 15 - e_out)))
 // The probabilities 2^(15-k) span 16 bits, so P is split into two u8 planes (k <= 7 -> 2^(7-k) in units of
 // 2^8; k >= 8 -> 2^(15-k)) and the AV product is two u8 x s8 tensor-core MMAs recombined as (hi << 8) + lo.
 //
-// One CTA = one (image, head), K/V staged once; each of its 7 warps walks 16-row query tiles, all keys.  Both products use
-// mma.sync m16n8k32 (IMMA): the score fragment layout (row g, cols 2t,2t+1 of each 8-key tile) is re-used
-// directly as the A operand of the AV product by permuting the key order of V when it is transposed into
-// shared memory, so the 4-bit codes never round-trip through memory.
+// One CTA = one (image, head), K/V staged once; each of its 7 warps walks 16-row query tiles, all keys; three CTAs
+// per SM.  Both products use mma.sync m16n8k32 (IMMA): the score fragment layout (row g, cols 2t,2t+1 of each 8-key
+// tile) is re-used directly as the A operand of the AV product by permuting the key order of V when it is transposed
+// into shared memory, so the 4-bit codes never leave the SM.  The kernel is bound by CUDA-core issue and
+// shared-memory wavefronts of the softmax code path, not by the tensor pipe (profiles/r1_summary.md items 11-12, 19);
+// what each phase does to stay cheap is described where it happens.
 #include <math.h>
 
 #include "p2v_common.cuh"
