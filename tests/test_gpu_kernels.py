@@ -119,6 +119,10 @@ def _ln_plan(rng, d, pot):
     mask[rng.integers(0, d)] = 1.0
     gamma = rng.uniform(0.5, 1.5, size=d).astype(np.float32) * rng.choice([-1.0, 1.0], size=d, p=[0.1, 0.9]).astype(np.float32)
     beta = (rng.standard_normal(d) * 0.1).astype(np.float32)
+    # the corners of get_MN (layers.py:234-238): A = 0, N clamped at 31 (tiny |A|) and at 0 with M clamped at 255
+    # (huge |A|), plus an offset beyond the fast path's 2^21 bound
+    gamma[2], gamma[3], gamma[5], gamma[6] = 0.0, 1e-9, -3e-10, 4e5
+    beta[7] = 3e5
     cs = (2.0 ** rng.integers(0, 3, size=d)).astype(np.float32)
     cs2 = (2.0 ** rng.integers(0, 3, size=d)).astype(np.float32)
     s_out = np.float32(2.0 ** -5) if pot else np.float32(0.0291)
