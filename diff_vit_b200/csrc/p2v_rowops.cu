@@ -166,7 +166,7 @@ __device__ __forceinline__ int sext_byte(uint32_t w, int j) {
 
 // G = 4-channel groups per lane.  FULL: d == 128 * G (no partial group).  DUMP: also write the unclamped LN codes.
 template <int G, bool FULL, bool DUMP>
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256, 2)
 layernorm_int_pot_kernel(const int8_t* __restrict__ in, int64_t in_row_stride, int8_t* __restrict__ out,
                          int32_t* __restrict__ ln_codes, int rows, int d, const p2v_layernorm p) {
   const int lane = threadIdx.x & 31;
@@ -393,7 +393,7 @@ extern "C" int p2v_layernorm_int(const int8_t* in, int64_t in_row_stride, int8_t
   if (p->pot) {
     P2V_REQUIRE(p->ln_out_rscale && p->post_mul, "p2v_layernorm_int: pot path needs ln_out_rscale and post_mul");
     const int groups = (d / 4 + 31) / 32;
-    const int pgrid = grid < kNumSMs * 3 ? grid : kNumSMs * 3;   // persistent warps (3 resident CTAs per SM): constants stay in registers
+    const int pgrid = grid < kNumSMs * 2 ? grid : kNumSMs * 2;   // persistent warps (3 resident CTAs per SM): constants stay in registers
 #define P2V_LN_LAUNCH(G_)                                                                                          \
   do {                                                                                                             \
     const bool full = d == 128 * (G_);                                                                             \
