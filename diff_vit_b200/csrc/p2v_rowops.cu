@@ -393,7 +393,7 @@ extern "C" int p2v_layernorm_int(const int8_t* in, int64_t in_row_stride, int8_t
   if (p->pot) {
     P2V_REQUIRE(p->ln_out_rscale && p->post_mul, "p2v_layernorm_int: pot path needs ln_out_rscale and post_mul");
     const int groups = (d / 4 + 31) / 32;
-    const int pgrid = grid < kNumSMs * 2 ? grid : kNumSMs * 2;   // persistent warps (3 resident CTAs per SM): constants stay in registers
+    const int pgrid = grid < kNumSMs * 2 ? grid : kNumSMs * 2;   // persistent warps (2 resident CTAs per SM, 119 registers: three CTAs at 80 registers spilled and were slower): constants stay in registers
 #define P2V_LN_LAUNCH(G_)                                                                                          \
   do {                                                                                                             \
     const bool full = d == 128 * (G_);                                                                             \
