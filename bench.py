@@ -35,7 +35,7 @@ def parse():
     ap.add_argument('--model', default=MODEL)
     ap.add_argument('--batch', type=int, default=BATCH, help='images per GPU per step')
     ap.add_argument('--calib-batch', type=int, default=32)
-    ap.add_argument('--e2e-steps', type=int, default=10)
+    ap.add_argument('--e2e-steps', type=int, default=40, help='batches of the host-buffer serving loop (its un-overlapped first upload is inside the timed region)')
     ap.add_argument('--cpu-sample', type=int, default=32, help='images in the CPU-baseline sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     return ap.parse_args()
