@@ -64,3 +64,22 @@ def test_calibration_keeps_the_distance_rows(micro_model):
     assert len(gd) == len(micro_model.flops()) - 1 and all(len(row) == 4 for row in gd)
     cfg = [8] * len(micro_model.flops())
     assert search.omega(cfg, gd) >= 0.0 and torch.isfinite(torch.tensor(search.omega(cfg, gd)))
+
+
+def test_test_quant_entry_point_float_path_on_cpu():
+    """The command-line entry point parses the reference's flags and runs the float model on CPU (the quantized
+    branch needs the GPU engine and is exercised by the GPU suite / the bench box)."""
+    import os
+    import subprocess
+    import sys
+    from conftest import ROOT
+    out = subprocess.run([sys.executable, os.path.join(ROOT, 'test_quant.py'), '--model', 'deit_tiny', '--device', 'cpu',
+                          '--val-batchsize', '2', '--data', 'synthetic:1', '--ptf', 'True', '--lis', 'True',
+                          '--quant-method', 'minmax', '--calib-batchsize', '4', '--seed', '1'],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert 'float model: 2 hits' in out.stdout
+    bad = subprocess.run([sys.executable, os.path.join(ROOT, 'test_quant.py'), '--quant', '--device', 'cpu',
+                          '--val-batchsize', '2', '--calib-batchsize', '2', '--data', 'synthetic:1'],
+                         capture_output=True, text=True, timeout=900)
+    assert bad.returncode != 0 and 'no CPU fallback' in (bad.stderr + bad.stdout)
