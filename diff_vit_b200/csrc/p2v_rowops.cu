@@ -155,6 +155,28 @@ __device__ __forceinline__ float ln_code_fast(float xq, const LnRow& row, float 
   return fsub(ffma(y, u2f(0x7f000000u - p2n), kMagic), kMagic);   // RNE(y 2^-N)
 }
 
+// Two adjacent elements at once with the packed fp32 instructions of sm_100 (fma.rn.f32x2 and friends: each half
+// rounds exactly like the scalar _rn op, so the codes are those of ln_code_fast); the bit-domain steps stay scalar.
+__device__ __forceinline__ void ln_code_fast2(const float (&xq)[2], const LnRow& row, const float (&go)[2],
+                                              const float (&bo)[2], bool& ok, float (&code)[2]) {
+  const float2 kMagic = make_float2(12582912.0f, 12582912.0f), kMagicNeg = make_float2(-12582912.0f, -12582912.0f);
+  const float2 g2 = make_float2(go[0], go[1]);
+  const float2 A = __fmul2_rn(make_float2(row.t, row.t), g2);
+  const uint32_t fa0 = f2u(A.x), fa1 = f2u(A.y);
+  const uint32_t ex0 = fa0 & 0x7f800000u, ex1 = fa1 & 0x7f800000u;
+  const uint32_t p0 = 0x82800000u - ex0, p1 = 0x82800000u - ex1;               // bits of 2^(7 - e)
+  const float2 sM = make_float2(u2f((fa0 & 0x807f0000u) | 0x43000000u), u2f((fa1 & 0x807f0000u) | 0x43000000u));
+  const float2 ugn = __fmul2_rn(make_float2(-row.u, -row.u), g2);              // -(u go): negation is exact
+  const float2 b = __fadd2_rn(make_float2(bo[0], bo[1]), ugn);                 // bo - u go
+  const float2 Bq = __fadd2_rn(__ffma2_rn(b, make_float2(u2f(p0), u2f(p1)), kMagic), kMagicNeg);
+  ok = ok & (ex0 - 0x33800000u < 0x10000000u) & (ex1 - 0x33800000u < 0x10000000u) &
+       (fabsf(Bq.x) <= 2097152.0f) & (fabsf(Bq.y) <= 2097152.0f);
+  const float2 y = __ffma2_rn(sM, make_float2(xq[0], xq[1]), Bq);
+  const float2 c = __fadd2_rn(__ffma2_rn(y, make_float2(u2f(0x7f000000u - p0), u2f(0x7f000000u - p1)), kMagic), kMagicNeg);
+  code[0] = c.x;
+  code[1] = c.y;
+}
+
 // byte J of w, sign-extended, in one PRMT (selector nibble 8 | J replicates the byte's msb; __byte_perm would mask
 // that bit away, hence the PTX)
 __device__ __forceinline__ int sext_byte(uint32_t w, int j) {
@@ -238,15 +260,28 @@ layernorm_int_pot_kernel(const int8_t* __restrict__ in, int64_t in_row_stride, i
         float v[4], code[4];
         bool ok = true;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) code[j] = ln_code_fast(xq[g][j], st, go[g][j], bo[g][j], ok);
+        for (int j = 0; j < 4; j += 2) {
+          const float x2[2] = {xq[g][j], xq[g][j + 1]}, g2[2] = {go[g][j], go[g][j + 1]}, b2[2] = {bo[g][j], bo[g][j + 1]};
+          float c2[2];
+          ln_code_fast2(x2, st, g2, b2, ok, c2);
+          code[j] = c2[0];
+          code[j + 1] = c2[1];
+        }
         if (!ok) {   // rare: a dyadic exponent outside [0, 31] before clamping, or a huge offset
 #pragma unroll
           for (int j = 0; j < 4; ++j) code[j] = ln_code_folded(xq[g][j], st, go[g][j], bo[g][j]);
         }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          if (DUMP) ln_codes[(int64_t)row * d + grp * 4 + j] = (int)code[j];
-          v[j] = ffma(code[j], pm[g][j], p.post_zp);   // code * 2^k is exact: one rounding, like mul then add
+        for (int j = 0; j < 4; j += 2) {
+          if (DUMP) {
+            ln_codes[(int64_t)row * d + grp * 4 + j] = (int)code[j];
+            ln_codes[(int64_t)row * d + grp * 4 + j + 1] = (int)code[j + 1];
+          }
+          // code * 2^k is exact: one rounding, like mul then add
+          const float2 v2 = __ffma2_rn(make_float2(code[j], code[j + 1]), make_float2(pm[g][j], pm[g][j + 1]),
+                                       make_float2(p.post_zp, p.post_zp));
+          v[j] = v2.x;
+          v[j + 1] = v2.y;
         }
         *reinterpret_cast<uint32_t*>(out + (int64_t)row * d + grp * 4) = pack_sat4f(v[0], v[1], v[2], v[3]);
       }
