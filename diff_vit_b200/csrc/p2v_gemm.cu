@@ -93,12 +93,20 @@ __device__ __forceinline__ float div_round(float y, float s, float rs, float zp)
 // taken branch per group re-does the flagged elements exactly.
 __device__ __forceinline__ void div_round4(const float (&y)[4], const float (&s)[4], const float (&rs)[4], float zp,
                                            float (&r)[4]) {
+  // element pairs on the packed fp32 instructions (each half rounds like the scalar _rn op)
+  const float2 zp2 = make_float2(zp, zp), kMagic = make_float2(12582912.0f, 12582912.0f);
+  const float2 kMagicNeg = make_float2(-12582912.0f, -12582912.0f), kNegOne = make_float2(-1.0f, -1.0f);
   uint32_t flags = 0;
 #pragma unroll
-  for (int e = 0; e < 4; ++e) {
-    const float t = fadd(fmul(y[e], rs[e]), zp);
-    r[e] = rne_small(t);
-    flags |= (fabsf(fabsf(fsub(t, r[e])) - 0.5f) < kTieGuard) ? (1u << e) : 0u;
+  for (int e = 0; e < 4; e += 2) {
+    // (a contraction of this mul + add into one fma moves t by at most one ulp, far inside the tie guard)
+    const float2 t = fadd2(fmul2(make_float2(y[e], y[e + 1]), make_float2(rs[e], rs[e + 1])), zp2);
+    const float2 rr = fadd2(fadd2(t, kMagic), kMagicNeg);      // rne_small
+    const float2 df = ffma2(rr, kNegOne, t);                       // t - r, exact
+    r[e] = rr.x;
+    r[e + 1] = rr.y;
+    flags |= (fabsf(fabsf(df.x) - 0.5f) < kTieGuard) ? (1u << e) : 0u;
+    flags |= (fabsf(fabsf(df.y) - 0.5f) < kTieGuard) ? (2u << e) : 0u;
   }
   if (flags) {
 #pragma unroll
@@ -242,7 +250,14 @@ __device__ __forceinline__ void epilogue16(const uint32_t (&acc)[16], const floa
       // fp32: dequantize residual stream and branch, add, re-quantize on the block-level grid
       float sum[4], q2[4];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) sum[e] = fadd(fmul(res[e], sr[e]), fmul(code[j4 + e], so[e]));
+      for (int e = 0; e < 4; e += 2) {
+        // packed products, scalar adds: ptxas contracts a packed mul feeding a packed add into one FFMA2 even with
+        // explicit .rn (seen in the SASS), which would round once where the reference rounds twice
+        const float2 pr = fmul2(make_float2(res[e], res[e + 1]), make_float2(sr[e], sr[e + 1]));
+        const float2 pc = fmul2(make_float2(code[j4 + e], code[j4 + e + 1]), make_float2(so[e], so[e + 1]));
+        sum[e] = fadd(pr.x, pc.x);
+        sum[e + 1] = fadd(pr.y, pc.y);
+      }
       div_round4(sum, s2, r2, 0.f, q2);
 #pragma unroll
       for (int e = 0; e < 4; ++e) code[j4 + e] = q2[e];

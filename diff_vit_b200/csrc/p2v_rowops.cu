@@ -161,18 +161,20 @@ __device__ __forceinline__ void ln_code_fast2(const float (&xq)[2], const LnRow&
                                               const float (&bo)[2], bool& ok, float (&code)[2]) {
   const float2 kMagic = make_float2(12582912.0f, 12582912.0f), kMagicNeg = make_float2(-12582912.0f, -12582912.0f);
   const float2 g2 = make_float2(go[0], go[1]);
-  const float2 A = __fmul2_rn(make_float2(row.t, row.t), g2);
+  const float2 A = fmul2(make_float2(row.t, row.t), g2);
   const uint32_t fa0 = f2u(A.x), fa1 = f2u(A.y);
   const uint32_t ex0 = fa0 & 0x7f800000u, ex1 = fa1 & 0x7f800000u;
   const uint32_t p0 = 0x82800000u - ex0, p1 = 0x82800000u - ex1;               // bits of 2^(7 - e)
   const float2 sM = make_float2(u2f((fa0 & 0x807f0000u) | 0x43000000u), u2f((fa1 & 0x807f0000u) | 0x43000000u));
-  const float2 ugn = __fmul2_rn(make_float2(-row.u, -row.u), g2);              // -(u go): negation is exact
-  const float2 b = __fadd2_rn(make_float2(bo[0], bo[1]), ugn);                 // bo - u go
-  const float2 Bq = __fadd2_rn(__ffma2_rn(b, make_float2(u2f(p0), u2f(p1)), kMagic), kMagicNeg);
+  // bo - u go with two roundings as in the reference: packed product, scalar subtractions (a packed add fed by a
+  // packed mul gets contracted into one FFMA2 by ptxas, explicit .rn or not)
+  const float2 ug = fmul2(make_float2(row.u, row.u), g2);
+  const float2 b = make_float2(fsub(bo[0], ug.x), fsub(bo[1], ug.y));
+  const float2 Bq = fadd2(ffma2(b, make_float2(u2f(p0), u2f(p1)), kMagic), kMagicNeg);
   ok = ok & (ex0 - 0x33800000u < 0x10000000u) & (ex1 - 0x33800000u < 0x10000000u) &
        (fabsf(Bq.x) <= 2097152.0f) & (fabsf(Bq.y) <= 2097152.0f);
-  const float2 y = __ffma2_rn(sM, make_float2(xq[0], xq[1]), Bq);
-  const float2 c = __fadd2_rn(__ffma2_rn(y, make_float2(u2f(0x7f000000u - p0), u2f(0x7f000000u - p1)), kMagic), kMagicNeg);
+  const float2 y = ffma2(sM, make_float2(xq[0], xq[1]), Bq);
+  const float2 c = fadd2(ffma2(y, make_float2(u2f(0x7f000000u - p0), u2f(0x7f000000u - p1)), kMagic), kMagicNeg);
   code[0] = c.x;
   code[1] = c.y;
 }
@@ -278,7 +280,7 @@ layernorm_int_pot_kernel(const int8_t* __restrict__ in, int64_t in_row_stride, i
             ln_codes[(int64_t)row * d + grp * 4 + j + 1] = (int)code[j + 1];
           }
           // code * 2^k is exact: one rounding, like mul then add
-          const float2 v2 = __ffma2_rn(make_float2(code[j], code[j + 1]), make_float2(pm[g][j], pm[g][j + 1]),
+          const float2 v2 = ffma2(make_float2(code[j], code[j + 1]), make_float2(pm[g][j], pm[g][j + 1]),
                                        make_float2(p.post_zp, p.post_zp));
           v[j] = v2.x;
           v[j + 1] = v2.y;
