@@ -201,9 +201,15 @@ __device__ __forceinline__ void epilogue16(const uint32_t (&acc)[16], const floa
     float y4[4], r4[4];
     constexpr bool kGeluPot = (FLAGS & EPI_GELU) && (FLAGS & EPI_OUT_POT);
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      y4[e] = ffma((float)(int)acc[j4 + e], a4[e], b4[e]);   // kFold: already on the output grid
-      if ((FLAGS & EPI_GELU) && !kGeluPot) y4[e] = gelu_erf(y4[e]);
+    for (int e = 0; e < 4; e += 2) {   // acc * scale + bias, two columns per fma.rn.f32x2 (kFold: already on the output grid)
+      const float2 yy = ffma2(make_float2((float)(int)acc[j4 + e], (float)(int)acc[j4 + e + 1]),
+                              make_float2(a4[e], a4[e + 1]), make_float2(b4[e], b4[e + 1]));
+      y4[e] = yy.x;
+      y4[e + 1] = yy.y;
+    }
+    if ((FLAGS & EPI_GELU) && !kGeluPot) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) y4[e] = gelu_erf(y4[e]);
     }
     if (kGeluPot) {
       bool ok = true;
