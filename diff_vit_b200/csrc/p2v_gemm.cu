@@ -126,28 +126,39 @@ __device__ __forceinline__ float clamp_code(float r) { return fminf(fmaxf(r, -12
 // is accepted only if it lies further than 1.5e-6 |0.5 y rso| from a rounding boundary - more than the difference
 // to the reference expression gelu_erf(y) * rso (approximation error plus a few ulp of association) - so accepted
 // elements round to the same int8 code as the reference expression; the others (~2e-4) are redone with gelu_erf.
-// p2v_test_gelu_fast sweeps all 2^32 inputs on the device and counts accepted elements whose codes differ: zero.
+// p2v_test_gelu_fast sweeps all 2^32 inputs on the device (as the pairs the epilogue forms) and counts accepted
+// elements whose codes differ: zero.
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-__device__ __forceinline__ float gelu_code_fast(float y, float half_rso, bool& ok) {
-  const float x = fmul(y, 0.70710678118654752440f);
-  const float t = fminf(fabsf(x), 4.0f);
-  float q = 1.0022142669185996e-4f;
-  q = ffma(q, t, -4.6157639008015394e-4f);
-  q = ffma(q, t, -2.3022270761430264e-3f);
-  q = ffma(q, t, 2.9452499002218246e-2f);
-  q = ffma(q, t, -1.4896366000175476e-1f);
-  q = ffma(q, t, -9.183286428451538e-1f);
-  q = ffma(q, t, -1.6279137134552002f);
-  const float erfv = copysignf(fsub(1.0f, ex2_approx(fmul(t, q))), x);
-  const float hr = fmul(y, half_rso);
-  const float tq = ffma(hr, erfv, hr);
-  const float rr = fsub(fadd(tq, 12582912.0f), 12582912.0f);          // RNE(tq) for |tq| < 2^22 (beyond: saturates anyway)
-  ok = ok & (fabsf(fabsf(fsub(tq, rr)) - 0.5f) >= fmul(fabsf(hr), 1.5e-6f));   // no short circuit: branch-free
-  return tq;
+// two adjacent outputs: the operations whose operands are registers anyway go through the packed instructions, the
+// polynomial keeps the scalar immediate-operand FFMA form
+__device__ __forceinline__ void gelu_code_fast2(const float (&y)[2], const float (&half_rso)[2], bool& ok, float (&tq)[2]) {
+  const float2 y2 = make_float2(y[0], y[1]);
+  const float2 x2 = fmul2(y2, make_float2(0.70710678118654752440f, 0.70710678118654752440f));
+  float e[2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const float xi = i == 0 ? x2.x : x2.y;
+    const float t = fminf(fabsf(xi), 4.0f);
+    float q = 1.0022142669185996e-4f;
+    q = ffma(q, t, -4.6157639008015394e-4f);
+    q = ffma(q, t, -2.3022270761430264e-3f);
+    q = ffma(q, t, 2.9452499002218246e-2f);
+    q = ffma(q, t, -1.4896366000175476e-1f);
+    q = ffma(q, t, -9.183286428451538e-1f);
+    q = ffma(q, t, -1.6279137134552002f);
+    e[i] = copysignf(fsub(1.0f, ex2_approx(fmul(t, q))), xi);
+  }
+  const float2 hr = fmul2(y2, make_float2(half_rso[0], half_rso[1]));
+  const float2 t2 = ffma2(hr, make_float2(e[0], e[1]), hr);
+  const float2 rr = fadd2(fadd2(t2, make_float2(12582912.0f, 12582912.0f)), make_float2(-12582912.0f, -12582912.0f));
+  const float2 df = ffma2(rr, make_float2(-1.0f, -1.0f), t2);   // tq - RNE(tq), exact
+  ok = ok & (fabsf(fabsf(df.x) - 0.5f) >= fmul(fabsf(hr.x), 1.5e-6f)) & (fabsf(fabsf(df.y) - 0.5f) >= fmul(fabsf(hr.y), 1.5e-6f));
+  tq[0] = t2.x;
+  tq[1] = t2.y;
 }
 
 // Epilogue of 16 consecutive columns of one output row (one thread).  ch: this accumulator stage's
@@ -214,7 +225,13 @@ __device__ __forceinline__ void epilogue16(const uint32_t (&acc)[16], const floa
     if (kGeluPot) {
       bool ok = true;
 #pragma unroll
-      for (int e = 0; e < 4; ++e) r4[e] = gelu_code_fast(y4[e], rso[e], ok);   // rso[] holds rso / 2 here
+      for (int e = 0; e < 4; e += 2) {   // rso[] holds rso / 2 here
+        const float yy[2] = {y4[e], y4[e + 1]}, hh[2] = {rso[e], rso[e + 1]};
+        float tt[2];
+        gelu_code_fast2(yy, hh, ok, tt);
+        r4[e] = tt[0];
+        r4[e + 1] = tt[1];
+      }
       if (!ok) {
 #pragma unroll
         for (int e = 0; e < 4; ++e) r4[e] = fmul(gelu_erf(y4[e]), fmul(rso[e], 2.0f));
@@ -765,18 +782,24 @@ gemm_i8_bs_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 __global__ void gelu_fast_sweep_kernel(float rso, unsigned long long* __restrict__ counts) {
   unsigned long long bad = 0, rejected = 0, total = 0;
   const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
-  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < (1ull << 32); i += stride) {
-    const float y = __uint_as_float((uint32_t)i);
-    if (!isfinite(y)) continue;
-    bool ok = true;
-    const float tq = gelu_code_fast(y, 0.5f * rso, ok);
-    const float ref = fmul(gelu_erf(y), rso);
-    const int cf = max(-128, min(127, __float2int_rn(fminf(fmaxf(tq, -1e6f), 1e6f))));
-    const int cr = max(-128, min(127, __float2int_rn(fminf(fmaxf(ref, -1e6f), 1e6f))));
-    if (ok && cf != cr) ++bad;
-    if (fabsf(y) < 8.f) {
-      ++total;
-      if (!ok) ++rejected;
+  // the epilogue evaluates pairs (gelu_code_fast2): sweep consecutive bit patterns two at a time
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < (1ull << 31); i += stride) {
+    const float yy[2] = {__uint_as_float((uint32_t)(2 * i)), __uint_as_float((uint32_t)(2 * i + 1))};
+    const float hh[2] = {0.5f * rso, 0.5f * rso};
+    bool ok = true;   // shared by the pair, as in the epilogue: a rejected partner sends both to the reference path
+    float tq[2];
+    gelu_code_fast2(yy, hh, ok, tq);
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      if (!isfinite(yy[k])) continue;
+      const float ref = fmul(gelu_erf(yy[k]), rso);
+      const int cf = max(-128, min(127, __float2int_rn(fminf(fmaxf(tq[k], -1e6f), 1e6f))));
+      const int cr = max(-128, min(127, __float2int_rn(fminf(fmaxf(ref, -1e6f), 1e6f))));
+      if (ok && cf != cr) ++bad;
+      if (fabsf(yy[k]) < 8.f) {
+        ++total;
+        if (!ok) ++rejected;
+      }
     }
   }
   atomicAdd(&counts[0], bad);
