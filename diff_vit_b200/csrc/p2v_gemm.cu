@@ -326,7 +326,7 @@ __device__ __forceinline__ void load_channels(float (*ch)[CW], const p2v_epilogu
         A = fmul(A, RSO);
         B = fmul(B, RSO);
       }
-      if ((FLAGS & EPI_GELU) && (FLAGS & EPI_OUT_POT)) RSO = fmul(RSO, 0.5f);   // gelu_code_fast takes rso / 2 (exact)
+      if ((FLAGS & EPI_GELU) && (FLAGS & EPI_OUT_POT)) RSO = fmul(RSO, 0.5f);   // gelu_code_fast2 takes rso / 2 (exact)
       if (FLAGS & EPI_RESIDUAL) {
         SR = e.res_scale[col];
         SO2 = e.out2_scale[col];
@@ -776,7 +776,7 @@ gemm_i8_bs_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   if (warp == 2) tmem_dealloc<512>(tmem_base);
 }
 
-// ---- exhaustive check of gelu_code_fast (test hook) ---------------------------------------------------------------
+// ---- exhaustive check of gelu_code_fast2 (test hook) ---------------------------------------------------------------
 // All 2^32 fp32 bit patterns: counts[0] = accepted elements whose int8 code differs from the reference expression,
 // counts[1] = rejected (guard) among |y| < 8, counts[2] = finite inputs with |y| < 8.
 __global__ void gelu_fast_sweep_kernel(float rso, unsigned long long* __restrict__ counts) {
