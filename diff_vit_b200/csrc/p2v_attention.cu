@@ -115,13 +115,20 @@ __device__ __forceinline__ bool code_guarded(uint32_t bits) {
 __device__ __forceinline__ int prob16x4(uint32_t w, uint32_t revR, float fsum, uint32_t (&v)[4], uint32_t (&bits)[4]) {
   static_assert(kCodeGuard == 64, "the mask below encodes a 64-ulp guard");
   int worst = 0x7fffffff;
+  const float2 fs2 = make_float2(fsum, fsum), sixth2 = make_float2(0.16666667f, 0.16666667f);
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const uint32_t byte = __byte_perm(w, 0, 0x4440 + i);
-    bits[i] = __float_as_uint(__fmaf_rn(fsum, lds_f32(revR + (byte << 2)), 0.16666667f));
-    worst = min(worst, (int)((bits[i] - 0x3f7fffc0u) & 0x807fff80u));
-    // 1 << (15 - k), k = E - 125: shift counts >= 32 (k >= 16, or the wrapped negative) give 0
-    asm("shl.b32 %0, %1, %2;" : "=r"(v[i]) : "r"(1u), "r"(140u - (bits[i] >> 23)));
+  for (int i = 0; i < 4; i += 2) {
+    const float r0 = lds_f32(revR + (__byte_perm(w, 0, 0x4440 + i) << 2));
+    const float r1 = lds_f32(revR + (__byte_perm(w, 0, 0x4441 + i) << 2));
+    const float2 u = ffma2(fs2, make_float2(r0, r1), sixth2);   // two keys per fma.rn.f32x2
+    bits[i] = __float_as_uint(u.x);
+    bits[i + 1] = __float_as_uint(u.y);
+#pragma unroll
+    for (int k = i; k < i + 2; ++k) {
+      worst = min(worst, (int)((bits[k] - 0x3f7fffc0u) & 0x807fff80u));
+      // 1 << (15 - k), k = E - 125: shift counts >= 32 (k >= 16, or the wrapped negative) give 0
+      asm("shl.b32 %0, %1, %2;" : "=r"(v[k]) : "r"(1u), "r"(140u - (bits[k] >> 23)));
+    }
   }
   return worst;
 }
@@ -283,6 +290,7 @@ attention_int_kernel(const int8_t* __restrict__ qkv, int8_t* __restrict__ out, i
     // taken out again inside the fma's addend, which stays exactly representable.  No int -> float converts.
     // The row maximum is taken on the fp32 values (the conversion is monotone) and converted once.
     float fmaxA = -INFINITY, fmaxB = -INFINITY;
+    const float2 mul2 = make_float2(p.score_mul, p.score_mul), zq2 = make_float2(zq, zq);
     auto score_tile = [&](int j, float (&f)[4]) {
       const uint4 kf = *reinterpret_cast<const uint4*>(sm.Ks + (j * 8 + g) * kKStride + t * 16);
       int c[4];
@@ -292,8 +300,10 @@ attention_int_kernel(const int8_t* __restrict__ qkv, int8_t* __restrict__ out, i
         const int2 zk = *reinterpret_cast<const int2*>(&sm.zks[j * 8 + t * 2]);
         c[0] -= rcA + zk.x; c[1] -= rcA + zk.y; c[2] -= rcB + zk.x; c[3] -= rcB + zk.y;
       }
-#pragma unroll
-      for (int e = 0; e < 4; ++e) f[e] = __fmaf_rn(kPot ? __int_as_float(c[e]) : (float)c[e], p.score_mul, zq);
+      // two scores per fma.rn.f32x2 (rows A and B of the tile each hold an adjacent pair)
+      const float2 fa = ffma2(make_float2(kPot ? __int_as_float(c[0]) : (float)c[0], kPot ? __int_as_float(c[1]) : (float)c[1]), mul2, zq2);
+      const float2 fb = ffma2(make_float2(kPot ? __int_as_float(c[2]) : (float)c[2], kPot ? __int_as_float(c[3]) : (float)c[3]), mul2, zq2);
+      f[0] = fa.x; f[1] = fa.y; f[2] = fb.x; f[3] = fb.y;
     };
 #pragma unroll 1
     for (int s = 0; s < full_steps; ++s) {
