@@ -573,6 +573,8 @@ extern "C" int p2v_attention_int(const int8_t* qkv, int8_t* out, int b, int n, i
                                  void* stream) {
   P2V_REQUIRE(qkv && out && p && p->exp_lut, "p2v_attention_int: null pointer");
   P2V_REQUIRE(b > 0 && heads > 0 && n > 0, "p2v_attention_int: bad shape b=%d n=%d heads=%d", b, n, heads);
+  P2V_REQUIRE((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
+              "p2v_attention_int: qkv and out must be 16-byte aligned");
   P2V_REQUIRE(n <= kMaxKeys, "p2v_attention_int: n=%d tokens exceeds the %d-key tile of this kernel", n, kMaxKeys);
   P2V_REQUIRE((p->dump_scores == nullptr) == (p->dump_softmax == nullptr),
               "p2v_attention_int: dump_scores and dump_softmax must be given together");
