@@ -43,7 +43,7 @@ struct GemmSmem {
   alignas(1024) uint8_t a[kStages][kTileBytes];
   alignas(1024) uint8_t b[kStages][kTileBytes];
   alignas(16) float chan[CH_FIELDS][kChanCols];   // whole n when n <= kChanCols, else two 128-column slots
-  alignas(16) uint8_t stage[4][32 * 144];
+  alignas(16) uint8_t stage[4][2][32 * 144];   // per TMEM lane quarter, double-buffered (see epilogue_block)
   alignas(8) uint64_t full[kStages];
   uint64_t empty[kStages];
   uint64_t acc_full[kAccStages];
@@ -396,7 +396,8 @@ __device__ __forceinline__ void epilogue_block(const uint32_t (&v0)[16], const u
       *reinterpret_cast<uint4*>(g.out + (int64_t)(row0 + rr) * g.ld_out + col0 + ck * 16) =
           *reinterpret_cast<const uint4*>(stage + rr * kStagePitch + ck * 16);
   }
-  quarter_barrier(quarter);   // the tile is free for the next block
+  // no second barrier: the next block of this quarter writes the OTHER tile, and a warp reaches the barrier of that
+  // block only after it has finished reading this one, so the tile is free again when its turn comes (block + 2)
 }
 
 // Coalesced staging needs 16-byte aligned rows and whole 16-column chunks.  It pays off for the light
@@ -532,6 +533,7 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
     }
     uint32_t acc = 0, acc_phase = 0;
+    uint32_t stage_turn = 0;   // which of the quarter's two staging tiles the next block uses
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m0 = (tile / tiles_n) * kBlockM, n0 = (tile % tiles_n) * kBlockN;
       int cbase = n0;   // column of this tile's constants inside s.chan
@@ -579,7 +581,8 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         __syncwarp();
         if (lane == 0) mbar_arrive(&s.acc_empty[acc]);
         epilogue_block<FLAGS, kChanCols>(v0, v1, s.chan, cbase, g, m0 + quarter * 32, n0, quarter, cgroup, lane,
-                                         s.stage[quarter], staged);
+                                         s.stage[quarter][stage_turn & 1], staged);
+        ++stage_turn;
       }
       if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
     }
@@ -598,7 +601,7 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 // M128 x N256 x K32 MMA chain into a 256-column accumulator, and two accumulators ping-pong so the 16
 // epilogue warps drain one while the tensor pipe fills the other.  Per-channel constants are staged once.
 constexpr int kBsMaxKb = 3;        // k <= 384
-constexpr int kBsStagesA = 6;
+constexpr int kBsStagesA = 5;   // A ring (the double-buffered epilogue staging tiles took the sixth stage's shared memory)
 constexpr int kBsSlabCols = 256;
 constexpr int kBsMaxSlabs = 16;
 
@@ -615,7 +618,7 @@ struct BsSmem {
   alignas(1024) uint8_t b[kBsMaxKb][2][kTileBytes];   // [k-block][128-column half] = rows of the slab
   alignas(1024) uint8_t a[kBsStagesA][kTileBytes];
   alignas(16) float chan[CH_FIELDS][kBsSlabCols];
-  alignas(16) uint8_t stage[4][32 * 144];
+  alignas(16) uint8_t stage[4][2][32 * 144];   // per TMEM lane quarter, double-buffered (see epilogue_block)
   alignas(8) uint64_t full[kBsStagesA];
   uint64_t empty[kBsStagesA];
   uint64_t b_full;
@@ -715,6 +718,7 @@ gemm_i8_bs_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       load_channels<FLAGS, kBsSlabCols>(s.chan, g.epi, n0, g.n, (int)threadIdx.x - 128);
       asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
       uint32_t it = 0;
+      uint32_t stage_turn = 0;   // which of the quarter's two staging tiles the next block uses
       const bool staged = can_stage<FLAGS>(g);
       constexpr bool kHeavy = (FLAGS & (EPI_GELU | EPI_RESIDUAL)) != 0;
       for (int tile = local; tile < tiles_m; tile += cnt, ++it) {
@@ -765,7 +769,8 @@ gemm_i8_bs_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
               if (lane == 0) mbar_arrive(&s.acc_empty[p]);
             }
             epilogue_block<FLAGS, kBsSlabCols>(v0, v1, s.chan, h * kBlockN, g, row0, n0 + h * kBlockN, quarter, cgroup,
-                                               lane, s.stage[quarter], staged);
+                                               lane, s.stage[quarter][stage_turn & 1], staged);
+            ++stage_turn;
           }
         }
       }
