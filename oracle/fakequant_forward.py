@@ -23,6 +23,43 @@ import torch.nn.functional as F
 
 _W_RANGE = {4: (-8, 7), 8: (-128, 127)}
 
+# Accumulation mode of every contraction and row reduction (F.linear, F.conv2d, q @ k^T, attn @ v, the LayerNorm
+# row sums, the softmax row sum).  'fp32' is the reference as it runs (ATen's fp32 kernels, summation order of the
+# host BLAS).  'fp64' evaluates the SAME fp32 operands with fp64 products and sums and rounds the result to fp32
+# once: the reference's expression without the accumulation noise of one particular BLAS.  On power-of-two grids
+# both modes give identical codes (the sums are exact either way); with float scales (percentile / omse / ema) the
+# fp32 sums are inexact, and the 'fp64' mode is what an exact-accumulation integer implementation can be held to
+# (tests/test_gpu_model.py config 3 measures oracle-fp32 vs oracle-fp64 next to kernel vs oracle-fp64).
+_ACCUM = 'fp32'
+
+
+def _wide():
+    return _ACCUM == 'fp64'
+
+
+def _linear(x, w, b):
+    if _wide():
+        return (x.double() @ w.double().t()).float() + b
+    return F.linear(x, w, b)
+
+
+def _conv2d(x, w, b, stride):
+    if _wide():
+        return F.conv2d(x.double(), w.double(), None, stride=stride).float() + b.reshape(1, -1, 1, 1)
+    return F.conv2d(x, w, b, stride=stride)
+
+
+def _matmul(a, b):
+    if _wide():
+        return (a.double() @ b.double()).float()
+    return a @ b
+
+
+def _rowsum(x):
+    if _wide():
+        return x.double().sum(dim=-1).float()
+    return x.sum(dim=-1)
+
 
 def _bshape(x, weight_kind=None):
     """Broadcast shape of a per-channel scale (reference: models/ptq/quantizer/base.py:14-33)."""
@@ -77,9 +114,9 @@ def int_layernorm(x, in_scale, out_scale, gamma, beta):
     in_scale1 = in_scale.min()
     in_scale_mask = (in_scale / in_scale1).round()
     x_q = x_q * in_scale_mask
-    mean_x_q = x_q.mean(dim=-1) * in_scale1
+    mean_x_q = (_rowsum(x_q) / channel_nums if _wide() else x_q.mean(dim=-1)) * in_scale1
     std_x_q = (in_scale1 / channel_nums) * torch.sqrt(
-        channel_nums * (x_q ** 2).sum(dim=-1) - x_q.sum(dim=-1) ** 2)
+        channel_nums * _rowsum(x_q ** 2) - _rowsum(x_q) ** 2)
     A = (in_scale1 / std_x_q).unsqueeze(-1) * gamma.reshape(1, 1, -1) / out_scale
     A_sign = A.sign()
     # dyadic approximation A ~ M / 2^N (get_MN, layers.py:234-238)
@@ -113,7 +150,7 @@ def log_int_softmax(x, scale, bits):
     z = r * z
     z = z + c_int
     exp_int = torch.clamp(torch.floor(z * 2 ** (n - q)), min=0)
-    exp_int_sum = exp_int.sum(dim=-1, keepdim=True)
+    exp_int_sum = _rowsum(exp_int).unsqueeze(-1)
     softmax_out = torch.round(exp_int_sum / exp_int)
     big = softmax_out.log2().floor()
     extra = (softmax_out - 2 ** big) >= 2 ** (big - 1)
@@ -138,18 +175,18 @@ def _attention(state, i, x, bits_qkv, bits_proj, trace):
     cs = state['cs'][pre]
     x = _qact(state, pre + '.qact0', x / cs.reshape(1, 1, -1), trace)
     w = _qweight(state, pre + '.qkv', P[pre + '.qkv.weight'] * cs.reshape(1, -1), bits_qkv, 'linear')
-    x = F.linear(x, w, P[pre + '.qkv.bias'])
+    x = _linear(x, w, P[pre + '.qkv.bias'])
     x = _qact(state, pre + '.qact1', x, trace)
     qkv = x.reshape(B, N, 3, H, C // H).permute(2, 0, 3, 1, 4)
     q, k, v = qkv[0], qkv[1], qkv[2]
-    attn = (q @ k.transpose(-2, -1)) * arch['attn_scale']
+    attn = _matmul(q, k.transpose(-2, -1)) * arch['attn_scale']
     attn = _qact(state, pre + '.qact_attn1', attn, trace)
     codes, attn = log_int_softmax(attn, state['act'][pre + '.qact_attn1'][0], arch['softmax_bits'])
     trace.put('softmax/' + pre + '.log_int_softmax', codes)
-    x = (attn @ v).transpose(1, 2).reshape(B, N, C)
+    x = _matmul(attn, v).transpose(1, 2).reshape(B, N, C)
     x = _qact(state, pre + '.qact2', x, trace)
     w = _qweight(state, pre + '.proj', P[pre + '.proj.weight'], bits_proj, 'linear')
-    x = F.linear(x, w, P[pre + '.proj.bias'])
+    x = _linear(x, w, P[pre + '.proj.bias'])
     return _qact(state, pre + '.qact3', x, trace)
 
 
@@ -160,26 +197,38 @@ def _mlp(state, i, x, bits_fc1, bits_fc2, trace):
     cs = state['cs'][pre]
     x = _qact(state, pre + '.qact0', x / cs.reshape(1, 1, -1), trace)
     w = _qweight(state, pre + '.fc1', P[pre + '.fc1.weight'] * cs.reshape(1, -1), bits_fc1, 'linear')
-    x = F.linear(x, w, P[pre + '.fc1.bias'])
+    x = _linear(x, w, P[pre + '.fc1.bias'])
     x = F.gelu(x)
     x = _qact(state, pre + '.qact1', x, trace)
     w = _qweight(state, pre + '.fc2', P[pre + '.fc2.weight'], bits_fc2, 'linear')
-    x = F.linear(x, w, P[pre + '.fc2.bias'])
+    x = _linear(x, w, P[pre + '.fc2.bias'])
     return _qact(state, pre + '.qact2', x, trace)
 
 
-def forward(state, x, bit_config, capture=False):
+def forward(state, x, bit_config, capture=False, accum='fp32'):
     """Quantized forward.  Returns (logits fp32 [B, classes], {key: int32 codes}).
+
+    accum: 'fp32' (the reference as it runs) or 'fp64' (same operands, exact-to-fp64 sums; see _ACCUM).
 
     bit_config index map: 0 = patch-embed conv, 1+4i..4+4i = block i qkv/proj/fc1/fc2,
     -1 = head."""
+    global _ACCUM
+    assert accum in ('fp32', 'fp64')
+    prev, _ACCUM = _ACCUM, accum
+    try:
+        return _forward(state, x, bit_config, capture)
+    finally:
+        _ACCUM = prev
+
+
+def _forward(state, x, bit_config, capture):
     arch, P = state['arch'], state['params']
     trace = Trace(capture)
     with torch.no_grad():
         B = x.shape[0]
         x = _qact(state, 'qact_input', x, trace)
         w = _qweight(state, 'patch_embed.proj', P['patch_embed.proj.weight'], bit_config[0], 'conv')
-        x = F.conv2d(x, w, P['patch_embed.proj.bias'], stride=arch['patch_size'])
+        x = _conv2d(x, w, P['patch_embed.proj.bias'], arch['patch_size'])
         x = x.flatten(2).transpose(1, 2)
         x = _qact(state, 'patch_embed.qact', x, trace)
         x = torch.cat((P['cls_token'].expand(B, -1, -1), x), dim=1)
@@ -210,6 +259,6 @@ def forward(state, x, bit_config, capture=False):
         trace.put('ln/norm', codes)
         x = _qact(state, 'qact2', x[:, 0], trace)
         w = _qweight(state, 'head', P['head.weight'], bit_config[-1], 'linear')
-        x = F.linear(x, w, P['head.bias'])
+        x = _linear(x, w, P['head.bias'])
         x = _qact(state, 'act_out', x, trace)
     return x, trace.codes

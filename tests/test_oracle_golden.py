@@ -47,3 +47,15 @@ def test_softmax_extreme_rows():
     assert codes[0, 0, 2].unique().tolist() == [6]          # 1/64 -> 2^-6
     assert len(set(codes[0, 0, 1].tolist())) >= 8   # the ramp spans many codes
     assert codes.max() == 16 and codes.min() == 0
+
+
+def test_fp64_accumulation_mode_equals_reference_on_power_of_two_grids(micro_state, micro_golden):
+    """The oracle's 'fp64' accumulation mode (what the exact-accumulation kernels are held to when scales are
+    floats, BASELINE config 3) changes nothing where the reference's fp32 sums are exact: on the power-of-two
+    grids of the minmax observer it reproduces the reference's golden codes bit for bit."""
+    z = micro_golden
+    logits, codes = orc.forward(micro_state, torch.from_numpy(z['x_eval']), [8] * 10, capture=True, accum='fp64')
+    for k, v in codes.items():
+        g = z['w8/' + k]
+        np.testing.assert_array_equal(g.astype(np.int64), v.numpy().astype(np.int64).reshape(g.shape), err_msg=k)
+    np.testing.assert_array_equal(z['w8/logits'], logits.numpy())
