@@ -149,11 +149,33 @@ def small_c2():
     return model, extract_state(model), x
 
 
+def _teacher_forced(state, x_cpu, bits, dump, accum='fp32'):
+    """Oracle run in which every layer continues with the ENGINE's codes (oracle `override`), so that each oracle layer
+    is evaluated on exactly the inputs the engine's layer saw.  Returns the per-layer report rows."""
+    want, ref = orc.forward(state, x_cpu, bits, capture=True, accum=accum, override=dump)
+    return want, _layer_report(dump, {k: v.numpy() for k, v in ref.items()})
+
+
+def _assert_forced(rep, gelu_only_inexact=True):
+    """north_star per layer on identical inputs: bit-exact where the arithmetic is bit-defined (everything except the
+    erf-GELU re-quantisation), <= 1 LSB on <= 0.1 % of the elements for the GELU layers."""
+    for k, mx, frac, _, _ in rep:
+        if k.endswith('.mlp.qact1') or not gelu_only_inexact:
+            assert mx <= 1 and frac <= 1e-3, '%s: max %d, %.2e differ' % (k, mx, frac)
+        else:
+            assert mx == 0, '%s is bit-defined on identical inputs: max %d, %.2e differ' % (k, mx, frac)
+
+
 def test_deit_small_c2_headline_batch256_vs_oracle(small_c2):
     """The headline configuration (deit_small W8A8 PoT minmax, batch 256, the very model / batch bench.py times):
     the 256-image forward's logits, and EVERY quantizer's integer codes of 32 of those images, against the CPU
-    oracle on the same calibrated state.  Tolerance = north_star: <= 1 LSB on <= 0.1 % per layer (GELU ties:
-    device erf vs ATen CPU erf); everything that is bit-defined (all layers up to the first GELU) must be equal."""
+    oracle on the same calibrated state.
+
+    (1) layer by layer on identical inputs (oracle teacher-forced with the engine's codes): every layer of every
+        block bit-exact, except the twelve GELU re-quantisations, which are held to north_star (<= 1 LSB on <= 0.1 %:
+        device erf vs ATen CPU erf at rounding ties);
+    (2) free-running: identical until the first GELU tie flip; what a flip does afterwards is the random-init
+        network's own sensitivity (printed), not the kernels'."""
     model, state, x = small_c2
     bits = [8] * 50
     eng = model.integer_engine()
@@ -162,20 +184,21 @@ def test_deit_small_c2_headline_batch256_vs_oracle(small_c2):
     rows = torch.cat([full[:24], full[250:256], full[128:130]])
     logits, dump = eng.forward_dump(sub, bits)
     assert torch.equal(logits, rows), 'batch-256 graph replay and the 32-image dump run disagree'
-    want, ref = orc.forward(state, sub.cpu(), bits, capture=True)
-    rep = _layer_report(dump, {k: v.numpy() for k, v in ref.items()})
+    want, rep = _teacher_forced(state, sub.cpu(), bits, dump)
     assert len(rep) >= 2 + 13 * 12 + 3 and sum(r[4] for r in rep) > 6e8
-    worst = max(rep, key=lambda r: r[2])
-    print('deit_small C2: %d layers, %d codes compared, %d differ; worst layer %s: %.2e differing'
-          % (len(rep), sum(r[4] for r in rep), sum(round(r[2] * r[4]) for r in rep), worst[0], worst[2]))
-    for k, mx, frac, frac2, _ in rep:
-        assert mx <= 1 and frac <= 1e-3, '%s: max %d, %.2e differ' % (k, mx, frac)
-    first_gelu = [r[0] for r in rep].index('act/blocks.0.mlp.qact1')
-    for k, mx, frac, _, _ in rep[:first_gelu]:
-        assert mx == 0, k + ' is bit-defined and must be identical'
+    gelu = [r for r in rep if r[0].endswith('.mlp.qact1')]
+    print('deit_small C2, identical inputs per layer: %d layers, %d codes, %d differ (all in the %d GELU layers, worst %.2e)'
+          % (len(rep), sum(r[4] for r in rep), sum(round(r[2] * r[4]) for r in rep), len(gelu), max(r[2] for r in gelu)))
+    _assert_forced(rep)
     lsb = float(state['act']['act_out'][0])
-    assert (rows.cpu() - want).abs().max().item() <= lsb
-    assert ((rows.cpu() != want).float().mean().item()) <= 1e-2
+    assert (rows.cpu() - want).abs().max().item() <= lsb and (rows.cpu() != want).float().mean().item() <= 1e-3
+    # free-running oracle: exact up to the first GELU, north_star until the first flip has been amplified
+    want_free, ref = orc.forward(state, sub.cpu(), bits, capture=True)
+    free = _layer_report(dump, {k: v.numpy() for k, v in ref.items()})
+    first_gelu = [r[0] for r in free].index('act/blocks.0.mlp.qact1')
+    assert all(r[1] == 0 for r in free[:first_gelu])
+    assert free[first_gelu][1] <= 1 and free[first_gelu][2] <= 1e-3
+    print('free-running: ' + ', '.join('%s %.1e' % (r[0].replace('act/blocks.', 'b'), r[2]) for r in free if r[0].endswith('.qact4')))
 
 
 def test_deit_small_c4_int4_and_restore_set_vs_oracle(small_c2):
@@ -191,13 +214,9 @@ def test_deit_small_c4_int4_and_restore_set_vs_oracle(small_c2):
     eng = model.integer_engine()
     for bits in ([4] * 50, restore):
         logits, dump = eng.forward_dump(sub, bits)
-        want, ref = orc.forward(state, sub.cpu(), bits, capture=True)
-        rep = _layer_report(dump, {k: v.numpy() for k, v in ref.items()})
+        want, rep = _teacher_forced(state, sub.cpu(), bits, dump)
         assert len(rep) >= 2 + 13 * 12 + 3
-        for k, mx, frac, _, _ in rep:
-            assert mx <= 1 and frac <= 1e-3, '%s: max %d, %.2e differ' % (k, mx, frac)
-        first_gelu = [r[0] for r in rep].index('act/blocks.0.mlp.qact1')
-        assert all(r[1] == 0 for r in rep[:first_gelu])
+        _assert_forced(rep)
         assert (logits.cpu() - want).abs().max().item() <= lsb
         print('deit_small C4 %s: %d codes, %d differ' % ('restore' if 8 in bits else 'w4', sum(r[4] for r in rep),
                                                          sum(round(r[2] * r[4]) for r in rep)))
@@ -251,10 +270,10 @@ def test_gpu_calibration_kernels_reproduce_reference_scales(micro_golden, tiny_g
 def test_deit_base_and_mixed_precision_vs_oracle():
     """D = 768 / 12 heads (DeiT-B, ViT-B): K = 768 takes the operand-streaming GEMM and the generic LayerNorm
     path.  Calibrated on the GPU, compared with the CPU oracle on the same state for W8 and the published
-    4->8 layer-restore configuration (BASELINE config 4 index set).  Everything up to the first GELU is
-    bit-defined and must be identical; GELU outputs may differ by 1 LSB at rounding ties (device erff vs ATen's
-    CPU erf: the reference itself differs between CPU and GPU there), and such a flip then propagates through the
-    remaining blocks, so later layers and the logits are held to the allowance, not to equality."""
+    4->8 layer-restore configuration (BASELINE config 4 index set), every layer of all 12 blocks on identical
+    inputs (oracle teacher-forced with the engine's codes): bit-exact everywhere except the GELU re-quantisations,
+    which may differ by 1 LSB at rounding ties (device erf vs ATen's CPU erf: the reference itself differs between
+    CPU and GPU there) on <= 0.1 % of the elements."""
     import diff_vit_b200 as dv
     from diff_vit_b200.plan import extract_state
     torch.manual_seed(0)
@@ -270,20 +289,10 @@ def test_deit_base_and_mixed_precision_vs_oracle():
     eng = model.integer_engine()
     for bits in ([8] * 50, restore):
         got, dump = eng.forward_dump(x, bits)
-        want, ref = orc.forward(state, x.cpu(), bits, capture=True)
-        exact = ['act/patch_embed.qact', 'act/qact1', 'ln/blocks.0.norm1', 'act/blocks.0.attn.qact0',
-                 'act/blocks.0.attn.qact1', 'act/blocks.0.attn.qact_attn1', 'softmax/blocks.0.attn.log_int_softmax',
-                 'act/blocks.0.attn.qact2', 'act/blocks.0.attn.qact3', 'act/blocks.0.qact2', 'ln/blocks.0.norm2',
-                 'act/blocks.0.mlp.qact0']
-        for k in exact:
-            r = ref[k].numpy().astype(np.int64)
-            np.testing.assert_array_equal(dump[k].astype(np.int64).reshape(r.shape), r, err_msg=k)
-        r = ref['act/blocks.0.mlp.qact1'].numpy().astype(np.int64)
-        d = np.abs(dump['act/blocks.0.mlp.qact1'].astype(np.int64).reshape(r.shape) - r)
-        assert d.max() <= 1 and (d != 0).mean() <= 1e-3
-        # later layers: a single GELU flip is amplified ~5-10x per stage by the random-init network (the same
-        # happens between the reference's own CPU and GPU runs), so only sanity is checked from here on; the
-        # D = 768 kernels are held to bit-exactness with identical inputs in tests/test_gpu_kernels.py
+        want, rep = _teacher_forced(state, x.cpu(), bits, dump)
+        assert len(rep) >= 2 + 13 * 12 + 3
+        _assert_forced(rep)       # all 12 blocks: bit-exact on identical inputs, GELU layers within north_star
+        assert (got.cpu() - want).abs().max().item() <= lsb
         codes = got / lsb
         assert torch.equal(codes, codes.round()) and codes.abs().max() <= 128 and got.std() > 0
 
@@ -297,10 +306,12 @@ def test_vit_base_percentile_config3_vs_oracle():
 
     With float scales the reference's fp32 GEMM / row sums are no longer exact, so its codes depend on the summation
     order of the host BLAS.  The kernels accumulate exactly, and are therefore held to the oracle in its 'fp64'
-    accumulation mode (same fp32 operands, sums exact to fp64, one rounding): north_star tolerance, <= 1 LSB on
-    <= 0.1 % of every layer of the first block.  How far the reference's own fp32 accumulation sits from that exact
-    evaluation is measured beside it (oracle fp32 vs oracle fp64) and printed: it is the noise floor of this config,
-    and the kernels must be inside it."""
+    accumulation mode (same fp32 operands, sums exact to fp64, one rounding), every layer of all twelve blocks on
+    identical inputs (oracle teacher-forced with the engine's codes): north_star tolerance, <= 1 LSB on <= 0.1 % per
+    layer, and <= 0.01 % overall.  How far the reference's own fp32 accumulation sits from the same kernel codes is
+    measured beside it: it is the noise floor of this config, and it must be far above the kernels' distance to the
+    exact evaluation (round 1 had widened the gate to 15 % / 8 LSB because a free-running fp32 oracle and the kernels
+    are both one tie flip away from chaos in a random-init network)."""
     import diff_vit_b200 as dv
     from diff_vit_b200.plan import extract_state
     torch.manual_seed(0)
@@ -312,33 +323,30 @@ def test_vit_base_percentile_config3_vs_oracle():
     scales = [float(v[0].reshape(-1)[0]) for k, v in state['act'].items() if v[0].numel() == 1]
     assert any(abs(np.log2(s) - round(np.log2(s))) > 1e-3 for s in scales), 'expected float scales from percentile'
     got, dump = model.integer_engine().forward_dump(x, [8] * 50)
-    _, ref32 = orc.forward(state, x.cpu(), [8] * 50, capture=True)
-    _, ref64 = orc.forward(state, x.cpu(), [8] * 50, capture=True, accum='fp64')
-    keys = [k for k in ref64 if k in dump]          # every quantizer of all 12 blocks
-    assert len(keys) >= 2 + 13 * 12 + 3
-    k64 = {r[0]: r for r in _layer_report(dump, {k: ref64[k].numpy() for k in keys})}
-    k32 = {r[0]: r for r in _layer_report(dump, {k: ref32[k].numpy() for k in keys})}
-    o32 = {r[0]: r for r in _layer_report({k: ref32[k].numpy() for k in keys}, {k: ref64[k].numpy() for k in keys})}
-    print('%-42s | kernel vs oracle-fp64     | oracle-fp32 vs oracle-fp64 | kernel vs oracle-fp32' % 'layer')
-    for k in keys:
-        if k.startswith('act/blocks.') and not k.startswith('act/blocks.0.') and not k.endswith('.qact4'):
-            continue
-        print('%-42s | max %d  %.2e  >1 %.1e | max %d  %.2e  >1 %.1e | max %d  %.2e  >1 %.1e'
-              % ((k,) + k64[k][1:4] + o32[k][1:4] + k32[k][1:4]))
-    first_gelu = keys.index('act/blocks.0.mlp.qact1')
-    for i, k in enumerate(keys):
-        _, mx, frac, frac2, _ = k64[k]
-        if i < first_gelu:     # bit-defined: the exact-accumulation evaluation and the integer kernels must agree
-            assert mx == 0, '%s: max %d, %.2e differ from the exact-accumulation oracle' % (k, mx, frac)
-        elif k.startswith('ln/'):
+    # layer by layer on identical inputs (teacher forcing), against both accumulation modes of the oracle
+    want64, k64 = _teacher_forced(state, x.cpu(), [8] * 50, dump, accum='fp64')
+    _, k32 = _teacher_forced(state, x.cpu(), [8] * 50, dump, accum='fp32')
+    assert len(k64) >= 2 + 13 * 12 + 3
+    print('%-42s | kernel vs oracle-fp64       | kernel vs oracle-fp32 (identical inputs per layer)' % 'layer')
+    for r64, r32 in zip(k64, k32):
+        if r64[2] or r32[2]:
+            print('%-42s | max %d  %.2e  >1 %.1e | max %d  %.2e  >1 %.1e' % (r64[:4] + r32[1:4]))
+    for k, mx, frac, frac2, _ in k64:
+        if k.startswith('ln/'):
             # LayerNorm codes sit on the fine LN output grid before the QAct: one step of the 8-bit dyadic multiplier
             # M moves a code by |x_q| / 2^N, so the bound is on the fraction only
             assert frac <= 1e-3, '%s: %.2e of the LN codes differ from the exact-accumulation oracle' % (k, frac)
         else:
             assert mx <= 1 and frac <= 1e-3, '%s: max %d, %.2e differ from the exact-accumulation oracle' % (k, mx, frac)
-    # the reference's own fp32 accumulation is measurably further from the exact evaluation than the kernels are
-    assert sum(o32[k][2] * o32[k][4] for k in keys) > 10 * sum(k64[k][2] * k64[k][4] for k in keys)
-    want64, _ = orc.forward(state, x.cpu(), [8] * 50, accum='fp64')
+    d64 = sum(r[2] * r[4] for r in k64)
+    d32 = sum(r[2] * r[4] for r in k32)
+    total = sum(r[4] for r in k64)
+    print('config 3, %d codes: %d differ from the exact-accumulation oracle, %d from the fp32-accumulation oracle'
+          % (total, d64, d32))
+    # measured on B200 (round 2): 281 of 81 060 368 codes (3.5e-6, all 1 LSB) differ from the exact-accumulation
+    # oracle, 809 from the fp32-accumulation one: the kernels sit closer to the exact evaluation of the reference's
+    # expression than the reference's own fp32 run does
+    assert d64 <= 1e-4 * total and d32 >= d64
     lsb = float(state['act']['act_out'][0])
     codes = got / lsb
     assert torch.allclose(codes, codes.round(), atol=1e-3) and got.std() > 0
@@ -413,12 +421,7 @@ def test_omse_zero_points_through_the_engine(micro_golden):
         np.testing.assert_array_equal(dump[k].astype(np.int64).reshape(host[k].shape), host[k].astype(np.int64), err_msg=k)
     # against the oracle: exact-accumulation mode (float scales make the fp32 sums of the reference order-dependent,
     # see test_vit_base_percentile_config3_vs_oracle); north_star tolerance per layer, logits within 1 LSB
-    ref_logits, ref = orc.forward(state, x, [8] * 10, capture=True, accum='fp64')
-    ref32_logits, ref32 = orc.forward(state, x, [8] * 10, capture=True)
-    rep = _layer_report(dump, {k: v.numpy() for k, v in ref.items()})
-    rep32 = _layer_report({k: v.numpy() for k, v in ref32.items()}, {k: v.numpy() for k, v in ref.items()})
-    for (k, mx, frac, frac2, _), r32 in zip(rep, rep32):
-        print('%-42s kernel vs fp64: max %d %.2e | oracle fp32 vs fp64: max %d %.2e' % (k, mx, frac, r32[1], r32[2]))
+    ref_logits, rep = _teacher_forced(state, x, [8] * 10, dump, accum='fp64')
     for k, mx, frac, frac2, _ in rep:
         if not k.startswith('ln/'):
             assert mx <= 1, k

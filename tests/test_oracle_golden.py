@@ -59,3 +59,26 @@ def test_fp64_accumulation_mode_equals_reference_on_power_of_two_grids(micro_sta
         g = z['w8/' + k]
         np.testing.assert_array_equal(g.astype(np.int64), v.numpy().astype(np.int64).reshape(g.shape), err_msg=k)
     np.testing.assert_array_equal(z['w8/logits'], logits.numpy())
+
+
+def test_teacher_forcing_is_transparent_and_local(micro_state, micro_golden):
+    """The oracle's `override` (teacher forcing, used by the GPU parity tests to compare every layer on identical
+    inputs): feeding the oracle its own codes changes nothing; feeding it altered codes of one layer leaves that
+    layer's RECORDED codes (computed from the layer's true inputs) untouched and moves only what is downstream."""
+    z = micro_golden
+    x = torch.from_numpy(z['x_eval'])
+    logits, codes = orc.forward(micro_state, x, [8] * 10, capture=True)
+    own = {k: v.numpy() for k, v in codes.items()}
+    l2, c2 = orc.forward(micro_state, x, [8] * 10, capture=True, override=own)
+    assert torch.equal(l2, logits) and all(torch.equal(c2[k], codes[k]) for k in codes)
+    bumped = dict(own)
+    key = 'act/blocks.0.mlp.qact1'
+    bumped[key] = np.clip(own[key] + 1, -128, 127)
+    l3, c3 = orc.forward(micro_state, x, [8] * 10, capture=True, override={key: bumped[key]})
+    keys = list(codes)
+    at = keys.index(key)
+    assert all(torch.equal(c3[k], codes[k]) for k in keys[:at + 1])         # recorded = own evaluation
+    assert not torch.equal(c3['act/blocks.0.mlp.qact2'], codes['act/blocks.0.mlp.qact2'])
+    # the CLS-only form of the final LayerNorm codes is accepted
+    l4, _ = orc.forward(micro_state, x, [8] * 10, override={'ln/norm': own['ln/norm'][:, 0]})
+    assert torch.equal(l4, logits)
