@@ -31,7 +31,7 @@ class LayerNorm(C.Structure):
 class Attention(C.Structure):
     _fields_ = [('score_mul', C.c_float), ('score_zp', C.c_float), ('out_mul', C.c_double), ('out_zp', C.c_float),
                 ('softmax_levels', C.c_int), ('exp_lut', _vp), ('dump_scores', _vp), ('dump_softmax', _vp),
-                ('in_zp', C.c_float)]
+                ('in_zp', C.c_float), ('lut_sig_bits', C.c_int32), ('force_legacy', C.c_int32)]
 
 
 class LinearDesc(C.Structure):

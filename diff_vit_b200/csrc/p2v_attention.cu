@@ -543,6 +543,8 @@ attention_int_kernel(const int8_t* __restrict__ qkv, int8_t* __restrict__ out, i
   }
 }
 
+int attention_tc_configure();
+
 template <bool kDump, bool kPot, bool kZp>
 static int attention_configure_one() {
   P2V_CHECK_CUDA(cudaFuncSetAttribute(attention_int_kernel<kDump, kPot, kZp>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -552,17 +554,23 @@ static int attention_configure_one() {
   return P2V_OK;
 }
 static int attention_configure() {
-  static int state = 1;
-  if (state == 1) {
+  static unsigned long long done = 0;   // one bit per device
+  int dev = 0;
+  if (needs_configure(done, &dev)) {
     int rc;
     if ((rc = attention_configure_one<false, false, false>()) || (rc = attention_configure_one<false, true, false>()) ||
         (rc = attention_configure_one<true, false, false>()) || (rc = attention_configure_one<true, true, false>()) ||
         (rc = attention_configure_one<false, false, true>()) || (rc = attention_configure_one<true, false, true>()))
       return rc;
-    state = 0;
+    if ((rc = attention_tc_configure())) return rc;
+    mark_configured(done, dev);
   }
   return P2V_OK;
 }
+int attention_tc_configure();
+bool attention_tc_applicable(const int8_t* qkv, const int8_t* out, int b, int n, int heads, const p2v_attention* p);
+int attention_tc_launch(const int8_t* qkv, int8_t* out, int b, int n, int heads, const p2v_attention* p, cudaStream_t st);
+
 int attention_configure_once() { return attention_configure(); }
 
 }  // namespace p2v
@@ -578,6 +586,12 @@ extern "C" int p2v_attention_int(const int8_t* qkv, int8_t* out, int b, int n, i
   P2V_REQUIRE(n <= kMaxKeys, "p2v_attention_int: n=%d tokens exceeds the %d-key tile of this kernel", n, kMaxKeys);
   P2V_REQUIRE((p->dump_scores == nullptr) == (p->dump_softmax == nullptr),
               "p2v_attention_int: dump_scores and dump_softmax must be given together");
+  // power-of-two grids (every minmax-calibrated model): the tcgen05 / TMEM / TMA kernel of p2v_attention_tc.cu
+  if (!p->force_legacy && attention_tc_applicable(qkv, out, b, n, heads, p)) {
+    int rc0 = attention_configure_once();
+    if (rc0) return rc0;
+    return attention_tc_launch(qkv, out, b, n, heads, p, (cudaStream_t)stream);
+  }
   dim3 grid(b * heads);
   // power-of-two output multiplier 2^-sh (every minmax-calibrated model): integer RNE shift in the kernel
   int out_shift = 0, ex = 0;

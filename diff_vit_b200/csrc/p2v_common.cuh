@@ -30,6 +30,17 @@ void set_error(const char* fmt, ...);
 
 constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
 
+// cudaFuncSetAttribute (the > 48 KiB shared-memory opt-in) is per device: a process that drives several GPUs has to
+// repeat it on each.  Returns true the first time it is called with `done` on the CURRENT device; the caller then
+// configures and, on success, calls mark_configured.
+inline bool needs_configure(const unsigned long long& done, int* device) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+  *device = dev;
+  return ((done >> (dev & 63)) & 1ull) == 0ull;
+}
+inline void mark_configured(unsigned long long& done, int device) { done |= 1ull << (device & 63); }
+
 #if defined(__CUDACC__)
 // ---- small device helpers ------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {

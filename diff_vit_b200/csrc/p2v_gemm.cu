@@ -931,8 +931,9 @@ static bool make_bs_plan(int n, int k, int grid, BsPlan* plan) {
 // Opt every instantiation into > 48 KiB of dynamic shared memory.  Done once per process, outside any
 // stream capture.
 int gemm_configure() {
-  static int state = 1;  // 1 = not yet done
-  if (state == 1) {
+  static unsigned long long done = 0;   // one bit per device
+  int dev = 0;
+  if (needs_configure(done, &dev)) {
     int rc = configure_one<0>();
     if (!rc) rc = configure_one<1>();
     if (!rc) rc = configure_one<2>();
@@ -942,7 +943,7 @@ int gemm_configure() {
     if (!rc) rc = configure_one<6>();
     if (!rc) rc = configure_one<7>();
     if (rc) return rc;
-    state = 0;
+    mark_configured(done, dev);
   }
   return P2V_OK;
 }

@@ -97,6 +97,7 @@ class _BoundPlan:
         d.score_mul, d.score_zp, d.out_mul, d.out_zp = p.score_mul, p.score_zp, p.out_mul, p.out_zp
         d.softmax_levels = p.levels
         d.in_zp = getattr(p, 'in_zp', 0.0)
+        d.lut_sig_bits = p.lut_sig_bits
         d.exp_lut = self._p(p.exp_lut)
         return d
 

@@ -136,6 +136,16 @@ class AttentionPlan:
     exp_lut: torch.Tensor      # fp32 [256]
     in_zp: float = 0.0         # zero point of the q/k/v codes (asymmetric observers)
 
+    @property
+    def lut_sig_bits(self):
+        """Widest entry of exp_lut in significant bits (p2v_attention.lut_sig_bits: the kernel choice of the library)."""
+        widest = 0
+        for e in self.exp_lut.double().tolist():
+            v = int(e)
+            if v > 0:
+                widest = max(widest, v.bit_length() - ((v & -v).bit_length() - 1))
+        return widest
+
 
 @dataclass
 class BlockPlan:

@@ -135,6 +135,11 @@ typedef struct p2v_attention {
   float in_zp;        /* zero point of the q/k/v codes (qact1); non-zero only with asymmetric observers (omse):
                          S = sum (q - z)(k - z) and O = sum p (v - z) are formed from the raw int8 products plus row /
                          key sums, so the tensor-core operands stay int8 */
+  int32_t lut_sig_bits; /* widest entry of exp_lut in significant bits (highest minus lowest set bit + 1 of the
+                           integer); exp_lut is device memory, so the host-side kernel choice needs it from the caller.
+                           1..21 admits the tcgen05 / TMEM kernel (its fp64 row sums take the table words as the high
+                           halves of doubles); 0 = unknown: the mma.sync kernel is used */
+  int32_t force_legacy; /* test hook: non-zero pins the mma.sync kernel (cross-checks of the two kernels) */
 } p2v_attention;
 int p2v_attention_int(const int8_t* qkv, int8_t* out, int b, int n, int heads, const p2v_attention* p,
                       void* stream);

@@ -160,10 +160,15 @@ def test_layernorm_int_matches_host_arithmetic(cabi, rows, d, stride_rows, pot):
 @pytest.mark.parametrize('b,n,heads', [(2, 197, 3), (3, 10, 2), (1, 224, 1), (2, 33, 6), (1, 1, 1)])
 @pytest.mark.parametrize('spread', [1, 6])
 @pytest.mark.parametrize('in_zp', [0, 7, -11])
-def test_attention_int_matches_host_arithmetic(cabi, b, n, heads, spread, in_zp):
-    """in_zp != 0: asymmetric q/k/v codes (omse observer); the kernel completes the raw int8 products with row / key
+@pytest.mark.parametrize('kernel', ['tcgen05', 'mma.sync'])
+def test_attention_int_matches_host_arithmetic(cabi, b, n, heads, spread, in_zp, kernel):
+    """Both attention kernels against the host arithmetic, bit for bit: the tcgen05 / TMEM / TMA kernel
+    (p2v_attention_tc.cu: power-of-two grids, n <= 208) and the mma.sync kernel (p2v_attention.cu: everything else).
+    in_zp != 0: asymmetric q/k/v codes (omse observer); the kernel completes the raw int8 products with row / key
     sums and must equal the direct sum over (q - z)(k - z) and p (v - z) of the host arithmetic, with non-zero
     score and output zero points as well."""
+    if kernel == 'tcgen05' and (in_zp != 0 or n > 208):
+        pytest.skip('outside the tcgen05 kernel: the library routes this call to the mma.sync kernel')
     from diff_vit_b200.plan import AttentionPlan, softmax_exp_lut
     rng = np.random.default_rng(b * 100 + n + heads + spread)
     qkv = _rand_i8(rng, b * n, 3 * heads * 64, lo=max(-128, -20 * spread + in_zp), hi=min(127, 20 * spread + in_zp))
@@ -176,6 +181,9 @@ def test_attention_int_matches_host_arithmetic(cabi, b, n, heads, spread, in_zp)
     c.score_mul, c.score_zp, c.out_mul, c.out_zp, c.softmax_levels = p.score_mul, p.score_zp, p.out_mul, p.out_zp, 16
     c.in_zp = p.in_zp
     c.exp_lut = lut.data_ptr()
+    c.lut_sig_bits = p.lut_sig_bits
+    assert 0 < p.lut_sig_bits <= 21
+    c.force_legacy = int(kernel == 'mma.sync')
     sc = torch.zeros(b, heads, n, n, dtype=torch.int8, device='cuda')
     sm = torch.zeros(b, heads, n, n, dtype=torch.uint8, device='cuda')
     c.dump_scores, c.dump_softmax = sc.data_ptr(), sm.data_ptr()
@@ -194,6 +202,68 @@ def test_attention_int_matches_host_arithmetic(cabi, b, n, heads, spread, in_zp)
     cabi.check(cabi.lib().p2v_attention_int(qd.data_ptr(), out2.data_ptr(), b, n, heads, C.byref(c), _stream()))
     torch.cuda.synchronize()
     assert torch.equal(out, out2)
+
+
+def _run_attention(cabi, qkv, b, n, heads, p, legacy=False, dump=True):
+    lut = p.exp_lut.cuda()
+    c = cabi.Attention()
+    c.score_mul, c.score_zp, c.out_mul, c.out_zp, c.softmax_levels = p.score_mul, p.score_zp, p.out_mul, p.out_zp, 16
+    c.in_zp, c.exp_lut, c.lut_sig_bits, c.force_legacy = p.in_zp, lut.data_ptr(), p.lut_sig_bits, int(legacy)
+    sc = torch.zeros(b, heads, n, n, dtype=torch.int8, device='cuda')
+    sm = torch.zeros(b, heads, n, n, dtype=torch.uint8, device='cuda')
+    if dump:
+        c.dump_scores, c.dump_softmax = sc.data_ptr(), sm.data_ptr()
+    qd = torch.from_numpy(qkv).cuda()
+    out = torch.zeros(b * n, heads * 64, dtype=torch.int8, device='cuda')
+    cabi.check(cabi.lib().p2v_attention_int(qd.data_ptr(), out.data_ptr(), b, n, heads, C.byref(c), _stream()))
+    torch.cuda.synchronize()
+    return out.cpu().numpy(), sc.cpu().numpy(), sm.cpu().numpy()
+
+
+@pytest.mark.parametrize('n', [8, 16, 17, 128, 129, 160, 161, 192, 193, 197, 208])
+def test_attention_tcgen05_token_counts_and_zero_points(cabi, n):
+    """The tcgen05 attention kernel at every boundary of its tiling: one / two row tiles, ragged last key chunk of
+    1..32 columns (8-, 16- and 32-column TMEM loads), second-tile segments of 1, 32, 33, 64, 65 and 80 rows; non-zero
+    score and output zero points; score scales that clamp a large share of the scores at both ends."""
+    from diff_vit_b200.plan import AttentionPlan, softmax_exp_lut
+    rng = np.random.default_rng(1000 + n)
+    b, heads = 3, 2
+    for score_mul, szp, ozp, spread in ((2.0 ** -7, 0.0, 0.0, 2), (2.0 ** -5, 5.0, -3.0, 6), (2.0 ** -9, -100.0, 9.0, 6)):
+        qkv = _rand_i8(rng, b * n, 3 * heads * 64, lo=-20 * spread, hi=20 * spread)
+        p = AttentionPlan(score_mul=float(score_mul), score_zp=szp, out_mul=2.0 ** -15 * 2.0 ** -2, out_zp=ozp,
+                          levels=16, exp_lut=softmax_exp_lut(torch.tensor([2.0 ** -4])), in_zp=0.0)
+        want, want_sc, want_sm = hostmath.attention(qkv, b, n, heads, p)
+        got, sc, sm = _run_attention(cabi, qkv, b, n, heads, p)
+        np.testing.assert_array_equal(sc, want_sc)
+        np.testing.assert_array_equal(sm, want_sm)
+        np.testing.assert_array_equal(got, want)
+        got2, _, _ = _run_attention(cabi, qkv, b, n, heads, p, dump=False)
+        np.testing.assert_array_equal(got2, want)
+        old, _, _ = _run_attention(cabi, qkv, b, n, heads, p, legacy=True)
+        np.testing.assert_array_equal(old, want)
+
+
+def test_attention_tcgen05_many_items_per_cta(cabi):
+    """More (image, head) items than SMs, so that every persistent CTA walks five items through its two-stage operand
+    ring, both TMEM tile pipelines and all four rotations of the second row tile over the lane quarters; peaked rows
+    (one dominant key: the irregular first steps of the code function) and flat rows in the same batch."""
+    from diff_vit_b200.plan import AttentionPlan, softmax_exp_lut
+    rng = np.random.default_rng(77)
+    b, n, heads = 110, 197, 6                      # 660 items on 148 CTAs
+    qkv = _rand_i8(rng, b * n, 3 * heads * 64, lo=-40, hi=40)
+    q3 = qkv.reshape(b, n, 3, heads, 64)
+    q3[::3, :, 0] //= 8                            # flat rows: small queries
+    q3[1::3, 5, 1] = np.clip(q3[1::3, 5, 1].astype(np.int32) * 3, -128, 127).astype(np.int8)   # a dominant key
+    p = AttentionPlan(score_mul=float(2.0 ** -8), score_zp=0.0, out_mul=2.0 ** -15 * 2.0 ** -1, out_zp=0.0,
+                      levels=16, exp_lut=softmax_exp_lut(torch.tensor([2.0 ** -3])), in_zp=0.0)
+    want, want_sc, want_sm = hostmath.attention(qkv, b, n, heads, p)
+    got, sc, sm = _run_attention(cabi, qkv, b, n, heads, p)
+    np.testing.assert_array_equal(sc, want_sc)
+    np.testing.assert_array_equal(sm, want_sm)
+    np.testing.assert_array_equal(got, want)
+    assert want_sm.min() == 0 and want_sm.max() == 16
+    got2, _, _ = _run_attention(cabi, qkv, b, n, heads, p, dump=False)
+    np.testing.assert_array_equal(got2, want)
 
 
 def test_quant_patchify_and_embed(cabi):
