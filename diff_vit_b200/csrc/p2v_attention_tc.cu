@@ -45,7 +45,9 @@ namespace p2v {
 constexpr int kTcMaxN = 208;           // keys per item: N of the S MMA (multiple of 16)
 constexpr int kTcVRows = 224;          // V rows staged (multiple of 32: seven K = 32 steps of PV)
 constexpr int kTcSoftWarps = 8;
-constexpr int kTcThreads = (kTcSoftWarps + 2) * 32;
+constexpr int kTcThreads = (kTcSoftWarps + 4) * 32;   // warps 8, 9 unused: the two control warps sit on the
+                                                         // schedulers (warp id % 4 = 2, 3) whose softmax warps have the least to do
+constexpr int kTcProducerWarp = 10, kTcMmaWarp = 11;
 constexpr int kTcStages = 2;
 constexpr int kTcTileCols = 240;       // TMEM columns per row tile
 constexpr int kColPhi = 0, kColPlo1 = 56, kColOhi = 80, kColOlo = 144, kColPlo0 = 208;
@@ -72,6 +74,7 @@ struct TcArgs {
   const float* exp_lut;
   int8_t* dump_scores;
   uint8_t* dump_softmax;
+  long long* timeline;       // test hook (p2v_attention_tc_set_timeline): per-phase clock64 stamps of CTA 0
 };
 
 // ---- PTX wrappers this kernel adds to p2v_common.cuh -------------------------------------------------------------
@@ -290,7 +293,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_co
   const int nchunks = (n + 31) >> 5;                 // 32-key chunks = K steps of P V
   const int my_items = ((int)a.items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
-  if (warp == 8 && lane == 0) {
+  if (warp == kTcProducerWarp && lane == 0) {
     tma_prefetch_desc(&tm_q128); tma_prefetch_desc(&tm_q32); tma_prefetch_desc(&tm_q16);
     tma_prefetch_desc(&tm_k); tma_prefetch_desc(&tm_v); tma_prefetch_desc(&tm_out);
     for (int i = 0; i < kTcStages; ++i) {
@@ -305,7 +308,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_co
     }
     fence_mbar_init();
   }
-  if (warp == 9) tmem_alloc<512>(&s.tmem_base);
+  if (warp == kTcMmaWarp) tmem_alloc<512>(&s.tmem_base);
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
@@ -339,7 +342,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_co
   __syncthreads();
   tc_fence_after_sync();
 
-  if (warp == 8) {
+  if (warp == kTcProducerWarp) {
     // ---- TMA producer -----------------------------------------------------------------------------------------------
     if (elect_one()) {
       const uint32_t bytes = 8192u + (ntiles == 2 ? 5120u : 0u) + (uint32_t)(kTcMaxN * 64) + (uint32_t)(kTcVRows * 64);
@@ -361,7 +364,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_co
         tma_load_3d(s.v[st], &tm_v, &s.full[st], (2 * a.heads + head) * 64, 0, img);
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == kTcMmaWarp) {
     // ---- MMA issuer: two independent tile pipelines, polled -----------------------------------------------------------
     if (elect_one()) {
       const uint32_t idesc_s = umma_idesc_i8x(128, (uint32_t)nmma, true, true, false);
@@ -416,7 +419,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_co
         if (!progressed) __nanosleep(64);
       }
     }
-  } else {
+  } else if (warp < kTcSoftWarps) {
     // ---- softmax + epilogue warps -------------------------------------------------------------------------------------
     const int t = warp >> 2, q = warp & 3;
     if (t < ntiles) {
@@ -444,8 +447,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_co
         rc.c0 = valid ? a.c0 : __uint_as_float(kMagic + 128u);
         rc.flo = __uint_as_float(kMagic);
         rc.fhi = __uint_as_float(kMagic + 255u);
-        mbar_wait(&s.s_full[t], i & 1);
+        auto stamp = [&](int phase) {
+          if (a.timeline != nullptr && blockIdx.x == 0 && lane == 0 && i < 12)
+            a.timeline[(i * 8 + warp) * 8 + phase] = clock64();
+        };
+        stamp(0);
+        mbar_wait_parked(&s.s_full[t], i & 1);
         tc_fence_after_sync();
+        stamp(1);
         if (warp_on) {
           uint32_t v[32];
           // ---- pass 1: row maximum / minimum of the raw accumulators ----
@@ -459,6 +468,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_co
             else if (last_cn == 16) { ld_chunk<16>(tile + 32 * nfull, v); minmax_chunk<16, true>(v, last_cnt, mx, mn); }
             else { ld_chunk<32>(tile + 32 * nfull, v); minmax_chunk<32, true>(v, last_cnt, mx, mn); }
           }
+          stamp(2);
           const int gmax = (int)(__float_as_uint(__fmaf_rn(__int_as_float(mx), rc.mul, rc.c0)) - kMagic);
           const int gmin = (int)(__float_as_uint(__fmaf_rn(__int_as_float(mn), rc.mul, rc.c0)) - kMagic);
           const bool clampw = __any_sync(0xffffffffu, gmax > 255 || gmin < 0);
@@ -479,6 +489,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_co
             else if (last_cn == 16) { ld_chunk<16>(tile + 32 * nfull, v); sum_chunk<true, 16, true>(v, last_cnt, rc, ke, acc); }
             else { ld_chunk<32>(tile + 32 * nfull, v); sum_chunk<true, 32, true>(v, last_cnt, rc, ke, acc); }
           }
+          stamp(3);
           const float fsum = __double2float_rn((acc[0] + acc[1]) + (acc[2] + acc[3]));   // exact integer -> RNE, as u64 -> f32
           // u = S / (3e) + 1/6 is evaluated scaled by 2^-120 (exact), which puts its exponent field into 5 .. 31:
           // a shift count, 2^(15-k) = 0x100000 >> field
@@ -543,10 +554,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_co
         tc_fence_before_sync();
         __syncwarp();
         if (lane == 0) mbar_arrive(&s.p_ready[t]);
+        stamp(4);
 
         // ---- epilogue: O = (O_hi << 8) + O_lo -> RNE shift to the qact2 grid -> int8, out through a TMA store ----
-        mbar_wait(&s.o_full[t], i & 1);
+        mbar_wait_parked(&s.o_full[t], i & 1);
         tc_fence_after_sync();
+        stamp(5);
         if (warp_on) {
           if (lane == 0) tma_store_wait_read();      // the previous item's store has finished reading the staging tile
           __syncwarp();
@@ -576,6 +589,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_co
           }
           fence_proxy_async_smem();
         }
+        stamp(6);
         // hand the region back with the accumulator bias in place for the next item's S (every warp: with the rotation
         // of the second tile a quarter that idles now holds rows next time)
 #pragma unroll
@@ -583,6 +597,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_co
         tmem_ld_wait_st();
         tc_fence_before_sync();
         __syncwarp();
+        stamp(7);
         if (lane == 0) {
           mbar_arrive(&s.s_free[t]);
           if (warp_on) {
@@ -596,7 +611,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_co
   }
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 9) tmem_dealloc<512>(tmem_base);
+  if (warp == kTcMmaWarp) tmem_dealloc<512>(tmem_base);
 }
 
 // ---- host side ---------------------------------------------------------------------------------------------------
@@ -639,6 +654,7 @@ static int make_tmap_tokens(CUtensorMap* map, const void* ptr, int b, int n, int
 }
 
 constexpr int kTcSmemBytes = (int)sizeof(TcSmem) + 1024;
+static long long* g_tc_timeline = nullptr;
 
 int attention_tc_configure() {
   P2V_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
@@ -684,6 +700,7 @@ int attention_tc_launch(const int8_t* qkv, int8_t* out, int b, int n, int heads,
   a.exp_lut = p->exp_lut;
   a.dump_scores = p->dump_scores;
   a.dump_softmax = p->dump_softmax;
+  a.timeline = g_tc_timeline;
   const int grid = a.items < kNumSMs ? a.items : kNumSMs;
   if (p->dump_scores != nullptr)
     attention_tc_kernel<true><<<grid, kTcThreads, kTcSmemBytes, st>>>(tq128, tq32, tq16, tk, tv, to, a);
@@ -694,3 +711,11 @@ int attention_tc_launch(const int8_t* qkv, int8_t* out, int b, int n, int heads,
 }
 
 }  // namespace p2v
+
+// Test hook: device buffer of 12 x 8 x 8 int64 that receives clock64 stamps of CTA 0's softmax warps
+// ([item][warp][phase]: 0 before / 1 after the S wait, 2 / 3 / 4 after passes 1 / 2 / 3, 5 after the O wait, 6 after the
+// epilogue arithmetic, 7 after the accumulator bias was restored); NULL switches it off.
+extern "C" int p2v_attention_tc_set_timeline(long long* buf) {
+  p2v::g_tc_timeline = buf;
+  return P2V_OK;
+}

@@ -87,6 +87,23 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "r"(parity)
       : "memory");
 }
+// The same wait with a suspend-time hint: the thread is parked by the hardware until the phase completes (or the hint,
+// in ns, runs out) instead of coming back from try_wait every few hundred cycles.  For warps that wait long and share
+// a scheduler with working warps (ncu: the spin of the plain form was a quarter of all instructions the tcgen05
+// attention kernel executed).
+__device__ __forceinline__ void mbar_wait_parked(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity), "r"(0x989680u)
+      : "memory");
+}
 
 // Same wait for the single-thread producer / MMA roles, which spend most of an epilogue-bound kernel blocked: sleep
 // between polls, so that their try_wait / branch loop (ncu: 8 % of all issued instructions of the fc1 GEMM) stops

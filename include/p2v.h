@@ -143,6 +143,9 @@ typedef struct p2v_attention {
 } p2v_attention;
 int p2v_attention_int(const int8_t* qkv, int8_t* out, int b, int n, int heads, const p2v_attention* p,
                       void* stream);
+/* Test hook of the tcgen05 attention kernel: buf (device, 12 x 8 x 8 int64, or NULL = off) receives clock64 stamps of
+ * CTA 0's softmax warps, [item][warp][phase] (tools/att_timeline.py prints them). */
+int p2v_attention_tc_set_timeline(long long* buf);
 
 /* Standalone QAct on fp32 data (module-level use): out = (clamp(RNE(x/s + zp)) - zp) * s with a scale
  * per channel of the innermost (inner == 1) or of an outer dimension.  models/ptq/layers.py:207-220. */
