@@ -17,10 +17,14 @@
 //   columns  56.. 79  P low plane, keys 128..223          columns 208..239  P low plane, keys 0..127
 //   columns  80..143  O high = P_hi V    columns 144..207  O low = P_lo V   (M128 x N64 x K32 per 32 keys, V MN-major)
 //
-// Warp roles (10 warps): 0-3 softmax + epilogue of tile 0 (warp q owns TMEM lane quarter q = its 32 rows), 4-7 the
-// same for tile 1, 8 TMA producer (Q, K, V of the next item into a 2-stage ring), 9 MMA issuer (one elected lane; it
-// polls both tile pipelines, which run independently of each other).  With tcgen05.ld 32x32b a thread owns a whole
-// score row: row maximum, exact row sum and the per-row constants need no shuffles.
+// Warp roles (19 warps): 0-7 softmax + epilogue of tile 0, 8-15 of tile 1, 16 / 17 MMA issuers of tile 0 / 1 (one elected
+// lane each; the two tile pipelines run independently of each other), 18 TMA producer (Q, K, V of the next item into a
+// 2-stage ring).  Control warps only ever sleep on mbarriers (try_wait with a suspend hint): no polling.  A softmax warp w owns TMEM lane quarter w % 4 of its tile (tcgen05.ld lets a warp touch no other lanes),
+// i.e. 32 rows, one per thread (32x32b loads): row maximum, exact row sum and per-row constants need no shuffles.  Two
+// warps share each 32 rows and walk alternate 32-key chunks of them (w / 4 even: chunks 0, 2, 4, 6; odd: 1, 3, 5),
+// exchanging the row maximum / minimum and the partial row sums through shared memory: a lone warp spends most of its
+// time on the latencies of TMEM loads, table lookups and the fp64 sum chain (timeline: 0.4 instructions per cycle),
+// four resident warps per scheduler hide them.
 //
 // Arithmetic per score element (the kernel is bound by CUDA-core issue, not by the tensor pipe, so this is what counts):
 //   * the TMEM accumulator starts from 0x4B400000 (tcgen05.st by the softmax warps, MMAs accumulate on top), so the
@@ -44,10 +48,12 @@ namespace p2v {
 
 constexpr int kTcMaxN = 208;           // keys per item: N of the S MMA (multiple of 16)
 constexpr int kTcVRows = 224;          // V rows staged (multiple of 32: seven K = 32 steps of PV)
-constexpr int kTcSoftWarps = 8;
-constexpr int kTcThreads = (kTcSoftWarps + 4) * 32;   // warps 8, 9 unused: the two control warps sit on the
-                                                         // schedulers (warp id % 4 = 2, 3) whose softmax warps have the least to do
-constexpr int kTcProducerWarp = 10, kTcMmaWarp = 11;
+constexpr int kTcSoftWarps = 16;       // 2 row tiles x 4 lane quarters x 2 column halves
+constexpr int kTcThreads = (kTcSoftWarps + 3) * 32;   // 608 threads: up to 104 registers each (the kernel needs 96)
+constexpr int kTcMmaWarp0 = 16;        // MMA issuer of tile 0 (one elected lane), tile 1: the next warp
+constexpr int kTcProducerWarp = 18;
+// (setmaxnreg was tried to move registers from the control warps to the softmax warps: ptxas 12.9 then either fails to
+// allocate or spills more than without it, so the softmax passes work on 16-column pieces that fit the plain budget.)
 constexpr int kTcStages = 2;
 constexpr int kTcTileCols = 240;       // TMEM columns per row tile
 constexpr int kColPhi = 0, kColPlo1 = 56, kColOhi = 80, kColOlo = 144, kColPlo0 = 208;
@@ -57,10 +63,13 @@ struct TcSmem {
   alignas(1024) uint8_t q[kTcStages][2][128 * 64];
   alignas(1024) uint8_t k[kTcStages][kTcMaxN * 64];
   alignas(1024) uint8_t v[kTcStages][kTcVRows * 64];
-  alignas(1024) uint8_t ostage[kTcSoftWarps][32 * 64];   // per warp: its 32 output rows, 64-byte swizzle, TMA-stored
+  alignas(1024) uint8_t ostage[8][32 * 64];   // per warp pair: its 32 output rows, 64-byte swizzle, TMA-stored
   alignas(16) uint32_t tab_e[256 * 32];   // [255 - d][lane]: high word of (double)e(d)
   alignas(16) float2 tab_r[256 * 32];     // [255 - d][lane]: low / high bracket of 1 / (3 e(d))
   float lut[256];                         // e(d), exact path
+  // exchange between the two warps that share 32 rows (each walks every other 32-key chunk of them)
+  int2 x_minmax[8][2][32];
+  double x_sum[8][2][32];
   alignas(8) uint64_t full[kTcStages];
   uint64_t empty[kTcStages];
   uint64_t s_full[2], p_ready[2], o_full[2], s_free[2];
@@ -133,6 +142,10 @@ __device__ __forceinline__ void tmem_fill_32x16(uint32_t taddr, uint32_t c) {
       "r"(c)
       : "memory");
 }
+__device__ __forceinline__ void tmem_fill_32x8(uint32_t taddr, uint32_t c) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(taddr), "r"(c) : "memory");
+}
+__device__ __forceinline__ void pair_barrier(int pair) { asm volatile("bar.sync %0, 64;" ::"r"(1 + pair) : "memory"); }
 __device__ __forceinline__ void tmem_ld_32x32_nowait(uint32_t taddr, uint32_t (&v)[32]) { tmem_ld_32x32(taddr, v); }
 
 // Shared-memory matrix descriptors for tiles whose rows are 64 bytes with the 64-byte swizzle (what a TMA box of
@@ -199,12 +212,11 @@ __device__ __forceinline__ float2 score_pair(uint32_t r0, uint32_t r1, const Row
   return f;
 }
 
-// CN (8, 16 or 32) consecutive columns of this thread's row
+// CN (8 or 16) consecutive columns of this thread's row.  (Pieces of 16 columns, not 32: the passes keep a piece and
+// its per-element temporaries in registers, and sixteen softmax warps leave 120 registers per thread.)
 template <int CN>
-__device__ __forceinline__ void ld_chunk(uint32_t taddr, uint32_t (&v)[32]) {
-  if constexpr (CN == 32) {
-    tmem_ld_32x32(taddr, v);
-  } else if constexpr (CN == 16) {
+__device__ __forceinline__ void ld_piece(uint32_t taddr, uint32_t (&v)[16]) {
+  if constexpr (CN == 16) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
         "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
@@ -221,9 +233,9 @@ __device__ __forceinline__ void ld_chunk(uint32_t taddr, uint32_t (&v)[32]) {
   tmem_ld_wait();
 }
 
-// pass 1 over one chunk: row maximum / minimum of the raw accumulators (monotone in the score code)
+// pass 1 over one piece: row maximum / minimum of the raw accumulators (monotone in the score code)
 template <int CN, bool kMask>
-__device__ __forceinline__ void minmax_chunk(const uint32_t (&v)[32], int cnt, int& mx, int& mn) {
+__device__ __forceinline__ void minmax_piece(const uint32_t (&v)[16], int cnt, int& mx, int& mn) {
 #pragma unroll
   for (int j = 0; j < CN; ++j) {
     if (!kMask || j < cnt) {
@@ -233,9 +245,9 @@ __device__ __forceinline__ void minmax_chunk(const uint32_t (&v)[32], int cnt, i
   }
 }
 
-// pass 2 over one chunk: exact sum of e(d) over its first `cnt` columns (all CN without kMask)
+// pass 2 over one piece: exact sum of e(d) over its first `cnt` columns (all CN without kMask)
 template <bool kClamp, int CN, bool kMask>
-__device__ __forceinline__ void sum_chunk(const uint32_t (&v)[32], int cnt, const RowConst& rc, uint32_t ke, double (&acc)[4]) {
+__device__ __forceinline__ void sum_piece(const uint32_t (&v)[16], int cnt, const RowConst& rc, uint32_t ke, double (&acc)[4]) {
 #pragma unroll
   for (int j = 0; j < CN; j += 2) {
     const float2 f = score_pair<kClamp>(v[j], v[j + 1], rc);
@@ -246,10 +258,10 @@ __device__ __forceinline__ void sum_chunk(const uint32_t (&v)[32], int cnt, cons
   }
 }
 
-// pass 3 over one chunk: 16-bit probabilities 2^(15-k) of its first `cnt` columns into v (0 beyond, up to column 32),
+// pass 3 over one piece: 16-bit probabilities 2^(15-k) of its first `cnt` columns into v (0 beyond, up to column 16),
 // returns the OR of (low-bracket bits ^ high-bracket bits): a set exponent bit means some element sits next to a step
 template <bool kClamp, bool kPeak, int CN, bool kMask>
-__device__ __forceinline__ uint32_t prob_chunk(uint32_t (&v)[32], int cnt, const RowConst& rc, uint32_t kr, float fsum,
+__device__ __forceinline__ uint32_t prob_piece(uint32_t (&v)[16], int cnt, const RowConst& rc, uint32_t kr, float fsum,
                                                float sixth, uint32_t fmax_bits, uint32_t p_top) {
   uint32_t guard = 0;
 #pragma unroll
@@ -275,7 +287,7 @@ __device__ __forceinline__ uint32_t prob_chunk(uint32_t (&v)[32], int cnt, const
     v[j + 1] = pb;
   }
 #pragma unroll
-  for (int j = CN; j < 32; ++j) v[j] = 0u;
+  for (int j = CN; j < 16; ++j) v[j] = 0u;
   return guard;
 }
 
@@ -298,25 +310,25 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_co
     tma_prefetch_desc(&tm_k); tma_prefetch_desc(&tm_v); tma_prefetch_desc(&tm_out);
     for (int i = 0; i < kTcStages; ++i) {
       mbar_init(&s.full[i], 1);
-      mbar_init(&s.empty[i], 1);
+      mbar_init(&s.empty[i], (uint32_t)ntiles);   // one commit per tile pipeline
     }
     for (int t = 0; t < 2; ++t) {
       mbar_init(&s.s_full[t], 1);
-      mbar_init(&s.p_ready[t], 4);
+      mbar_init(&s.p_ready[t], 8);
       mbar_init(&s.o_full[t], 1);
-      mbar_init(&s.s_free[t], 4);
+      mbar_init(&s.s_free[t], 8);
     }
     fence_mbar_init();
   }
-  if (warp == kTcMmaWarp) tmem_alloc<512>(&s.tmem_base);
+  if (warp == kTcMmaWarp0) tmem_alloc<512>(&s.tmem_base);
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = s.tmem_base;
 
   if (warp < kTcSoftWarps) {
-    // ---- tables (all eight softmax warps) and the initial accumulator bias of this warp's lanes ----------------------
-    {
+    // ---- tables (warps 0-7, 32 entries each) and the initial accumulator bias of this warp's half of its lanes' columns --
+    if (warp < 8) {
       const int d = warp * 32 + lane;                 // this lane evaluates entry d ...
       const float e = a.exp_lut[d];
       s.lut[d] = e;
@@ -332,10 +344,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_co
         s.tab_r[(255 - dj) * 32 + lane] = make_float2(lj, hj);
       }
     }
-    const int t = warp >> 2, q = warp & 3;
+    const int t = warp >> 3, hf = (warp >> 2) & 1, q = warp & 3;
     const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + t * kTcTileCols;
-#pragma unroll
-    for (int c = 0; c < kTcMaxN; c += 16) tmem_fill_32x16(trow + c, kMagic);
+    for (int c = hf * (kTcMaxN / 2); c < (hf + 1) * (kTcMaxN / 2); c += 8) tmem_fill_32x8(trow + c, kMagic);
     tmem_ld_wait_st();
     tc_fence_before_sync();
   }
@@ -364,74 +375,48 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_co
         tma_load_3d(s.v[st], &tm_v, &s.full[st], (2 * a.heads + head) * 64, 0, img);
       }
     }
-  } else if (warp == kTcMmaWarp) {
-    // ---- MMA issuer: two independent tile pipelines, polled -----------------------------------------------------------
-    if (elect_one()) {
+  } else if (warp == kTcMmaWarp0 || warp == kTcMmaWarp0 + 1) {
+    // ---- MMA issuers: one warp (one elected lane) per tile pipeline ----------------------------------------------------
+    const int t = warp - kTcMmaWarp0;
+    if (t < ntiles && elect_one()) {
       const uint32_t idesc_s = umma_idesc_i8x(128, (uint32_t)nmma, true, true, false);
       const uint32_t idesc_pv = umma_idesc_i8x(128, 64, false, true, true);
-      int s_item[2] = {0, 0};    // next item whose S this tile needs
-      int pv_item[2] = {0, 0};   // next item whose P V this tile needs
-      int released = 0;          // items whose smem stage went back to the producer
-      const int last_tile = ntiles - 1;
-      while (pv_item[0] < my_items || (ntiles == 2 && pv_item[1] < my_items)) {
-        bool progressed = false;
-#pragma unroll
-        for (int t = 0; t < 2; ++t) {
-          if (t > last_tile) continue;
-          const uint32_t tile = tmem_base + t * kTcTileCols;
-          // S of item s_item[t]: its operands have landed, and the tile's TMEM region was handed back
-          if (s_item[t] < my_items && s_item[t] == pv_item[t]) {
-            const int i = s_item[t], st = i & 1;
-            if (mbar_test(&s.full[st], (i >> 1) & 1) && (i == 0 || mbar_test(&s.s_free[t], (i - 1) & 1))) {
-              tc_fence_after_sync();
-              const uint64_t dq = umma_desc_sw64(smem_u32(s.q[st][t])), dk = umma_desc_sw64(smem_u32(s.k[st]));
-              tc_mma_i8(tile, dq, dk, idesc_s, 1u);                 // accumulates onto the 1.5 * 2^23 bias
-              tc_mma_i8(tile, dq + 2, dk + 2, idesc_s, 1u);         // second half of the head dimension: +32 bytes
-              tc_commit(&s.s_full[t]);
-              ++s_item[t];
-              progressed = true;
-            }
-          }
-          // P V of item pv_item[t]: all four warps of the tile have written their probability planes
-          if (pv_item[t] < s_item[t]) {
-            const int i = pv_item[t], st = i & 1;
-            if (mbar_test(&s.p_ready[t], i & 1)) {
-              tc_fence_after_sync();
-              const uint64_t dv = umma_desc_sw64(smem_u32(s.v[st]));
-              for (int ks = 0; ks < nchunks; ++ks) {
-                const uint64_t dvk = dv + (uint64_t)(ks * (2048 >> 4));
-                tc_mma_i8_ts(tile + kColOhi, tile + kColPhi + 8 * ks, dvk, idesc_pv, (uint32_t)(ks != 0));
-                tc_mma_i8_ts(tile + kColOlo, tile + (ks < 4 ? kColPlo0 + 8 * ks : kColPlo1 + 8 * (ks - 4)), dvk, idesc_pv,
-                             (uint32_t)(ks != 0));
-              }
-              tc_commit(&s.o_full[t]);
-              ++pv_item[t];
-              progressed = true;
-              // the stage is free once both tiles' P V of its item have been issued (the commit covers all earlier MMAs)
-              const int done = ntiles == 2 ? min(pv_item[0], pv_item[1]) : pv_item[0];
-              while (released < done) {
-                tc_commit(&s.empty[released & 1]);
-                ++released;
-              }
-            }
-          }
+      const uint32_t tile = tmem_base + t * kTcTileCols;
+      for (int i = 0; i < my_items; ++i) {
+        const int st = i & 1;
+        // S of item i: its operands have landed, and the tile's TMEM region was handed back (bias restored)
+        mbar_wait_parked(&s.full[st], (i >> 1) & 1);
+        if (i > 0) mbar_wait_parked(&s.s_free[t], (i - 1) & 1);
+        tc_fence_after_sync();
+        const uint64_t dq = umma_desc_sw64(smem_u32(s.q[st][t])), dk = umma_desc_sw64(smem_u32(s.k[st]));
+        tc_mma_i8(tile, dq, dk, idesc_s, 1u);                 // accumulates onto the 1.5 * 2^23 bias
+        tc_mma_i8(tile, dq + 2, dk + 2, idesc_s, 1u);         // second half of the head dimension: +32 bytes
+        tc_commit(&s.s_full[t]);
+        // P V of item i: all eight warps of the tile have written their probability planes
+        mbar_wait_parked(&s.p_ready[t], i & 1);
+        tc_fence_after_sync();
+        const uint64_t dv = umma_desc_sw64(smem_u32(s.v[st]));
+        for (int ks = 0; ks < nchunks; ++ks) {
+          const uint64_t dvk = dv + (uint64_t)(ks * (2048 >> 4));
+          tc_mma_i8_ts(tile + kColOhi, tile + kColPhi + 8 * ks, dvk, idesc_pv, (uint32_t)(ks != 0));
+          tc_mma_i8_ts(tile + kColOlo, tile + (ks < 4 ? kColPlo0 + 8 * ks : kColPlo1 + 8 * (ks - 4)), dvk, idesc_pv,
+                       (uint32_t)(ks != 0));
         }
-        if (!progressed) __nanosleep(64);
+        tc_commit(&s.o_full[t]);
+        tc_commit(&s.empty[st]);      // this pipeline is done with the stage once these MMAs retire
       }
     }
   } else if (warp < kTcSoftWarps) {
     // ---- softmax + epilogue warps -------------------------------------------------------------------------------------
-    const int t = warp >> 2, q = warp & 3;
+    const int t = warp >> 3, hf = (warp >> 2) & 1, q = warp & 3;
+    const int pair = t * 4 + q;                       // the two warps (hf = 0, 1) that share 32 rows
     if (t < ntiles) {
       const uint32_t tile = tmem_base + ((uint32_t)(q * 32) << 16) + t * kTcTileCols;
       const float sixth = __fmul_rn(0.16666667f, __uint_as_float((127u - 120u) << 23));
       const uint32_t tab_e = smem_u32(s.tab_e) + lane * 4, tab_r = smem_u32(s.tab_r) + lane * 8;
       const int sh = a.out_shift;
       const int half_m1 = (1 << (sh - 1)) - 1 + (a.out_zp << sh);   // RNE shift with the zero point folded in
-      uint8_t* const ost = s.ostage[warp];
-      const int nfull = n >> 5;                       // chunks of 32 valid columns
-      const int last_cnt = n - 32 * nfull;            // valid columns of the ragged last chunk (0: none)
-      const int last_cn = last_cnt <= 8 ? 8 : (last_cnt <= 16 ? 16 : 32);
+      uint8_t* const ost = s.ostage[pair];
 
       for (int i = 0; i < my_items; ++i) {
         const int item = blockIdx.x + i * gridDim.x, img = item / a.heads, head = item % a.heads;
@@ -449,24 +434,31 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_co
         rc.fhi = __uint_as_float(kMagic + 255u);
         auto stamp = [&](int phase) {
           if (a.timeline != nullptr && blockIdx.x == 0 && lane == 0 && i < 12)
-            a.timeline[(i * 8 + warp) * 8 + phase] = clock64();
+            a.timeline[(i * 16 + warp) * 8 + phase] = clock64();
         };
         stamp(0);
         mbar_wait_parked(&s.s_full[t], i & 1);
         tc_fence_after_sync();
         stamp(1);
         if (warp_on) {
-          uint32_t v[32];
-          // ---- pass 1: row maximum / minimum of the raw accumulators ----
+          uint32_t v[16];
+          // ---- pass 1: row maximum / minimum of the raw accumulators, this warp's chunks, then both halves ----
           int mx = (int)0x80000000, mn = 0x7fffffff;
-          for (int c = 0; c < nfull; ++c) {
-            ld_chunk<32>(tile + 32 * c, v);
-            minmax_chunk<32, false>(v, 32, mx, mn);
+          for (int c = hf; c < nchunks; c += 2) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const int col = 32 * c + 16 * h, cnt = n - col;
+              if (cnt >= 16) { ld_piece<16>(tile + col, v); minmax_piece<16, false>(v, 16, mx, mn); }
+              else if (cnt > 8) { ld_piece<16>(tile + col, v); minmax_piece<16, true>(v, cnt, mx, mn); }
+              else if (cnt > 0) { ld_piece<8>(tile + col, v); minmax_piece<8, true>(v, cnt, mx, mn); }
+            }
           }
-          if (last_cnt > 0) {
-            if (last_cn == 8) { ld_chunk<8>(tile + 32 * nfull, v); minmax_chunk<8, true>(v, last_cnt, mx, mn); }
-            else if (last_cn == 16) { ld_chunk<16>(tile + 32 * nfull, v); minmax_chunk<16, true>(v, last_cnt, mx, mn); }
-            else { ld_chunk<32>(tile + 32 * nfull, v); minmax_chunk<32, true>(v, last_cnt, mx, mn); }
+          s.x_minmax[pair][hf][lane] = make_int2(mx, mn);
+          pair_barrier(pair);
+          {
+            const int2 o = s.x_minmax[pair][hf ^ 1][lane];
+            mx = max(mx, o.x);
+            mn = min(mn, o.y);
           }
           stamp(2);
           const int gmax = (int)(__float_as_uint(__fmaf_rn(__int_as_float(mx), rc.mul, rc.c0)) - kMagic);
@@ -479,18 +471,23 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_co
 
           // ---- pass 2: exact row sum of the integer exp ----
           double acc[4] = {0.0, 0.0, 0.0, 0.0};
-          for (int c = 0; c < nfull; ++c) {
-            ld_chunk<32>(tile + 32 * c, v);
-            if (clampw) sum_chunk<true, 32, false>(v, 32, rc, ke, acc);
-            else sum_chunk<false, 32, false>(v, 32, rc, ke, acc);
+          for (int c = hf; c < nchunks; c += 2) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const int col = 32 * c + 16 * h, cnt = n - col;
+              if (cnt >= 16) {
+                ld_piece<16>(tile + col, v);
+                if (clampw) sum_piece<true, 16, false>(v, 16, rc, ke, acc);
+                else sum_piece<false, 16, false>(v, 16, rc, ke, acc);
+              } else if (cnt > 8) { ld_piece<16>(tile + col, v); sum_piece<true, 16, true>(v, cnt, rc, ke, acc); }
+              else if (cnt > 0) { ld_piece<8>(tile + col, v); sum_piece<true, 8, true>(v, cnt, rc, ke, acc); }
+            }
           }
-          if (last_cnt > 0) {
-            if (last_cn == 8) { ld_chunk<8>(tile + 32 * nfull, v); sum_chunk<true, 8, true>(v, last_cnt, rc, ke, acc); }
-            else if (last_cn == 16) { ld_chunk<16>(tile + 32 * nfull, v); sum_chunk<true, 16, true>(v, last_cnt, rc, ke, acc); }
-            else { ld_chunk<32>(tile + 32 * nfull, v); sum_chunk<true, 32, true>(v, last_cnt, rc, ke, acc); }
-          }
+          const double part = (acc[0] + acc[1]) + (acc[2] + acc[3]);     // integers < 2^53: exact in any order
+          s.x_sum[pair][hf][lane] = part;
+          pair_barrier(pair);
+          const float fsum = __double2float_rn(part + s.x_sum[pair][hf ^ 1][lane]);   // exact integer -> RNE, as u64 -> f32
           stamp(3);
-          const float fsum = __double2float_rn((acc[0] + acc[1]) + (acc[2] + acc[3]));   // exact integer -> RNE, as u64 -> f32
           // u = S / (3e) + 1/6 is evaluated scaled by 2^-120 (exact), which puts its exponent field into 5 .. 31:
           // a shift count, 2^(15-k) = 0x100000 >> field
           const float fsum_s = __fmul_rn(fsum, __uint_as_float((127u - 120u) << 23));
@@ -500,51 +497,65 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_co
           const bool peakw = __any_sync(0xffffffffu, k_top < 2);
 
           // ---- pass 3: probabilities 2^(15-k) as two byte planes, written back to TMEM as the A operand of P V ----
-          for (int c = 0; c < nchunks; ++c) {
-            const bool ragged = c == nfull;
-            const int cnt = ragged ? last_cnt : 32;
-            uint32_t guard;
-            if (!ragged) {
-              ld_chunk<32>(tile + 32 * c, v);
-              if (clampw) guard = peakw ? prob_chunk<true, true, 32, false>(v, 32, rc, kr, fsum_s, sixth, fmax_bits, p_top)
-                                        : prob_chunk<true, false, 32, false>(v, 32, rc, kr, fsum_s, sixth, fmax_bits, p_top);
-              else guard = peakw ? prob_chunk<false, true, 32, false>(v, 32, rc, kr, fsum_s, sixth, fmax_bits, p_top)
-                                 : prob_chunk<false, false, 32, false>(v, 32, rc, kr, fsum_s, sixth, fmax_bits, p_top);
-            } else if (last_cn == 8) {
-              ld_chunk<8>(tile + 32 * c, v);
-              guard = prob_chunk<true, true, 8, true>(v, cnt, rc, kr, fsum_s, sixth, fmax_bits, p_top);
-            } else if (last_cn == 16) {
-              ld_chunk<16>(tile + 32 * c, v);
-              guard = prob_chunk<true, true, 16, true>(v, cnt, rc, kr, fsum_s, sixth, fmax_bits, p_top);
-            } else {
-              ld_chunk<32>(tile + 32 * c, v);
-              guard = prob_chunk<true, true, 32, true>(v, cnt, rc, kr, fsum_s, sixth, fmax_bits, p_top);
+          // The probability planes of chunk c go to columns 8c.. (high) and 208 + 8c.. / 56 + 8(c - 4).. (low): score
+          // columns of chunks 0, 1 and 2.  Chunks 0 / 2 are read by the even warp of the pair, chunk 1 by the odd one, so
+          // a pair barrier after each warp's first and second chunk load keeps every write behind the reads of BOTH warps
+          // (P(1), P(3) -> chunk 0 and P(4), P(6) -> chunk 1 after barrier one; P(5) -> chunk 2 after barrier two).
+#pragma unroll 1
+          for (int it = 0; it < 4; ++it) {
+            const int c = hf + 2 * it;
+            if (c >= nchunks) {
+              if (it < 2) pair_barrier(pair);
+              continue;
             }
-            const bool redo = __any_sync(0xffffffffu, (guard & 0x7f800000u) != 0u);
-            if (redo || kDump) {
-              // redo (rare): some element within 2^-20 of a step of the code function: the whole chunk again with the
-              // exact IEEE-division formula.  The raw scores are still in TMEM (P is written behind the read position).
-              uint32_t r2[32];
-              ld_chunk<32>(tile + 32 * c, r2);
-              int8_t* dsc = kDump ? a.dump_scores + ((int64_t)item * n + row) * n + 32 * c : nullptr;
-              uint8_t* dsm = kDump ? a.dump_softmax + ((int64_t)item * n + row) * n + 32 * c : nullptr;
+            uint32_t hi[8], lo[8];                    // the chunk's two planes: words 0-3 keys 0-15, words 4-7 keys 16-31
 #pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                const float f = fminf(fmaxf(__fmaf_rn(__uint_as_float(r2[j]), rc.mul, rc.c0), rc.flo), rc.fhi);
-                const int g = (int)(__float_as_uint(f) - kMagic);
-                if (redo) v[j] = j < cnt ? tc_exact_prob16(fsum, s.lut[cmaxb - g]) : 0u;
-                if (kDump && valid && j < cnt) {
-                  dsc[j] = (int8_t)(g - 128);
-                  dsm[j] = (uint8_t)(v[j] ? __clz(v[j]) - 16 : 16);
+            for (int h = 0; h < 2; ++h) {
+              const int col = 32 * c + 16 * h, cnt = min(n - col, 16);
+              if (cnt >= 16 || cnt > 8) ld_piece<16>(tile + col, v);
+              else if (cnt > 0) ld_piece<8>(tile + col, v);
+              if (h == 1 && it < 2) pair_barrier(pair);      // both warps hold their whole chunk: P may now be written
+              if (cnt <= 0) {
+#pragma unroll
+                for (int w = 0; w < 4; ++w) hi[4 * h + w] = lo[4 * h + w] = 0u;
+                continue;
+              }
+              uint32_t guard;
+              if (cnt >= 16) {
+                if (clampw) guard = peakw ? prob_piece<true, true, 16, false>(v, 16, rc, kr, fsum_s, sixth, fmax_bits, p_top)
+                                          : prob_piece<true, false, 16, false>(v, 16, rc, kr, fsum_s, sixth, fmax_bits, p_top);
+                else guard = peakw ? prob_piece<false, true, 16, false>(v, 16, rc, kr, fsum_s, sixth, fmax_bits, p_top)
+                                   : prob_piece<false, false, 16, false>(v, 16, rc, kr, fsum_s, sixth, fmax_bits, p_top);
+              } else if (cnt > 8) {
+                guard = prob_piece<true, true, 16, true>(v, cnt, rc, kr, fsum_s, sixth, fmax_bits, p_top);
+              } else {
+                guard = prob_piece<true, true, 8, true>(v, cnt, rc, kr, fsum_s, sixth, fmax_bits, p_top);
+              }
+              const bool redo = __any_sync(0xffffffffu, (guard & 0x7f800000u) != 0u);
+              if (redo || kDump) {
+                // redo (rare): some element within 2^-20 of a step of the code function: the whole piece again with the
+                // exact IEEE-division formula.  The raw scores are still in TMEM (P is written behind the read position).
+                uint32_t r2[16];
+                ld_piece<16>(tile + col, r2);
+                int8_t* dsc = kDump ? a.dump_scores + ((int64_t)item * n + row) * n + col : nullptr;
+                uint8_t* dsm = kDump ? a.dump_softmax + ((int64_t)item * n + row) * n + col : nullptr;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                  const float f = fminf(fmaxf(__fmaf_rn(__uint_as_float(r2[j]), rc.mul, rc.c0), rc.flo), rc.fhi);
+                  const int g = (int)(__float_as_uint(f) - kMagic);
+                  if (redo) v[j] = j < cnt ? tc_exact_prob16(fsum, s.lut[cmaxb - g]) : 0u;
+                  if (kDump && valid && j < cnt) {
+                    dsc[j] = (int8_t)(g - 128);
+                    dsm[j] = (uint8_t)(v[j] ? __clz(v[j]) - 16 : 16);
+                  }
                 }
               }
-            }
-            uint32_t hi[8], lo[8];
 #pragma unroll
-            for (int w = 0; w < 8; ++w) {
-              const uint32_t a01 = v[4 * w] | (v[4 * w + 1] << 16), a23 = v[4 * w + 2] | (v[4 * w + 3] << 16);
-              lo[w] = __byte_perm(a01, a23, 0x6420);
-              hi[w] = __byte_perm(a01, a23, 0x7531);
+              for (int w = 0; w < 4; ++w) {
+                const uint32_t a01 = v[4 * w] | (v[4 * w + 1] << 16), a23 = v[4 * w + 2] | (v[4 * w + 3] << 16);
+                lo[4 * h + w] = __byte_perm(a01, a23, 0x6420);
+                hi[4 * h + w] = __byte_perm(a01, a23, 0x7531);
+              }
             }
             tmem_st_32x8(tile + kColPhi + 8 * c, hi);
             tmem_st_32x8(tile + (c < 4 ? kColPlo0 + 8 * c : kColPlo1 + 8 * (c - 4)), lo);
@@ -561,13 +572,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_co
         tc_fence_after_sync();
         stamp(5);
         if (warp_on) {
-          if (lane == 0) tma_store_wait_read();      // the previous item's store has finished reading the staging tile
-          __syncwarp();
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            uint32_t oh[32], ol[32];
-            tmem_ld_32x32(tile + kColOhi + 32 * h, oh);
-            tmem_ld_32x32(tile + kColOlo + 32 * h, ol);
+          if (hf == 0 && lane == 0) tma_store_wait_read();   // the previous item's store has finished reading the staging tile
+          pair_barrier(pair);
+          {
+            uint32_t oh[32], ol[32];                  // this warp's 32 of the 64 head channels
+            tmem_ld_32x32(tile + kColOhi + 32 * hf, oh);
+            tmem_ld_32x32(tile + kColOlo + 32 * hf, ol);
             tmem_ld_wait();
             uint32_t w8[8];
 #pragma unroll
@@ -583,35 +593,33 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_co
             // row `lane` of the 32 x 64-byte staging tile, 16-byte chunks XOR-swizzled by (row >> 1) & 3 (SWIZZLE_64B)
 #pragma unroll
             for (int ck = 0; ck < 2; ++ck) {
-              const int chunk = (2 * h + ck) ^ ((lane >> 1) & 3);
+              const int chunk = (2 * hf + ck) ^ ((lane >> 1) & 3);
               *reinterpret_cast<uint4*>(ost + lane * 64 + chunk * 16) = make_uint4(w8[4 * ck], w8[4 * ck + 1], w8[4 * ck + 2], w8[4 * ck + 3]);
             }
           }
           fence_proxy_async_smem();
-        }
-        stamp(6);
-        // hand the region back with the accumulator bias in place for the next item's S (every warp: with the rotation
-        // of the second tile a quarter that idles now holds rows next time)
-#pragma unroll
-        for (int c = 0; c < kTcMaxN; c += 16) tmem_fill_32x16(tile + c, kMagic);
-        tmem_ld_wait_st();
-        tc_fence_before_sync();
-        __syncwarp();
-        stamp(7);
-        if (lane == 0) {
-          mbar_arrive(&s.s_free[t]);
-          if (warp_on) {
+          pair_barrier(pair);
+          if (hf == 0 && lane == 0) {
             tma_store_3d(&tm_out, ost, head * 64, row0, img);   // rows >= n are clipped by the tensor map
             tma_store_commit();
           }
         }
+        stamp(6);
+        // hand the region back with the accumulator bias in place for the next item's S (every warp: with the rotation
+        // of the second tile a quarter that idles now holds rows next time)
+        for (int c = hf * (kTcMaxN / 2); c < (hf + 1) * (kTcMaxN / 2); c += 8) tmem_fill_32x8(tile + c, kMagic);
+        tmem_ld_wait_st();
+        tc_fence_before_sync();
+        __syncwarp();
+        stamp(7);
+        if (lane == 0) mbar_arrive(&s.s_free[t]);
       }
-      if (lane == 0) tma_store_wait_all();
+      if (hf == 0 && lane == 0) tma_store_wait_all();
     }
   }
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == kTcMmaWarp) tmem_dealloc<512>(tmem_base);
+  if (warp == kTcMmaWarp0) tmem_dealloc<512>(tmem_base);
 }
 
 // ---- host side ---------------------------------------------------------------------------------------------------
@@ -712,7 +720,7 @@ int attention_tc_launch(const int8_t* qkv, int8_t* out, int b, int n, int heads,
 
 }  // namespace p2v
 
-// Test hook: device buffer of 12 x 8 x 8 int64 that receives clock64 stamps of CTA 0's softmax warps
+// Test hook: device buffer of 12 x 16 x 8 int64 that receives clock64 stamps of CTA 0's softmax warps
 // ([item][warp][phase]: 0 before / 1 after the S wait, 2 / 3 / 4 after passes 1 / 2 / 3, 5 after the O wait, 6 after the
 // epilogue arithmetic, 7 after the accumulator bias was restored); NULL switches it off.
 extern "C" int p2v_attention_tc_set_timeline(long long* buf) {
