@@ -59,26 +59,34 @@ constexpr int kTcTileCols = 240;       // TMEM columns per row tile
 constexpr int kColPhi = 0, kColPlo1 = 56, kColOhi = 80, kColOlo = 144, kColPlo0 = 208;
 constexpr uint32_t kMagic = 0x4B400000u;   // 1.5 * 2^23
 
-struct TcSmem {
-  alignas(1024) uint8_t q[kTcStages][2][128 * 64];
-  alignas(1024) uint8_t k[kTcStages][kTcMaxN * 64];
-  alignas(1024) uint8_t v[kTcStages][kTcVRows * 64];
-  alignas(1024) uint8_t ostage[8][32 * 64];   // per warp pair: its 32 output rows, 64-byte swizzle, TMA-stored
-  alignas(16) uint32_t tab_e[256 * 32];   // [255 - d][lane]: high word of (double)e(d)
-  alignas(16) float2 tab_r[256 * 32];     // [255 - d][lane]: low / high bracket of 1 / (3 e(d))
-  float lut[256];                         // e(d), exact path
-  // exchange between the two warps that share 32 rows (each walks every other 32-key chunk of them)
-  int2 x_minmax[8][2][32];
+// Shared memory, by shared-window address (the lookup table must sit on a 64 KiB boundary, see below):
+//   [A0, A0 + 59 KiB)      operand stage 0 (Q tile 0 / 1, K, V) and the eight 2 KiB output staging tiles; A0 = the
+//                          1 KiB-aligned start of dynamic shared memory (must be <= 5 KiB)
+//   [64 KiB, 128 KiB)      table, one 256-byte row per reversed distance 255 - d:
+//                            bytes   0..127  high word of (double)e(d), replicated per lane (lane * 4)
+//                            bytes 128..255  (low, high) bracket of 1 / (3 e(d)), 16 replicas ((lane & 15) * 8): a
+//                                            64-bit load is served per half-warp, so lanes l and l + 16 never collide
+//                          A lookup address is base | (index << 8): one PRMT that drops the index byte into byte 1 of
+//                          the per-lane base - which is why the table needs the alignment.
+//   [128 KiB, ...)         operand stage 1, e(d) for the exact path, the pair exchange slots, mbarriers
+constexpr uint32_t kOffQ = 0, kOffK = 16384, kOffV = kOffK + kTcMaxN * 64, kStageBytes = kOffV + kTcVRows * 64;   // 44032
+constexpr uint32_t kOffOstage = kStageBytes;                     // relative to A0
+constexpr uint32_t kRegionABytes = kOffOstage + 8 * 2048;        // 60416
+constexpr uint32_t kTabAddr = 65536, kRegionCAddr = 131072;
+struct TcTail {                                                  // at kRegionCAddr + kStageBytes
+  float lut[256];
+  int2 x_minmax[8][2][32];     // exchange between the two warps that share 32 rows
   double x_sum[8][2][32];
   alignas(8) uint64_t full[kTcStages];
   uint64_t empty[kTcStages];
   uint64_t s_full[2], p_ready[2], o_full[2], s_free[2];
   uint32_t tmem_base;
 };
+constexpr uint32_t kTcSmemEnd = kRegionCAddr + kStageBytes + (uint32_t)sizeof(TcTail);
 
 struct TcArgs {
   int n, heads, items;
-  float score_mul, c0;       // f = fma(t, score_mul, c0) = 1.5 * 2^23 + RNE(acc * mul) + zp + 128
+  float score_mul, c0;       // f = fma(t, score_mul, c0) = acc * mul + zp + 128 for t = 1.5 * 2^23 + acc (exact)
   int out_shift, out_zp;
   const float* exp_lut;
   int8_t* dump_scores;
@@ -196,98 +204,113 @@ __device__ __noinline__ uint32_t tc_exact_prob16(float fsum, float e) {
   return k >= 16 ? 0u : (0x8000u >> k);
 }
 
-// ---- one row's three passes over its score row --------------------------------------------------------------------
-struct RowConst {
-  float mul, c0;          // score re-quantisation (see TcArgs)
-  float flo, fhi;         // clamp bounds: biased codes 0 and 255 in the magic representation
-};
-
-template <bool kClamp>
-__device__ __forceinline__ float2 score_pair(uint32_t r0, uint32_t r1, const RowConst& rc) {
-  float2 f = ffma2(make_float2(__uint_as_float(r0), __uint_as_float(r1)), make_float2(rc.mul, rc.mul), make_float2(rc.c0, rc.c0));
-  if (kClamp) {
-    f.x = fminf(fmaxf(f.x, rc.flo), rc.fhi);
-    f.y = fminf(fmaxf(f.y, rc.flo), rc.fhi);
-  }
-  return f;
+// ---- the softmax passes of one thread (= one score row) ---------------------------------------------------------------
+__device__ __forceinline__ void tmem_ld_32x4(uint32_t taddr, uint32_t (&v)[4]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3])
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x4(uint32_t taddr, const uint32_t (&v)[4]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(v[0]), "r"(v[1]),
+               "r"(v[2]), "r"(v[3])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+// RNE + unsigned saturation of two floats into bytes 0 and 1, `upper`'s low half into bytes 2 and 3 (one F2IP)
+__device__ __forceinline__ uint32_t pack2_u8f(float lo, float hi, uint32_t upper) {
+  uint32_t r;
+  const int a = __float2int_rn(hi), b = __float2int_rn(lo);
+  asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(upper));
+  return r;
+}
+// base | (byte `J` of w) << 8: the table address of one packed index (base has a zero byte 1)
+template <int J>
+__device__ __forceinline__ uint32_t tab_addr(uint32_t w, uint32_t base) {
+  return __byte_perm(w, base, 0x7604 | (J << 4));
 }
 
-// CN (8 or 16) consecutive columns of this thread's row.  (Pieces of 16 columns, not 32: the passes keep a piece and
-// its per-element temporaries in registers, and sixteen softmax warps leave 120 registers per thread.)
-template <int CN>
-__device__ __forceinline__ void ld_piece(uint32_t taddr, uint32_t (&v)[16]) {
-  if constexpr (CN == 16) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-        : "r"(taddr)
-        : "memory");
-  } else {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
-                 : "r"(taddr)
-                 : "memory");
-  }
-  tmem_ld_wait();
-}
-
-// pass 1 over one piece: row maximum / minimum of the raw accumulators (monotone in the score code)
-template <int CN, bool kMask>
-__device__ __forceinline__ void minmax_piece(const uint32_t (&v)[16], int cnt, int& mx, int& mn) {
+// Pass 1 over one 16-column piece: raw accumulators -> biased score codes clamp(RNE(acc * mul) + zp, -128, 127) + 128,
+// four to a word, and the row extrema of the raw accumulators (monotone in the code).  cnt < 16: the tail columns
+// are beyond n; their codes are never used.
+template <bool kMask>
+__device__ __forceinline__ void code_piece(const uint32_t (&v)[16], int cnt, float mul, float c0, uint32_t (&w)[4], int& mx, int& mn) {
 #pragma unroll
-  for (int j = 0; j < CN; ++j) {
-    if (!kMask || j < cnt) {
-      mx = max(mx, (int)v[j]);
-      mn = min(mn, (int)v[j]);
+  for (int j = 0; j < 16; j += 4) {
+    const float2 f0 = ffma2(make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), make_float2(mul, mul), make_float2(c0, c0));
+    const float2 f1 = ffma2(make_float2(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])), make_float2(mul, mul), make_float2(c0, c0));
+    w[j >> 2] = pack2_u8f(f0.x, f0.y, pack2_u8f(f1.x, f1.y, 0u));
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      if (!kMask || j + e < cnt) {
+        mx = max(mx, (int)v[j + e]);
+        mn = min(mn, (int)v[j + e]);
+      }
     }
   }
 }
 
-// pass 2 over one piece: exact sum of e(d) over its first `cnt` columns (all CN without kMask)
-template <bool kClamp, int CN, bool kMask>
-__device__ __forceinline__ void sum_piece(const uint32_t (&v)[16], int cnt, const RowConst& rc, uint32_t ke, double (&acc)[4]) {
+// Pass 2 over one piece: exact sum of e(d) over its first `cnt` codes.  bias: (255 - rowmax code) in every byte.
+template <bool kMask>
+__device__ __forceinline__ void sum_piece(const uint32_t (&w)[4], int cnt, uint32_t bias, uint32_t base_e, double (&acc)[4]) {
 #pragma unroll
-  for (int j = 0; j < CN; j += 2) {
-    const float2 f = score_pair<kClamp>(v[j], v[j + 1], rc);
-    const uint32_t e0 = lds32((__float_as_uint(f.x) << 7) + ke);
-    const uint32_t e1 = lds32((__float_as_uint(f.y) << 7) + ke);
-    if (!kMask || j < cnt) acc[(j >> 1) & 3] += __hiloint2double((int)e0, 0);
-    if (!kMask || j + 1 < cnt) acc[((j >> 1) + 2) & 3] += __hiloint2double((int)e1, 0);
+  for (int i = 0; i < 4; ++i) {
+    const uint32_t x = w[i] + bias;            // per byte: 255 - d, no carries (code <= rowmax)
+    const uint32_t e0 = lds32(tab_addr<0>(x, base_e)), e1 = lds32(tab_addr<1>(x, base_e));
+    const uint32_t e2 = lds32(tab_addr<2>(x, base_e)), e3 = lds32(tab_addr<3>(x, base_e));
+    if (!kMask || 4 * i < cnt) acc[0] += __hiloint2double((int)e0, 0);
+    if (!kMask || 4 * i + 1 < cnt) acc[1] += __hiloint2double((int)e1, 0);
+    if (!kMask || 4 * i + 2 < cnt) acc[2] += __hiloint2double((int)e2, 0);
+    if (!kMask || 4 * i + 3 < cnt) acc[3] += __hiloint2double((int)e3, 0);
   }
 }
 
-// pass 3 over one piece: 16-bit probabilities 2^(15-k) of its first `cnt` columns into v (0 beyond, up to column 16),
-// returns the OR of (low-bracket bits ^ high-bracket bits): a set exponent bit means some element sits next to a step
-template <bool kClamp, bool kPeak, int CN, bool kMask>
-__device__ __forceinline__ uint32_t prob_piece(uint32_t (&v)[16], int cnt, const RowConst& rc, uint32_t kr, float fsum,
-                                               float sixth, uint32_t fmax_bits, uint32_t p_top) {
+// One element of pass 3: 2^(15-k) as a 16-bit integer from the bracketed 1 / (3e) (see file header).  The exponent
+// field comes out of a multiply-high (FMA pipe): the ALU pipe, which issues a warp instruction every other cycle, is
+// what bounds this kernel.
+template <bool kPeak>
+__device__ __forceinline__ uint32_t prob_one(uint32_t addr, float fsum, float sixth, uint32_t top_addr, uint32_t p_top, uint32_t& guard) {
+  const float2 r = lds64f(addr);
+  const float2 u = ffma2(make_float2(fsum, fsum), r, make_float2(sixth, sixth));
+  guard = __float_as_uint(u.x) ^ __float_as_uint(u.y);
+  uint32_t p = shr_clamp(0x100000u, __umulhi(__float_as_uint(u.x), 512u));   // >> 23
+  if (kPeak) p = addr == top_addr ? p_top : p;   // the row maximum itself: its exact probability
+  return p;
+}
+// Pass 3 over one piece: the two probability byte planes of its 16 keys (keys >= cnt: 0).  Returns the OR of
+// (low-bracket bits ^ high-bracket bits): a set exponent bit means some element sits next to a step of the code function.
+template <bool kPeak, bool kMask>
+__device__ __forceinline__ uint32_t prob_piece(const uint32_t (&w)[4], int cnt, uint32_t bias, uint32_t base_r, float fsum,
+                                               float sixth, uint32_t p_top, uint32_t (&hi)[4], uint32_t (&lo)[4]) {
   uint32_t guard = 0;
+  const uint32_t top_addr = base_r | 0xff00u;
 #pragma unroll
-  for (int j = 0; j < CN; j += 2) {
-    const float2 f = score_pair<kClamp>(v[j], v[j + 1], rc);
-    const float2 ra = lds64f((__float_as_uint(f.x) << 8) + kr);
-    const float2 rb = lds64f((__float_as_uint(f.y) << 8) + kr);
-    const float2 ua = ffma2(make_float2(fsum, fsum), ra, make_float2(sixth, sixth));
-    const float2 ub = ffma2(make_float2(fsum, fsum), rb, make_float2(sixth, sixth));
-    uint32_t ga = __float_as_uint(ua.x) ^ __float_as_uint(ua.y), gb = __float_as_uint(ub.x) ^ __float_as_uint(ub.y);
-    uint32_t pa = shr_clamp(0x100000u, __float_as_uint(ua.x) >> 23);
-    uint32_t pb = shr_clamp(0x100000u, __float_as_uint(ub.x) >> 23);
-    if (kPeak) {   // the row maximum itself: its exact probability (the irregular first steps of the code function)
-      pa = __float_as_uint(f.x) == fmax_bits ? p_top : pa;
-      pb = __float_as_uint(f.y) == fmax_bits ? p_top : pb;
+  for (int i = 0; i < 4; ++i) {
+    const uint32_t x = w[i] + bias;
+    uint32_t g0, g1, g2, g3;
+    uint32_t p0 = prob_one<kPeak>(tab_addr<0>(x, base_r), fsum, sixth, top_addr, p_top, g0);
+    uint32_t p1 = prob_one<kPeak>(tab_addr<1>(x, base_r), fsum, sixth, top_addr, p_top, g1);
+    uint32_t p2 = prob_one<kPeak>(tab_addr<2>(x, base_r), fsum, sixth, top_addr, p_top, g2);
+    uint32_t p3 = prob_one<kPeak>(tab_addr<3>(x, base_r), fsum, sixth, top_addr, p_top, g3);
+    if (kMask) {   // keys beyond n: probability 0, and their (meaningless) brackets must not trigger the exact path
+      if (4 * i >= cnt) { p0 = 0u; g0 = 0u; }
+      if (4 * i + 1 >= cnt) { p1 = 0u; g1 = 0u; }
+      if (4 * i + 2 >= cnt) { p2 = 0u; g2 = 0u; }
+      if (4 * i + 3 >= cnt) { p3 = 0u; g3 = 0u; }
     }
-    if (kMask) {
-      if (j >= cnt) { pa = 0u; ga = 0u; }
-      if (j + 1 >= cnt) { pb = 0u; gb = 0u; }
-    }
-    guard |= ga | gb;
-    v[j] = pa;
-    v[j + 1] = pb;
+    guard |= (g0 | g1) | (g2 | g3);
+    const uint32_t a01 = p0 | (p1 << 16), a23 = p2 | (p3 << 16);
+    lo[i] = __byte_perm(a01, a23, 0x6420);
+    hi[i] = __byte_perm(a01, a23, 0x7531);
   }
-#pragma unroll
-  for (int j = CN; j < 16; ++j) v[j] = 0u;
   return guard;
 }
 
@@ -297,13 +320,19 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_co
                     const __grid_constant__ CUtensorMap tm_q16, const __grid_constant__ CUtensorMap tm_k,
                     const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_out, const TcArgs a) {
   extern __shared__ uint8_t tc_smem_raw[];
-  TcSmem& s = *reinterpret_cast<TcSmem*>(tc_smem_raw + ((1024u - (smem_u32(tc_smem_raw) & 1023u)) & 1023u));
+  const uint32_t raw_addr = smem_u32(tc_smem_raw);
+  const uint32_t a0 = (raw_addr + 1023u) & ~1023u;
+  uint8_t* const win = tc_smem_raw - raw_addr;          // generic pointer of shared-window address 0
+  uint8_t* const stage_ptr[2] = {win + a0, win + kRegionCAddr};
+  uint8_t* const ostage = win + a0 + kOffOstage;
+  TcTail& s = *reinterpret_cast<TcTail*>(win + kRegionCAddr + kStageBytes);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n = a.n;
   const int ntiles = n > 128 ? 2 : 1;
   const int nmma = max(16, (n + 15) & ~15);          // N of the S MMA
   const int nchunks = (n + 31) >> 5;                 // 32-key chunks = K steps of P V
   const int my_items = ((int)a.items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  if (a0 + kRegionABytes > kTabAddr) __trap();       // static shared memory crept in: the layout above no longer holds
 
   if (warp == kTcProducerWarp && lane == 0) {
     tma_prefetch_desc(&tm_q128); tma_prefetch_desc(&tm_q32); tma_prefetch_desc(&tm_q16);
@@ -327,7 +356,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_co
   const uint32_t tmem_base = s.tmem_base;
 
   if (warp < kTcSoftWarps) {
-    // ---- tables (warps 0-7, 32 entries each) and the initial accumulator bias of this warp's half of its lanes' columns --
+    // ---- table (warps 0-7, 32 entries each) and the initial accumulator bias of this warp's half of its lanes' columns --
     if (warp < 8) {
       const int d = warp * 32 + lane;                 // this lane evaluates entry d ...
       const float e = a.exp_lut[d];
@@ -337,11 +366,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_co
       const float rhi = __fmul_rn(r3, 1.0f + 9.5367431640625e-07f);
       const uint32_t ehi = (uint32_t)__double2hiint((double)e);
       for (int j = 0; j < 32; ++j) {                  // ... and the warp writes each of its entries once per lane replica
-        const int dj = warp * 32 + j;
+        uint8_t* rowp = win + kTabAddr + (uint32_t)(255 - (warp * 32 + j)) * 256u;
         const uint32_t ej = __shfl_sync(0xffffffffu, ehi, j);
         const float lj = __shfl_sync(0xffffffffu, rlo, j), hj = __shfl_sync(0xffffffffu, rhi, j);
-        s.tab_e[(255 - dj) * 32 + lane] = ej;
-        s.tab_r[(255 - dj) * 32 + lane] = make_float2(lj, hj);
+        reinterpret_cast<uint32_t*>(rowp)[lane] = ej;
+        if (lane < 16) reinterpret_cast<float2*>(rowp + 128)[lane] = make_float2(lj, hj);
       }
     }
     const int t = warp >> 3, hf = (warp >> 2) & 1, q = warp & 3;
@@ -360,19 +389,20 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_co
       for (int i = 0; i < my_items; ++i) {
         const int item = blockIdx.x + i * gridDim.x, img = item / a.heads, head = item % a.heads;
         const int st = i & 1;
-        mbar_wait_relaxed(&s.empty[st], ((i >> 1) & 1) ^ 1);
+        uint8_t* const sp = stage_ptr[st];
+        mbar_wait_parked(&s.empty[st], ((i >> 1) & 1) ^ 1);
         mbar_expect_tx(&s.full[st], bytes);
-        tma_load_3d(s.q[st][0], &tm_q128, &s.full[st], head * 64, 0, img);
-        tma_load_3d(s.k[st], &tm_k, &s.full[st], (a.heads + head) * 64, 0, img);
+        tma_load_3d(sp + kOffQ, &tm_q128, &s.full[st], head * 64, 0, img);
+        tma_load_3d(sp + kOffK, &tm_k, &s.full[st], (a.heads + head) * 64, 0, img);
         if (ntiles == 2) {
           // rows 128.. of the second tile, 32 at a time, rotated over the four lane quarters from item to item so
           // that the short tile (69 rows for n = 197) loads every scheduler's warps equally in the long run
           const int rot = i & 3;
-          tma_load_3d(s.q[st][1] + ((0 + rot) & 3) * 2048, &tm_q32, &s.full[st], head * 64, 128, img);
-          tma_load_3d(s.q[st][1] + ((1 + rot) & 3) * 2048, &tm_q32, &s.full[st], head * 64, 160, img);
-          tma_load_3d(s.q[st][1] + ((2 + rot) & 3) * 2048, &tm_q16, &s.full[st], head * 64, 192, img);
+          tma_load_3d(sp + kOffQ + 8192 + ((0 + rot) & 3) * 2048, &tm_q32, &s.full[st], head * 64, 128, img);
+          tma_load_3d(sp + kOffQ + 8192 + ((1 + rot) & 3) * 2048, &tm_q32, &s.full[st], head * 64, 160, img);
+          tma_load_3d(sp + kOffQ + 8192 + ((2 + rot) & 3) * 2048, &tm_q16, &s.full[st], head * 64, 192, img);
         }
-        tma_load_3d(s.v[st], &tm_v, &s.full[st], (2 * a.heads + head) * 64, 0, img);
+        tma_load_3d(sp + kOffV, &tm_v, &s.full[st], (2 * a.heads + head) * 64, 0, img);
       }
     }
   } else if (warp == kTcMmaWarp0 || warp == kTcMmaWarp0 + 1) {
@@ -384,18 +414,19 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_co
       const uint32_t tile = tmem_base + t * kTcTileCols;
       for (int i = 0; i < my_items; ++i) {
         const int st = i & 1;
+        const uint32_t sa = (st ? kRegionCAddr : a0);
         // S of item i: its operands have landed, and the tile's TMEM region was handed back (bias restored)
         mbar_wait_parked(&s.full[st], (i >> 1) & 1);
         if (i > 0) mbar_wait_parked(&s.s_free[t], (i - 1) & 1);
         tc_fence_after_sync();
-        const uint64_t dq = umma_desc_sw64(smem_u32(s.q[st][t])), dk = umma_desc_sw64(smem_u32(s.k[st]));
+        const uint64_t dq = umma_desc_sw64(sa + kOffQ + t * 8192), dk = umma_desc_sw64(sa + kOffK);
         tc_mma_i8(tile, dq, dk, idesc_s, 1u);                 // accumulates onto the 1.5 * 2^23 bias
         tc_mma_i8(tile, dq + 2, dk + 2, idesc_s, 1u);         // second half of the head dimension: +32 bytes
         tc_commit(&s.s_full[t]);
         // P V of item i: all eight warps of the tile have written their probability planes
         mbar_wait_parked(&s.p_ready[t], i & 1);
         tc_fence_after_sync();
-        const uint64_t dv = umma_desc_sw64(smem_u32(s.v[st]));
+        const uint64_t dv = umma_desc_sw64(sa + kOffV);
         for (int ks = 0; ks < nchunks; ++ks) {
           const uint64_t dvk = dv + (uint64_t)(ks * (2048 >> 4));
           tc_mma_i8_ts(tile + kColOhi, tile + kColPhi + 8 * ks, dvk, idesc_pv, (uint32_t)(ks != 0));
@@ -413,10 +444,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_co
     if (t < ntiles) {
       const uint32_t tile = tmem_base + ((uint32_t)(q * 32) << 16) + t * kTcTileCols;
       const float sixth = __fmul_rn(0.16666667f, __uint_as_float((127u - 120u) << 23));
-      const uint32_t tab_e = smem_u32(s.tab_e) + lane * 4, tab_r = smem_u32(s.tab_r) + lane * 8;
+      const uint32_t base_e = kTabAddr + lane * 4, base_r = kTabAddr + 128 + (lane & 15) * 8;
       const int sh = a.out_shift;
       const int half_m1 = (1 << (sh - 1)) - 1 + (a.out_zp << sh);   // RNE shift with the zero point folded in
-      uint8_t* const ost = s.ostage[pair];
+      const int inv_sh = sh >= 2 ? (1 << (32 - sh)) : 0;
+      uint8_t* const ost = ostage + pair * 2048;
 
       for (int i = 0; i < my_items; ++i) {
         const int item = blockIdx.x + i * gridDim.x, img = item / a.heads, head = item % a.heads;
@@ -425,13 +457,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_co
         const int row = row0 + lane;
         const bool warp_on = row0 < n && (t == 0 || seg < 3);
         const bool valid = warp_on && row < n;
-        // lanes without a row (beyond n, or staging rows no load wrote) see a constant score row: their table
-        // addresses stay inside the tables whatever the tensor core left in their TMEM lanes
-        RowConst rc;
-        rc.mul = valid ? a.score_mul : 0.f;
-        rc.c0 = valid ? a.c0 : __uint_as_float(kMagic + 128u);
-        rc.flo = __uint_as_float(kMagic);
-        rc.fhi = __uint_as_float(kMagic + 255u);
+        // lanes without a row (beyond n, or staging rows no load wrote) see a constant score row
+        const float mul = valid ? a.score_mul : 0.f;
+        const float c0 = valid ? a.c0 : 128.f;
         auto stamp = [&](int phase) {
           if (a.timeline != nullptr && blockIdx.x == 0 && lane == 0 && i < 12)
             a.timeline[(i * 16 + warp) * 8 + phase] = clock64();
@@ -441,46 +469,55 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_co
         tc_fence_after_sync();
         stamp(1);
         if (warp_on) {
-          uint32_t v[16];
-          // ---- pass 1: row maximum / minimum of the raw accumulators, this warp's chunks, then both halves ----
+          // ---- pass 1 (the only read of the raw scores): codes, four to a word, kept in registers for both later passes;
+          // row extrema of this warp's chunks, then of both halves ----
+          uint32_t cw[4][2][4];                       // [own chunk][16-key piece][word]
           int mx = (int)0x80000000, mn = 0x7fffffff;
-          for (int c = hf; c < nchunks; c += 2) {
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              const int col = 32 * c + 16 * h, cnt = n - col;
-              if (cnt >= 16) { ld_piece<16>(tile + col, v); minmax_piece<16, false>(v, 16, mx, mn); }
-              else if (cnt > 8) { ld_piece<16>(tile + col, v); minmax_piece<16, true>(v, cnt, mx, mn); }
-              else if (cnt > 0) { ld_piece<8>(tile + col, v); minmax_piece<8, true>(v, cnt, mx, mn); }
+          for (int it = 0; it < 4; ++it) {
+            const int c = hf + 2 * it;
+            if (c < nchunks) {
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                const int col = 32 * c + 16 * h, cnt = n - col;
+                if (cnt > 0) {
+                  uint32_t v[16];
+                  tmem_ld_32x16(tile + col, v);
+                  tmem_ld_wait();
+                  if (cnt >= 16) code_piece<false>(v, 16, mul, c0, cw[it][h], mx, mn);
+                  else code_piece<true>(v, cnt, mul, c0, cw[it][h], mx, mn);
+                }
+              }
             }
           }
           s.x_minmax[pair][hf][lane] = make_int2(mx, mn);
-          pair_barrier(pair);
+          pair_barrier(pair);           // ... which also tells that the partner is done reading raw scores: P may be written
           {
             const int2 o = s.x_minmax[pair][hf ^ 1][lane];
             mx = max(mx, o.x);
             mn = min(mn, o.y);
           }
           stamp(2);
-          const int gmax = (int)(__float_as_uint(__fmaf_rn(__int_as_float(mx), rc.mul, rc.c0)) - kMagic);
-          const int gmin = (int)(__float_as_uint(__fmaf_rn(__int_as_float(mn), rc.mul, rc.c0)) - kMagic);
-          const bool clampw = __any_sync(0xffffffffu, gmax > 255 || gmin < 0);
-          const int cmaxb = min(max(gmax, 0), 255);                 // biased code of the row maximum
-          const uint32_t fmax_bits = kMagic + (uint32_t)cmaxb;
-          const uint32_t ke = tab_e + (uint32_t)(255 - cmaxb) * 128u - (kMagic << 7);
-          const uint32_t kr = tab_r + (uint32_t)(255 - cmaxb) * 256u - (kMagic << 8);
+          // biased code of the row maximum (RNE and the clamp are monotone: it is the code of the largest accumulator)
+          int cmaxb;
+          {
+            const float fm = __fmaf_rn(__int_as_float(mx), mul, c0);
+            asm("cvt.rni.sat.u8.f32 %0, %1;" : "=r"(cmaxb) : "f"(fm));
+          }
+          const uint32_t bias = (uint32_t)(255 - cmaxb) * 0x01010101u;
 
           // ---- pass 2: exact row sum of the integer exp ----
           double acc[4] = {0.0, 0.0, 0.0, 0.0};
-          for (int c = hf; c < nchunks; c += 2) {
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              const int col = 32 * c + 16 * h, cnt = n - col;
-              if (cnt >= 16) {
-                ld_piece<16>(tile + col, v);
-                if (clampw) sum_piece<true, 16, false>(v, 16, rc, ke, acc);
-                else sum_piece<false, 16, false>(v, 16, rc, ke, acc);
-              } else if (cnt > 8) { ld_piece<16>(tile + col, v); sum_piece<true, 16, true>(v, cnt, rc, ke, acc); }
-              else if (cnt > 0) { ld_piece<8>(tile + col, v); sum_piece<true, 8, true>(v, cnt, rc, ke, acc); }
+          for (int it = 0; it < 4; ++it) {
+            const int c = hf + 2 * it;
+            if (c < nchunks) {
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                const int cnt = n - (32 * c + 16 * h);
+                if (cnt >= 16) sum_piece<false>(cw[it][h], 16, bias, base_e, acc);
+                else if (cnt > 0) sum_piece<true>(cw[it][h], cnt, bias, base_e, acc);
+              }
             }
           }
           const double part = (acc[0] + acc[1]) + (acc[2] + acc[3]);     // integers < 2^53: exact in any order
@@ -496,65 +533,60 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_co
           const uint32_t p_top = k_top >= 16 ? 0u : (0x8000u >> k_top);
           const bool peakw = __any_sync(0xffffffffu, k_top < 2);
 
-          // ---- pass 3: probabilities 2^(15-k) as two byte planes, written back to TMEM as the A operand of P V ----
-          // The probability planes of chunk c go to columns 8c.. (high) and 208 + 8c.. / 56 + 8(c - 4).. (low): score
-          // columns of chunks 0, 1 and 2.  Chunks 0 / 2 are read by the even warp of the pair, chunk 1 by the odd one, so
-          // a pair barrier after each warp's first and second chunk load keeps every write behind the reads of BOTH warps
-          // (P(1), P(3) -> chunk 0 and P(4), P(6) -> chunk 1 after barrier one; P(5) -> chunk 2 after barrier two).
-#pragma unroll 1
+          // ---- pass 3: probabilities 2^(15-k) as two byte planes, written to TMEM as the A operand of P V: chunk c to
+          // columns 8c.. (high) and 208 + 8c.. / 56 + 8(c - 4).. (low) - raw score columns nobody reads any more ----
+#pragma unroll
           for (int it = 0; it < 4; ++it) {
             const int c = hf + 2 * it;
-            if (c >= nchunks) {
-              if (it < 2) pair_barrier(pair);
-              continue;
-            }
+            if (c >= nchunks) continue;
             uint32_t hi[8], lo[8];                    // the chunk's two planes: words 0-3 keys 0-15, words 4-7 keys 16-31
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-              const int col = 32 * c + 16 * h, cnt = min(n - col, 16);
-              if (cnt >= 16 || cnt > 8) ld_piece<16>(tile + col, v);
-              else if (cnt > 0) ld_piece<8>(tile + col, v);
-              if (h == 1 && it < 2) pair_barrier(pair);      // both warps hold their whole chunk: P may now be written
+              const int cnt = n - (32 * c + 16 * h);
+              uint32_t (&w)[4] = cw[it][h];
+              uint32_t (&ph)[4] = *reinterpret_cast<uint32_t(*)[4]>(&hi[4 * h]);
+              uint32_t (&pl)[4] = *reinterpret_cast<uint32_t(*)[4]>(&lo[4 * h]);
               if (cnt <= 0) {
 #pragma unroll
-                for (int w = 0; w < 4; ++w) hi[4 * h + w] = lo[4 * h + w] = 0u;
+                for (int x = 0; x < 4; ++x) ph[x] = pl[x] = 0u;
                 continue;
               }
               uint32_t guard;
-              if (cnt >= 16) {
-                if (clampw) guard = peakw ? prob_piece<true, true, 16, false>(v, 16, rc, kr, fsum_s, sixth, fmax_bits, p_top)
-                                          : prob_piece<true, false, 16, false>(v, 16, rc, kr, fsum_s, sixth, fmax_bits, p_top);
-                else guard = peakw ? prob_piece<false, true, 16, false>(v, 16, rc, kr, fsum_s, sixth, fmax_bits, p_top)
-                                   : prob_piece<false, false, 16, false>(v, 16, rc, kr, fsum_s, sixth, fmax_bits, p_top);
-              } else if (cnt > 8) {
-                guard = prob_piece<true, true, 16, true>(v, cnt, rc, kr, fsum_s, sixth, fmax_bits, p_top);
-              } else {
-                guard = prob_piece<true, true, 8, true>(v, cnt, rc, kr, fsum_s, sixth, fmax_bits, p_top);
-              }
+              if (cnt >= 16) guard = peakw ? prob_piece<true, false>(w, 16, bias, base_r, fsum_s, sixth, p_top, ph, pl)
+                                           : prob_piece<false, false>(w, 16, bias, base_r, fsum_s, sixth, p_top, ph, pl);
+              else guard = prob_piece<true, true>(w, cnt, bias, base_r, fsum_s, sixth, p_top, ph, pl);
               const bool redo = __any_sync(0xffffffffu, (guard & 0x7f800000u) != 0u);
               if (redo || kDump) {
-                // redo (rare): some element within 2^-20 of a step of the code function: the whole piece again with the
-                // exact IEEE-division formula.  The raw scores are still in TMEM (P is written behind the read position).
-                uint32_t r2[16];
-                ld_piece<16>(tile + col, r2);
+                // redo (rare): some element within 2^-20 of a step of the code function: all elements of the piece again
+                // with the exact IEEE-division formula
+                const int col = 32 * c + 16 * h;
                 int8_t* dsc = kDump ? a.dump_scores + ((int64_t)item * n + row) * n + col : nullptr;
                 uint8_t* dsm = kDump ? a.dump_softmax + ((int64_t)item * n + row) * n + col : nullptr;
+#pragma unroll 1
+                for (int x = 0; x < 4; ++x) {
+                  uint32_t p4[4];
+                  const uint32_t wx = x == 0 ? w[0] : (x == 1 ? w[1] : (x == 2 ? w[2] : w[3]));
+                  const uint32_t px_l = x == 0 ? pl[0] : (x == 1 ? pl[1] : (x == 2 ? pl[2] : pl[3]));
+                  const uint32_t px_h = x == 0 ? ph[0] : (x == 1 ? ph[1] : (x == 2 ? ph[2] : ph[3]));
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                  const float f = fminf(fmaxf(__fmaf_rn(__uint_as_float(r2[j]), rc.mul, rc.c0), rc.flo), rc.fhi);
-                  const int g = (int)(__float_as_uint(f) - kMagic);
-                  if (redo) v[j] = j < cnt ? tc_exact_prob16(fsum, s.lut[cmaxb - g]) : 0u;
-                  if (kDump && valid && j < cnt) {
-                    dsc[j] = (int8_t)(g - 128);
-                    dsm[j] = (uint8_t)(v[j] ? __clz(v[j]) - 16 : 16);
+                  for (int e = 0; e < 4; ++e) {
+                    const int g = (int)((wx >> (8 * e)) & 0xffu);
+                    const int j = 4 * x + e;
+                    if (redo) p4[e] = j < cnt ? tc_exact_prob16(fsum, s.lut[cmaxb - min(g, cmaxb)]) : 0u;
+                    else p4[e] = ((px_l >> (8 * e)) & 0xffu) | (((px_h >> (8 * e)) & 0xffu) << 8);
+                    if (kDump && valid && j < cnt) {
+                      dsc[j] = (int8_t)(g - 128);
+                      dsm[j] = (uint8_t)(p4[e] ? __clz(p4[e]) - 16 : 16);
+                    }
+                  }
+                  if (redo) {
+                    const uint32_t a01 = p4[0] | (p4[1] << 16), a23 = p4[2] | (p4[3] << 16);
+                    const uint32_t nl = __byte_perm(a01, a23, 0x6420), nh = __byte_perm(a01, a23, 0x7531);
+#pragma unroll
+                    for (int y = 0; y < 4; ++y)
+                      if (y == x) { pl[y] = nl; ph[y] = nh; }
                   }
                 }
-              }
-#pragma unroll
-              for (int w = 0; w < 4; ++w) {
-                const uint32_t a01 = v[4 * w] | (v[4 * w + 1] << 16), a23 = v[4 * w + 2] | (v[4 * w + 3] << 16);
-                lo[4 * h + w] = __byte_perm(a01, a23, 0x6420);
-                hi[4 * h + w] = __byte_perm(a01, a23, 0x7531);
               }
             }
             tmem_st_32x8(tile + kColPhi + 8 * c, hi);
@@ -574,28 +606,29 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_co
         if (warp_on) {
           if (hf == 0 && lane == 0) tma_store_wait_read();   // the previous item's store has finished reading the staging tile
           pair_barrier(pair);
-          {
-            uint32_t oh[32], ol[32];                  // this warp's 32 of the 64 head channels
-            tmem_ld_32x32(tile + kColOhi + 32 * hf, oh);
-            tmem_ld_32x32(tile + kColOlo + 32 * hf, ol);
-            tmem_ld_wait();
-            uint32_t w8[8];
 #pragma unroll
-            for (int w = 0; w < 8; ++w) {
+          for (int ck = 0; ck < 2; ++ck) {            // this warp's 32 of the 64 head channels, 16 at a time
+            uint32_t oh[16], ol[16];
+            tmem_ld_32x16(tile + kColOhi + 32 * hf + 16 * ck, oh);
+            tmem_ld_32x16(tile + kColOlo + 32 * hf + 16 * ck, ol);
+            tmem_ld_wait();
+            uint32_t w8[4];
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
               int qv[4];
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
-                const int acc2 = ((int)oh[4 * w + e] << 8) + (int)ol[4 * w + e];
-                qv[e] = (acc2 + half_m1 + ((acc2 >> sh) & 1)) >> sh;
+                // (hi << 8) + lo, then RNE(. / 2^sh) + zp = (x + 2^(sh-1) - 1 + parity(x >> sh) + (zp << sh)) >> sh; the
+                // two shifts are multiply-highs by 2^(32-sh) (FMA pipe; sh >= 2)
+                const int acc2 = (int)oh[4 * w + e] * 256 + (int)ol[4 * w + e];
+                qv[e] = sh >= 2 ? __mulhi(acc2 + half_m1 + (__mulhi(acc2, inv_sh) & 1), inv_sh)
+                                : (acc2 + half_m1 + ((acc2 >> sh) & 1)) >> sh;
               }
               w8[w] = pack4_s8(qv[0], qv[1], qv[2], qv[3]);
             }
             // row `lane` of the 32 x 64-byte staging tile, 16-byte chunks XOR-swizzled by (row >> 1) & 3 (SWIZZLE_64B)
-#pragma unroll
-            for (int ck = 0; ck < 2; ++ck) {
-              const int chunk = (2 * hf + ck) ^ ((lane >> 1) & 3);
-              *reinterpret_cast<uint4*>(ost + lane * 64 + chunk * 16) = make_uint4(w8[4 * ck], w8[4 * ck + 1], w8[4 * ck + 2], w8[4 * ck + 3]);
-            }
+            const int chunk = (2 * hf + ck) ^ ((lane >> 1) & 3);
+            *reinterpret_cast<uint4*>(ost + lane * 64 + chunk * 16) = make_uint4(w8[0], w8[1], w8[2], w8[3]);
           }
           fence_proxy_async_smem();
           pair_barrier(pair);
@@ -661,7 +694,7 @@ static int make_tmap_tokens(CUtensorMap* map, const void* ptr, int b, int n, int
   return P2V_OK;
 }
 
-constexpr int kTcSmemBytes = (int)sizeof(TcSmem) + 1024;
+constexpr int kTcSmemBytes = (int)kTcSmemEnd;   // as if dynamic shared memory started at window address 0
 static long long* g_tc_timeline = nullptr;
 
 int attention_tc_configure() {
@@ -676,7 +709,8 @@ bool attention_tc_applicable(const int8_t* qkv, const int8_t* out, int b, int n,
   if (n > kTcMaxN || p->in_zp != 0.f || p->softmax_levels != 16) return false;
   if (p->lut_sig_bits <= 0 || p->lut_sig_bits > 21) return false;
   int ex = 0;
-  if (!(p->score_mul > 0.f) || frexpf(p->score_mul, &ex) != 0.5f || ex > 1 || ex < -20) return false;
+  // mul = 2^-s, 0 <= s <= 15: acc * mul + zp + 128 (|acc| < 2^20) is then exact in fp32, so the pack rounds once
+  if (!(p->score_mul > 0.f) || frexpf(p->score_mul, &ex) != 0.5f || ex > 1 || ex < -14) return false;
   if (p->score_zp != (float)(int)p->score_zp || fabsf(p->score_zp) > 128.f) return false;
   int ex2 = 0;
   if (!(p->out_mul > 0) || frexp(p->out_mul, &ex2) != 0.5 || ex2 > 0 || ex2 < -29) return false;
@@ -699,8 +733,8 @@ int attention_tc_launch(const int8_t* qkv, int8_t* out, int b, int n, int heads,
   TcArgs a;
   a.n = n; a.heads = heads; a.items = b * heads;
   a.score_mul = p->score_mul;
-  // 1.5 * 2^23 * (1 - mul) + zp + 128: exact in fp32 for mul = 2^-s, s <= 20 (checked by attention_tc_applicable)
-  a.c0 = (float)(12582912.0 * (1.0 - (double)p->score_mul) + (double)p->score_zp + 128.0);
+  // zp + 128 - 1.5 * 2^23 * mul: exact in fp32 for mul = 2^-s, s <= 20 (checked by attention_tc_applicable)
+  a.c0 = (float)((double)p->score_zp + 128.0 - 12582912.0 * (double)p->score_mul);
   int ex = 0;
   frexp(p->out_mul, &ex);
   a.out_shift = 1 - ex;
