@@ -71,6 +71,7 @@ SYMBOLS = {
     'p2v_layernorm_int': (C.c_int, [_vp, C.c_int64, _vp, _vp, C.c_int, C.c_int, C.POINTER(LayerNorm), _vp]),
     'p2v_attention_int': (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.POINTER(Attention), _vp]),
     'p2v_attention_tc_set_timeline': (C.c_int, [_vp]),
+    'p2v_attention_tc_set_skew': (C.c_int, [C.c_int]),
     'p2v_fake_quant_f32': (C.c_int, [_vp, _vp, _vp, C.c_int64, C.c_int, C.c_int64, _vp, _vp, C.c_int, C.c_int, _vp]),
     'p2v_layernorm_int_f32': (C.c_int, [_vp, _vp, C.c_int64, C.c_int, _vp, _vp, C.c_float, _vp, _vp, _vp, _vp, _vp]),
     'p2v_softmax_log_int_f32': (C.c_int, [_vp, _vp, _vp, C.c_int64, C.c_int, C.c_float, C.c_float, C.c_float,

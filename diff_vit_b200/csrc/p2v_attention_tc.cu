@@ -92,6 +92,8 @@ struct TcArgs {
   int8_t* dump_scores;
   uint8_t* dump_softmax;
   long long* timeline;       // test hook (p2v_attention_tc_set_timeline): per-phase clock64 stamps of CTA 0
+  int skew;                  // cycles by which tile pipeline 1 starts late: its TMEM-bound pass 1 then overlaps the
+                             // ALU-bound pass 3 of pipeline 0 instead of competing with the other pipeline's same pass
 };
 
 // ---- PTX wrappers this kernel adds to p2v_common.cuh -------------------------------------------------------------
@@ -154,6 +156,13 @@ __device__ __forceinline__ void tmem_fill_32x8(uint32_t taddr, uint32_t c) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(taddr), "r"(c) : "memory");
 }
 __device__ __forceinline__ void pair_barrier(int pair) { asm volatile("bar.sync %0, 64;" ::"r"(1 + pair) : "memory"); }
+// Hand-over from a tile's MMA warp to its eight softmax warps: the MMA warp watches the mbarrier its tcgen05.commit
+// arrives on, then releases the softmax warps through a named barrier, on which they block in hardware.  (Waiting on
+// the mbarrier directly, every softmax warp came back from try_wait every few hundred cycles: ncu counted a fifth of
+// all issued instructions in those loops, on the schedulers that also run the working warps.)
+constexpr int kNbS = 9, kNbO = 11;      // + tile; ids 1..8 are the pair barriers
+__device__ __forceinline__ void tile_barrier_wait(int id) { asm volatile("bar.sync %0, 288;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ void tile_barrier_release(int id) { asm volatile("bar.arrive %0, 288;" ::"r"(id) : "memory"); }
 __device__ __forceinline__ void tmem_ld_32x32_nowait(uint32_t taddr, uint32_t (&v)[32]) { tmem_ld_32x32(taddr, v); }
 
 // Shared-memory matrix descriptors for tiles whose rows are 64 bytes with the 64-byte swizzle (what a TMA box of
@@ -390,7 +399,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_co
         const int item = blockIdx.x + i * gridDim.x, img = item / a.heads, head = item % a.heads;
         const int st = i & 1;
         uint8_t* const sp = stage_ptr[st];
-        mbar_wait_parked(&s.empty[st], ((i >> 1) & 1) ^ 1);
+        while (!mbar_test(&s.empty[st], ((i >> 1) & 1) ^ 1)) __nanosleep(1000);   // a whole item of slack
         mbar_expect_tx(&s.full[st], bytes);
         tma_load_3d(sp + kOffQ, &tm_q128, &s.full[st], head * 64, 0, img);
         tma_load_3d(sp + kOffK, &tm_k, &s.full[st], (a.heads + head) * 64, 0, img);
@@ -408,33 +417,47 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_co
   } else if (warp == kTcMmaWarp0 || warp == kTcMmaWarp0 + 1) {
     // ---- MMA issuers: one warp (one elected lane) per tile pipeline ----------------------------------------------------
     const int t = warp - kTcMmaWarp0;
-    if (t < ntiles && elect_one()) {
+    if (t < ntiles) {
       const uint32_t idesc_s = umma_idesc_i8x(128, (uint32_t)nmma, true, true, false);
       const uint32_t idesc_pv = umma_idesc_i8x(128, 64, false, true, true);
       const uint32_t tile = tmem_base + t * kTcTileCols;
       for (int i = 0; i < my_items; ++i) {
         const int st = i & 1;
         const uint32_t sa = (st ? kRegionCAddr : a0);
-        // S of item i: its operands have landed, and the tile's TMEM region was handed back (bias restored)
-        mbar_wait_parked(&s.full[st], (i >> 1) & 1);
-        if (i > 0) mbar_wait_parked(&s.s_free[t], (i - 1) & 1);
-        tc_fence_after_sync();
-        const uint64_t dq = umma_desc_sw64(sa + kOffQ + t * 8192), dk = umma_desc_sw64(sa + kOffK);
-        tc_mma_i8(tile, dq, dk, idesc_s, 1u);                 // accumulates onto the 1.5 * 2^23 bias
-        tc_mma_i8(tile, dq + 2, dk + 2, idesc_s, 1u);         // second half of the head dimension: +32 bytes
-        tc_commit(&s.s_full[t]);
-        // P V of item i: all eight warps of the tile have written their probability planes
-        mbar_wait_parked(&s.p_ready[t], i & 1);
-        tc_fence_after_sync();
-        const uint64_t dv = umma_desc_sw64(sa + kOffV);
-        for (int ks = 0; ks < nchunks; ++ks) {
-          const uint64_t dvk = dv + (uint64_t)(ks * (2048 >> 4));
-          tc_mma_i8_ts(tile + kColOhi, tile + kColPhi + 8 * ks, dvk, idesc_pv, (uint32_t)(ks != 0));
-          tc_mma_i8_ts(tile + kColOlo, tile + (ks < 4 ? kColPlo0 + 8 * ks : kColPlo1 + 8 * (ks - 4)), dvk, idesc_pv,
-                       (uint32_t)(ks != 0));
+        if (lane == 0) {
+          // S of item i: its operands have landed, and the tile's TMEM region was handed back (bias restored)
+          mbar_wait(&s.full[st], (i >> 1) & 1);
+          if (i > 0) mbar_wait(&s.s_free[t], (i - 1) & 1);
+          tc_fence_after_sync();
+          const uint64_t dq = umma_desc_sw64(sa + kOffQ + t * 8192), dk = umma_desc_sw64(sa + kOffK);
+          tc_mma_i8(tile, dq, dk, idesc_s, 1u);                 // accumulates onto the 1.5 * 2^23 bias
+          tc_mma_i8(tile, dq + 2, dk + 2, idesc_s, 1u);         // second half of the head dimension: +32 bytes
+          tc_commit(&s.s_full[t]);
+          mbar_wait(&s.s_full[t], i & 1);
+          tc_fence_after_sync();
+          tc_fence_before_sync();
         }
-        tc_commit(&s.o_full[t]);
-        tc_commit(&s.empty[st]);      // this pipeline is done with the stage once these MMAs retire
+        __syncwarp();
+        tile_barrier_release(kNbS + t);
+        if (lane == 0) {
+          // P V of item i: all eight warps of the tile have written their probability planes
+          mbar_wait(&s.p_ready[t], i & 1);
+          tc_fence_after_sync();
+          const uint64_t dv = umma_desc_sw64(sa + kOffV);
+          for (int ks = 0; ks < nchunks; ++ks) {
+            const uint64_t dvk = dv + (uint64_t)(ks * (2048 >> 4));
+            tc_mma_i8_ts(tile + kColOhi, tile + kColPhi + 8 * ks, dvk, idesc_pv, (uint32_t)(ks != 0));
+            tc_mma_i8_ts(tile + kColOlo, tile + (ks < 4 ? kColPlo0 + 8 * ks : kColPlo1 + 8 * (ks - 4)), dvk, idesc_pv,
+                         (uint32_t)(ks != 0));
+          }
+          tc_commit(&s.o_full[t]);
+          tc_commit(&s.empty[st]);      // this pipeline is done with the stage once these MMAs retire
+          mbar_wait(&s.o_full[t], i & 1);
+          tc_fence_after_sync();
+          tc_fence_before_sync();
+        }
+        __syncwarp();
+        tile_barrier_release(kNbO + t);
       }
     }
   } else if (warp < kTcSoftWarps) {
@@ -465,7 +488,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_co
             a.timeline[(i * 16 + warp) * 8 + phase] = clock64();
         };
         stamp(0);
-        mbar_wait_parked(&s.s_full[t], i & 1);
+        if (i == 0 && t == 1 && a.skew > 0) {   // start the second tile pipeline out of phase with the first (see TcArgs)
+          const long long t0 = clock64();
+          while (clock64() - t0 < a.skew) __nanosleep(256);
+        }
+        tile_barrier_wait(kNbS + t);
         tc_fence_after_sync();
         stamp(1);
         if (warp_on) {
@@ -473,6 +500,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_co
           // row extrema of this warp's chunks, then of both halves ----
           uint32_t cw[4][2][4];                       // [own chunk][16-key piece][word]
           int mx = (int)0x80000000, mn = 0x7fffffff;
+          // (fully unrolled over the warp's four chunks: the register array needs compile-time indices.  Keeping the loops
+          // rolled by rotating the array instead was measured: the 32 moves per chunk cost more than the instruction
+          // fetch stalls of the larger code.)
 #pragma unroll
           for (int it = 0; it < 4; ++it) {
             const int c = hf + 2 * it;
@@ -600,7 +630,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_co
         stamp(4);
 
         // ---- epilogue: O = (O_hi << 8) + O_lo -> RNE shift to the qact2 grid -> int8, out through a TMA store ----
-        mbar_wait_parked(&s.o_full[t], i & 1);
+        tile_barrier_wait(kNbO + t);
         tc_fence_after_sync();
         stamp(5);
         if (warp_on) {
@@ -696,6 +726,7 @@ static int make_tmap_tokens(CUtensorMap* map, const void* ptr, int b, int n, int
 
 constexpr int kTcSmemBytes = (int)kTcSmemEnd;   // as if dynamic shared memory started at window address 0
 static long long* g_tc_timeline = nullptr;
+static int g_tc_skew = 0;
 
 int attention_tc_configure() {
   P2V_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
@@ -743,6 +774,7 @@ int attention_tc_launch(const int8_t* qkv, int8_t* out, int b, int n, int heads,
   a.dump_scores = p->dump_scores;
   a.dump_softmax = p->dump_softmax;
   a.timeline = g_tc_timeline;
+  a.skew = g_tc_skew;
   const int grid = a.items < kNumSMs ? a.items : kNumSMs;
   if (p->dump_scores != nullptr)
     attention_tc_kernel<true><<<grid, kTcThreads, kTcSmemBytes, st>>>(tq128, tq32, tq16, tk, tv, to, a);
@@ -759,5 +791,9 @@ int attention_tc_launch(const int8_t* qkv, int8_t* out, int b, int n, int heads,
 // epilogue arithmetic, 7 after the accumulator bias was restored); NULL switches it off.
 extern "C" int p2v_attention_tc_set_timeline(long long* buf) {
   p2v::g_tc_timeline = buf;
+  return P2V_OK;
+}
+extern "C" int p2v_attention_tc_set_skew(int cycles) {
+  p2v::g_tc_skew = cycles;
   return P2V_OK;
 }

@@ -146,6 +146,8 @@ int p2v_attention_int(const int8_t* qkv, int8_t* out, int b, int n, int heads, c
 /* Test hook of the tcgen05 attention kernel: buf (device, 12 x 8 x 8 int64, or NULL = off) receives clock64 stamps of
  * CTA 0's softmax warps, [item][warp][phase] (tools/att_timeline.py prints them). */
 int p2v_attention_tc_set_timeline(long long* buf);
+/* Tuning hook: SM cycles by which the second row-tile pipeline of the tcgen05 attention kernel starts late. */
+int p2v_attention_tc_set_skew(int cycles);
 
 /* Standalone QAct on fp32 data (module-level use): out = (clamp(RNE(x/s + zp)) - zp) * s with a scale
  * per channel of the innermost (inner == 1) or of an outer dimension.  models/ptq/layers.py:207-220. */

@@ -38,6 +38,8 @@ def time_both(qkv, b, n, heads, att, label):
 
 
 def main():
+    if os.environ.get('P2V_ATT_SKEW'):
+        _cabi.check(_cabi.lib().p2v_attention_tc_set_skew(int(os.environ['P2V_ATT_SKEW'])))
     b = int(sys.argv[1]) if len(sys.argv) > 1 else 256
     mode = sys.argv[2] if len(sys.argv) > 2 else '60'
     n, heads = 197, 6
