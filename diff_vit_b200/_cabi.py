@@ -125,6 +125,7 @@ def ptr(t):
     return None if t is None else t.data_ptr()
 
 
-def current_stream():
+def current_stream(device=None):
+    """Raw handle of torch's current stream on `device` (default: the current device)."""
     import torch
-    return torch.cuda.current_stream().cuda_stream
+    return torch.cuda.current_stream(device).cuda_stream

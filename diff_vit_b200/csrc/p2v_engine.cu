@@ -44,6 +44,21 @@ struct DumpEntry {
 
 using namespace p2v;
 
+// Makes `device` current for the lifetime of the object and restores the caller's device afterwards: the library must
+// not change the device a torch program believes to be current.
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int device) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != device) ok = cudaSetDevice(device) == cudaSuccess;
+  }
+  ~DeviceGuard() {
+    int cur = -1;
+    if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
+  }
+};
+
 struct p2v_vit {
   p2v_vit_desc d;
   std::vector<p2v_block_desc> blocks;
@@ -260,7 +275,8 @@ extern "C" int p2v_vit_create(const p2v_vit_desc* desc, int device, p2v_vit** ou
               "p2v_vit_create: img_size=%d patch_size=%d unsupported", desc->img_size, desc->patch_size);
   int rc = p2v_check_device(device);
   if (rc) return rc;
-  P2V_CHECK_CUDA(cudaSetDevice(device));
+  DeviceGuard guard(device);
+  P2V_REQUIRE(guard.ok, "p2v_vit_create: cannot make device %d current", device);
   if ((rc = gemm_configure())) return rc;
   if ((rc = attention_configure_once())) return rc;
   p2v_vit* h = new p2v_vit();
@@ -326,6 +342,8 @@ extern "C" int p2v_vit_forward(p2v_vit* h, const float* x, float* logits, int8_t
   P2V_REQUIRE(h && x && logits && workspace, "p2v_vit_forward: null pointer");
   P2V_REQUIRE(b > 0, "p2v_vit_forward: batch must be positive");
   cudaStream_t st = (cudaStream_t)stream;
+  DeviceGuard guard(h->device);      // the handle's device, whatever is current in the calling thread
+  P2V_REQUIRE(guard.ok, "p2v_vit_forward: cannot make device %d current", h->device);
   P2V_TRY(bind(h, b, workspace));
   if (dump != nullptr) {
     build_dump_layout(h, b);

@@ -72,7 +72,7 @@ class _BoundPlan:
             n, k = lp.w4.shape[0], lp.w4.shape[1] * 2
             codes = torch.empty((n, k), dtype=torch.int8, device=self.device)
             _cabi.check(_cabi.lib().p2v_unpack_int4(packed.data_ptr(), codes.data_ptr(), packed.numel(),
-                                                    _cabi.current_stream()))
+                                                    _cabi.current_stream(self.device)))
             torch.cuda.current_stream(self.device).synchronize()
             self.keep.append(codes)
             d.w = codes.data_ptr()
@@ -189,7 +189,7 @@ class IntegerEngine:
         b = x.shape[0]
         _, ws, logits, codes = bp.buffers(b, slot)
         _cabi.check(_cabi.lib().p2v_vit_forward(bp.handle, x.data_ptr(), logits.data_ptr(), codes.data_ptr(), b, ws,
-                                                None, 1 if use_graph else 0, _cabi.current_stream()))
+                                                None, 1 if use_graph else 0, _cabi.current_stream(self.device)))
         self._last_input = x  # keep the (possibly re-laid-out) input alive until the stream consumed it
         return logits
 
@@ -211,7 +211,7 @@ class IntegerEngine:
         nbytes = lib.p2v_vit_dump_bytes(bp.handle, b)
         dump = torch.zeros(nbytes, dtype=torch.uint8, device=self.device)
         _cabi.check(lib.p2v_vit_forward(bp.handle, x.data_ptr(), logits.data_ptr(), codes.data_ptr(), b, ws,
-                                        dump.data_ptr(), 0, _cabi.current_stream()))
+                                        dump.data_ptr(), 0, _cabi.current_stream(self.device)))
         torch.cuda.synchronize(self.device)
         host = dump.cpu().numpy()
         out = {}
@@ -277,5 +277,5 @@ class IntegerEngine:
             bp._buffers[key] = torch.empty(x_host.shape, dtype=torch.float32, device=self.device)
         xdev = bp._buffers[key]
         _cabi.check(_cabi.lib().p2v_vit_forward_host(bp.handle, x_host.data_ptr(), logits_host.data_ptr(), b, ws,
-                                                     xdev.data_ptr(), logits.data_ptr(), _cabi.current_stream()))
+                                                     xdev.data_ptr(), logits.data_ptr(), _cabi.current_stream(self.device)))
         return logits_host

@@ -196,7 +196,21 @@ class VisionTransformer(nn.Module):
         self.apply(self._init_weights)
         self._engine = None
         self._submodules = None
+        self._int_active = False  # model_quant() arms the fused integer engine, model_dequant() disarms it
         self.per_module = False   # True: run every Q-module's own forward even when the fused engine could
+        # a loaded checkpoint invalidates the plan the engine extracted from the old parameters
+        self.register_load_state_dict_post_hook(lambda module, incompatible: module._drop_engine())
+
+    def _drop_engine(self):
+        """The engine's plan is a snapshot of the calibrated state (weights, scales, device): anything that changes
+        one of them drops it; the next quantized forward rebuilds it."""
+        self._engine = None
+        self._submodules = None
+
+    def _apply(self, fn, *args, **kwargs):      # .to() / .cuda() / .float(): parameters move or change
+        super()._apply(fn, *args, **kwargs)
+        self._drop_engine()
+        return self
 
     def _init_weights(self, m):
         if isinstance(m, nn.Linear):
@@ -217,6 +231,7 @@ class VisionTransformer(nn.Module):
     def reset_classifier(self, num_classes, global_pool=''):
         self.num_classes = num_classes
         self.head = nn.Linear(self.embed_dim, num_classes) if num_classes > 0 else nn.Identity()
+        self._drop_engine()
 
     # -- mode switches (reference: vit_fquant.py:667-698) -------------------------------------
     _Q_MODULES = (QConv2d, QLinear, QAct, QIntSoftmax)
@@ -234,13 +249,19 @@ class VisionTransformer(nn.Module):
             for m in self.modules():
                 if type(m) is QIntLayerNorm:
                     m.mode = 'int'
-        self._engine = None
+        self._int_active = True
+        self._drop_engine()
 
     def model_dequant(self):
+        """The reference clears the modules' flags and leaves the model-level `quant` set (vit_fquant.py:680-683): the
+        next forward runs the float modules.  So does this one: the fused engine stays off until model_quant()."""
         self._set_flag('quant', False)
+        self._int_active = False
+        self._drop_engine()
 
     def model_open_calibrate(self):
         self._set_flag('calibrate', True)
+        self._drop_engine()       # scales are about to change
 
     def model_open_last_calibrate(self):
         self._set_flag('last_calibrate', True)
@@ -301,7 +322,8 @@ class VisionTransformer(nn.Module):
         return any(m._forward_hooks or m._forward_pre_hooks for m in self._submodules)
 
     def forward(self, x, bit_config=None, plot=False, hessian_statistic=False):
-        if self.quant and not hessian_statistic and self._integer_path(bit_config) and not self._hooked():
+        if (self.quant and self._int_active and not hessian_statistic and self._integer_path(bit_config)
+                and not self._hooked()):
             logits = self.integer_engine().forward(x, bit_config)
             return logits, self.flops(), []
         FLOPs, global_distance = [], []
