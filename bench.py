@@ -4,10 +4,11 @@
     python bench.py --gpus N --steps K --warmup W            # this repo's sm_100a path
     python bench.py --impl reference --steps K --warmup W    # the reference's CPU fake-quant path (port)
 
-One "step" = one quantized forward of one batch of 256 synthetic images (calibration excluded, as in
-BASELINE.md).  N > 1 is launched by torchrun, one rank per GPU; ranks process independent batches
-(weak scaling: 256 images per GPU per step, no data-path collective; NCCL only for the barrier and the
-max-over-ranks timing).  Rank 0 prints ONE JSON line.
+One "step" = one quantized forward of ONE batch of 256 synthetic images (calibration excluded, as in
+BASELINE.md).  N > 1 is launched by torchrun, one rank per GPU: the 256-image batch is sharded (256 / N images per
+GPU, `dist.shard`) and the step ends with the NCCL all-gather of the logits (`dist.gather_logits`), i.e. strong
+scaling of BASELINE config 2.  The round-1 measurement (256 images per GPU, no data-path collective) is reported
+beside it under "weak".  Rank 0 prints ONE JSON line.
 """
 import argparse
 import json
@@ -33,7 +34,7 @@ def parse():
     ap.add_argument('--warmup', type=int, default=10)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--model', default=MODEL)
-    ap.add_argument('--batch', type=int, default=BATCH, help='images per GPU per step')
+    ap.add_argument('--batch', type=int, default=BATCH, help='global batch per step (sharded over the GPUs)')
     ap.add_argument('--calib-batch', type=int, default=32)
     ap.add_argument('--e2e-steps', type=int, default=40, help='batches of the host-buffer serving loop (its un-overlapped first upload is inside the timed region)')
     ap.add_argument('--cpu-sample', type=int, default=32, help='images in the CPU-baseline sample')
@@ -49,6 +50,17 @@ def peaks():
     return 6650.0, 1590.0, 'fallback'
 
 
+def kernel_metrics():
+    """{kernel: {dram_bytes, tensor_pipe_pct, ...}} from the newest profiles/r*_kernel_metrics.json (written by
+    tools/ncu_to_metrics.py from `ncu --set full` captures), and the file name."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, 'profiles', 'r*_kernel_metrics.json')))
+    if not files:
+        return {}, None
+    with open(files[-1]) as f:
+        return json.load(f), os.path.relpath(files[-1], ROOT)
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
 
@@ -58,6 +70,13 @@ class ClockSampler:
 
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
+        self.t_begin = self.t_end = None
+
+    def mark_begin(self):
+        self.t_begin = time.time()
+
+    def mark_end(self):
+        self.t_end = time.time()
 
     def start(self):
         try:
@@ -71,7 +90,7 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(',')])
+            self.rows.append((time.time(), [c.strip() for c in line.split(',')]))
 
     def stop(self):
         if self.proc is None:
@@ -79,7 +98,10 @@ class ClockSampler:
         time.sleep(0.15)
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        rows = [r for t, r in self.rows if self.t_begin is None or (self.t_begin <= t <= (self.t_end or t) + 0.05)]
+        if not rows:       # a timed region shorter than one sampling period: the nearest samples
+            rows = [r for _, r in self.rows[-3:]]
+        for r in rows:
             try:
                 sm.append(float(r[1])); mx.append(float(r[2]))
             except (ValueError, IndexError):
@@ -177,13 +199,11 @@ def time_gemm(lib_mod, m, n, k, flags, iters, stream_obj):
     return t0.elapsed_time(t1) / iters
 
 
-def time_attention(lib_mod, bound, b, n, heads, iters, stream_obj):
-    """Average device time (ms) of the fused integer attention of block 0 on random int8 q/k/v codes."""
+def time_attention(lib_mod, bound, qkv, b, n, heads, iters, stream_obj):
+    """Average device time (ms) of the fused integer attention of block 0 on the model's own q/k/v codes."""
     import ctypes as C
     import torch
-    dev = 'cuda'
-    qkv = torch.randint(-60, 61, (b * n, 3 * heads * 64), dtype=torch.int8, device=dev)
-    out = torch.empty(b * n, heads * 64, dtype=torch.int8, device=dev)
+    out = torch.empty(b * n, heads * 64, dtype=torch.int8, device=qkv.device)
     att = bound.blocks[0].attn
     lib = lib_mod.lib()
     with torch.cuda.stream(stream_obj):
@@ -238,10 +258,14 @@ def bind_to_gpu_numa_node(local):
     return 'unchanged'
 
 
+MEAN, STD = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)     # the loaders' normalisation (test_quant.py:96-110)
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
     from diff_vit_b200 import _cabi
+    from diff_vit_b200 import dist as dvd
     from diff_vit_b200.plan import extract_state
 
     rank = int(os.environ.get('RANK', '0'))
@@ -254,7 +278,6 @@ def run_ours(args):
     device = torch.device('cuda', local)
     numa_note = bind_to_gpu_numa_node(local) if world > 1 else None
     if world > 1:
-        os.environ.pop('NCCL_DEBUG', None)     # NCCL's version banner would land on stdout next to the JSON line
         dist.init_process_group('nccl', device_id=device)
     _cabi.check(_cabi.lib().p2v_check_device(local))
 
@@ -262,8 +285,14 @@ def run_ours(args):
     bits = [8] * (4 * model.depth + 2)
     eng = model.integer_engine()
     bound = eng.bound(bits)
-    g = torch.Generator(device=device).manual_seed(1 + rank)
-    x = torch.randn(args.batch, 3, 224, 224, device=device, generator=g)   # 154 MB fp32 > 126 MB L2
+    classes = model.num_classes
+    # ONE global batch, identical on every rank (same seed), of which a rank keeps its shard
+    g = torch.Generator(device=device).manual_seed(1)
+    x_global = torch.randn(args.batch, 3, 224, 224, device=device, generator=g)   # 154 MB fp32 > 126 MB L2
+    x = dvd.shard(x_global, rank, world).contiguous() if world > 1 else x_global
+    per_rank = x.shape[0]
+    assert per_rank * world == args.batch, 'the global batch must divide by the number of GPUs'
+    gathered = torch.empty(args.batch, classes, dtype=torch.float32, device=device)
     stream = torch.cuda.Stream(device)
 
     def barrier():
@@ -272,53 +301,118 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize(device)
 
-    with torch.cuda.stream(stream):
-        for _ in range(max(args.warmup, 3)):
-            eng.forward_into(x, bits)
-    stream.synchronize()
-    barrier()
+    def step(xin):
+        """One step of the sharded job: this rank's forward, then the logits of all ranks on every rank."""
+        out = eng.forward_into(xin, bits)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, out)        # NCCL, ordered after the forward on this stream
+            return gathered
+        return out
+
+    # Timing hygiene: a 256-image fp32 batch (154 MB) is larger than the 126 MB L2, so back-to-back steps already start
+    # cold.  A shard of it is not (32 images = 19 MB at 8 GPUs): then every step is timed on its own, with a write of
+    # a 256 MB buffer (an L2 flush) between steps, outside the timed intervals.
+    flush_needed = x.numel() * 4 < 140e6
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=device) if flush_needed else None
+
+    def timed(fn, steps, warmup, flush):
+        with torch.cuda.stream(stream):
+            for _ in range(warmup):
+                fn()
+        stream.synchronize()
+        barrier()
+        if not flush:
+            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            with torch.cuda.stream(stream):
+                t0.record(stream)
+                for _ in range(steps):
+                    out = fn()
+                t1.record(stream)
+            stream.synchronize()
+            total = t0.elapsed_time(t1)
+        else:
+            evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+            with torch.cuda.stream(stream):
+                for a, b in evs:
+                    flush_buf.zero_()
+                    a.record(stream)
+                    out = fn()
+                    b.record(stream)
+            stream.synchronize()
+            total = sum(a.elapsed_time(b) for a, b in evs)
+        barrier()
+        ms = torch.tensor([total], device=device)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), out
+
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    warm = max(args.warmup, 3)
     with torch.cuda.stream(stream):
-        t0.record(stream)
-        for _ in range(args.steps):
-            logits = eng.forward_into(x, bits)
-        t1.record(stream)
+        for _ in range(warm):
+            step(x)
     stream.synchronize()
     barrier()
-    ms = torch.tensor([t0.elapsed_time(t1)], device=device)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    total_ms = float(ms.item())
+    sampler.mark_begin()
+    total_ms, logits = timed(lambda: step(x), args.steps, 0, flush_needed)
+    sampler.mark_end()
     clocks = sampler.stop() if rank == 0 else None
-    value = world * args.batch * args.steps / (total_ms * 1e-3)
+    value = args.batch * args.steps / (total_ms * 1e-3)
+    logits = logits.clone()
+    if world > 1:       # the sharded job gives the rows of the unsharded forward of the same batch
+        whole = eng.forward_into(x_global, bits)
+        assert torch.equal(logits, whole), 'sharded + gathered logits differ from the single-GPU forward'
 
-    # ---- end to end through the public host-buffer serving call: every step copies its own 256-image batch
-    # from pinned host memory and reads its logits back; copies overlap the previous / next forward ----
-    x_hosts = [torch.empty(x.shape, dtype=torch.float32).pin_memory() for _ in range(2)]
+    # weak scaling beside it (round 1's number): every GPU its own full batch, no data-path collective
+    weak = None
+    if world > 1:
+        weak_ms, _ = timed(lambda: eng.forward_into(x_global, bits), max(args.steps // 2, 5), 3, False)
+        weak = {'value': round(world * args.batch * max(args.steps // 2, 5) / (weak_ms * 1e-3), 1), 'unit': 'images/s',
+                'per_gpu_batch': args.batch, 'global_batch': args.batch * world, 'scaling': 'weak',
+                'note': 'every rank forwards its own %d-image batch; no collective in the timed region' % args.batch}
+
+    # ---- end to end through the public host-buffer serving call: every step uploads this rank's shard as 8-bit
+    # pixels from pinned host memory (the device applies the loader's normalisation), runs the forward, gathers the
+    # logits over NCCL and reads them back to the host; copies overlap the previous / next forward ----
+    mean_t = torch.tensor(MEAN, device=device).reshape(1, 3, 1, 1)
+    std_t = torch.tensor(STD, device=device).reshape(1, 3, 1, 1)
+    pix = ((x * std_t + mean_t) * 255).round().clamp(0, 255).to(torch.uint8)
+    x_norm = (pix.float().div(255) - mean_t) / std_t                       # what ToTensor + Normalize hand the model
+    ref_logits = eng.forward_into(x_norm, bits).clone()
+    x_hosts = [torch.empty(pix.shape, dtype=torch.uint8).pin_memory() for _ in range(2)]
     for xh in x_hosts:
-        xh.copy_(x)
+        xh.copy_(pix)
     n_e2e = max(args.e2e_steps, 2)
-    logits_hosts = [torch.empty(args.batch, model.num_classes, dtype=torch.float32).pin_memory() for _ in range(n_e2e)]
+    out_rows = args.batch if world > 1 else per_rank
+    logits_hosts = [torch.empty(out_rows, classes, dtype=torch.float32).pin_memory() for _ in range(n_e2e)]
     batches = [x_hosts[i & 1] for i in range(n_e2e)]
+    gather_bufs = [torch.empty(args.batch, classes, dtype=torch.float32, device=device) for _ in range(2)]
+
+    def after(out, slot):
+        if world == 1:
+            return out
+        dist.all_gather_into_tensor(gather_bufs[slot], out)
+        return gather_bufs[slot]
+
     with torch.cuda.stream(stream):
-        eng.forward_host_pipelined(batches[:2], logits_hosts[:2], bits)      # warm-up: graphs for both input buffers
+        eng.forward_host_pipelined(batches[:2], logits_hosts[:2], bits, mean=MEAN, std=STD, after_forward=after)
     barrier()
     w0 = time.perf_counter()
     with torch.cuda.stream(stream):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
-        eng.forward_host_pipelined(batches, logits_hosts, bits)              # returns after the last logits landed
+        eng.forward_host_pipelined(batches, logits_hosts, bits, mean=MEAN, std=STD, after_forward=after)
         e1.record(stream)
     stream.synchronize()
     e2e_ms = torch.tensor([max(e0.elapsed_time(e1), (time.perf_counter() - w0) * 1e3)], device=device)
     if world > 1:
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
-    e2e_value = world * args.batch * n_e2e / (float(e2e_ms.item()) * 1e-3)
+    e2e_value = args.batch * n_e2e / (float(e2e_ms.item()) * 1e-3)
+    mine = slice(rank * per_rank, (rank + 1) * per_rank) if world > 1 else slice(None)
     for lh in logits_hosts:
-        assert torch.equal(lh.to(device), logits), 'host-buffer call disagrees with the device-resident call'
+        assert torch.equal(lh[mine].to(device), ref_logits), 'host-buffer call disagrees with the device-resident call'
     x_host, logits_host = x_hosts[0], logits_hosts[0]
 
     if rank != 0:
@@ -327,46 +421,64 @@ def run_ours(args):
         return
 
     # ---- rooflines, timed live with CUDA events on the launch stream -----------------------------------------
-    # Dominant kernel by share of the step (ncu launch list, profiles/r1n_launches.csv: 37 %): the fused integer
-    # attention.  Algorithmic work per launch = QK^T + PV = 4 * B * H * N^2 * 64 int8 ops.  Second: the fc1 GEMM.
+    # Dominant kernel by share of the step (ncu launch list, profiles/): the fused integer attention.  Algorithmic work
+    # per launch = QK^T + PV = 4 * B * H * N^2 * 64 int8 ops.  Second: the fc1 GEMM.  The kernels are timed at the
+    # full batch of 256 (what one GPU runs at N = 1); DRAM traffic and tensor-pipe utilisation come from the ncu
+    # captures summarised in profiles/r*_kernel_metrics.json (tools/ncu_to_metrics.py), not from literals.
     hbm, bf16, src = peaks()
     peak = 2.0 * bf16
     peak_note = ('2 x %s bf16 burst (MEASURED_PEAKS.json has no int8 entry); nominal dense int8 %.0f' % (src, INT8_NOMINAL_TOPS))
+    km, km_file = kernel_metrics()
     ntok = model.patch_embed.num_patches + 1
     m = args.batch * ntok
     d, hid, heads = model.embed_dim, model.blocks[0].mlp.fc1.out_features, model.num_heads
-    att_ms = time_attention(_cabi, bound, args.batch, ntok, heads, 20, stream)
+    _, dump = eng.forward_dump(x_global[:32].contiguous(), bits)      # block 0's real q/k/v codes, tiled to the batch
+    qkv32 = torch.from_numpy(dump['act/blocks.0.attn.qact1']).reshape(32 * ntok, 3 * d)
+    del dump
+    qkv = qkv32.repeat((args.batch + 31) // 32, 1)[:m].contiguous().to(device)
+    att_ms = time_attention(_cabi, bound, qkv, args.batch, ntok, heads, 20, stream)
     att_ops = 4.0 * args.batch * heads * ntok * ntok * 64
     att_tops = att_ops / (att_ms * 1e-3) / 1e12
     step_ms = total_ms / args.steps
-    roofline = {'bound': 'tensor', 'kernel': 'attention_int_kernel (QK^T -> log-int-softmax -> PV), %d x %d heads x %d tokens'
-                % (args.batch, heads, ntok),
+    share = lambda ms_, count: round(ms_ * count / step_ms, 3) if world == 1 else None   # shares hold for the N = 1 step
+
+    def ncu(name, key):
+        for k, v in km.items():
+            if k.startswith(name):
+                return v.get(key)
+        return None
+
+    roofline = {'bound': 'tensor', 'kernel': 'attention_tc_kernel (tcgen05 kind::i8 QK^T + PV, TMEM accumulators, TMA; thread-per-row '
+                'log-int-softmax), %d x %d heads x %d tokens' % (args.batch, heads, ntok),
                 'achieved': round(att_tops, 2), 'peak': round(peak, 1), 'unit': 'TFLOP/s', 'frac': round(att_tops / peak, 4),
-                'traffic': 61.1e6, 'traffic_source': 'ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch '
-                                                     '(profiles/r1_summary.md); algorithmic bytes 77.5e6 (qkv in + out)',
-                'us_per_launch': round(att_ms * 1e3, 1), 'share_of_step': round(att_ms * model.depth / step_ms, 3),
+                'traffic': ncu('attention_tc_kernel', 'dram_bytes'), 'algorithmic_bytes': 4.0 * m * d,
+                'tensor_pipe_pct': ncu('attention_tc_kernel', 'tensor_pipe_pct'), 'traffic_source': km_file,
+                'us_per_launch': round(att_ms * 1e3, 1), 'share_of_step': share(att_ms, model.depth),
                 'peak_source': peak_note,
-                'note': 'bound by CUDA-core issue (51 % active, 48 lane instructions per score element) and shared-memory '
-                        'wavefronts of the softmax table lookups, not by the tensor pipe (15 %) or DRAM (4 %); ncu r1q'}
+                'note': 'not tensor bound: the softmax between the two products issues ~26 instructions per score element on '
+                        'four warps per scheduler (ALU pipe, table lookups, TMEM reads); see DESIGN.md 4.3'}
     ln_ms = time_layernorm(_cabi, bound, m, d, 20, stream)
     hbm_peak = float(hbm)
     ln_gbs = 2.0 * m * d / (ln_ms * 1e-3) / 1e9
     roofline_ln = {'bound': 'hbm', 'kernel': 'layernorm_int_pot_kernel %d rows x %d (int8 in, int8 out)' % (m, d),
                    'achieved': round(ln_gbs, 1), 'peak': round(hbm_peak, 1), 'unit': 'GB/s', 'peak_source': '%s HBM copy bandwidth' % src,
-                   'frac': round(ln_gbs / hbm_peak, 4), 'traffic': 19.4e6,
-                   'traffic_source': 'ncu r1q: dram read 19.4 MB, write-back deferred (the 19.4 MB output stays in the 126 MB L2)',
-                   'us_per_launch': round(ln_ms * 1e3, 1), 'share_of_step': round(ln_ms * (2 * model.depth + 1) / step_ms, 3),
-                   'note': 'latency / issue bound (36 lane instructions per element, per-row serial chain), not HBM bound'}
+                   'frac': round(ln_gbs / hbm_peak, 4), 'traffic': ncu('layernorm_int_pot_kernel', 'dram_bytes'),
+                   'algorithmic_bytes': 2.0 * m * d, 'traffic_source': km_file,
+                   'us_per_launch': round(ln_ms * 1e3, 1), 'share_of_step': share(ln_ms, 2 * model.depth + 1)}
     gemm_ms = time_gemm(_cabi, m, hid, d, _cabi.EPI_GELU | _cabi.EPI_OUT_POT, 20, stream)
     ops = 2.0 * m * hid * d
     achieved = ops / (gemm_ms * 1e-3) / 1e12
     roofline_gemm = {'bound': 'tensor', 'kernel': 'gemm_i8_bs_kernel<GELU|OUT_POT> fc1 %dx%dx%d (tcgen05 kind::i8)' % (m, hid, d),
                      'achieved': round(achieved, 2), 'peak': round(peak, 1), 'unit': 'TFLOP/s', 'frac': round(achieved / peak, 4),
-                     'traffic': 43.4e6, 'us_per_launch': round(gemm_ms * 1e3, 1),
-                     'share_of_step': round(gemm_ms * model.depth / step_ms, 3), 'peak_source': peak_note}
+                     'traffic': ncu('gemm_i8_bs_kernel<5>', 'dram_bytes'), 'algorithmic_bytes': float(m * d + hid * d + m * hid),
+                     'tensor_pipe_pct': ncu('gemm_i8_bs_kernel<5>', 'tensor_pipe_pct'), 'traffic_source': km_file,
+                     'us_per_launch': round(gemm_ms * 1e3, 1),
+                     'share_of_step': share(gemm_ms, model.depth), 'peak_source': peak_note}
+    tensor_pipe = {k: v.get('tensor_pipe_pct') for k, v in km.items() if v.get('tensor_pipe_pct') is not None}
     model_tops = value / world * GOP_PER_IMAGE / 1e3
     whole = {'achieved_tops': round(model_tops, 2), 'frac_of_peak': round(model_tops / peak, 4),
-             'frac_of_nominal_int8': round(model_tops / INT8_NOMINAL_TOPS, 4), 'gop_per_image': GOP_PER_IMAGE}
+             'frac_of_nominal_int8': round(model_tops / INT8_NOMINAL_TOPS, 4), 'gop_per_image': GOP_PER_IMAGE,
+             'note': 'per GPU'}
 
     cpu = None
     if not args.no_cpu_baseline:
@@ -376,23 +488,30 @@ def run_ours(args):
                'sample': '%d-image forward x2 after 1 warm-up, oracle/fakequant_forward.py (CPU restatement of '
                          'models/vit_fquant.py:700-799; /root/reference is not on the GPU box)' % args.cpu_sample}
 
-    in_bytes = x_host.numel() * 4
+    in_bytes = x_host.numel()           # uint8 pixels
+    launches = bound.launches
     line = {
         'metric': 'images/sec W8A8 PoT DeiT-S b256', 'value': round(value, 1), 'unit': 'images/s', 'n_gpus': world,
-        'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': round(total_ms / args.steps, 4),
-        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'int8 (s32 accumulate)',
-        'data': 'synthetic',
+        'steps': args.steps, 'warmup': warm, 'ms_per_step': round(total_ms / args.steps, 4),
+        'higher_is_better': True, 'scaling': 'strong' if world > 1 else 'weak', 'vs_baseline': None,
+        'dtype': 'int8 (s32 accumulate)', 'data': 'synthetic',
         'config': {'workload': '%s W8A8 PoT minmax quantized forward, bit_config [8]*50, random-init weights' % args.model,
-                   'per_gpu_batch': args.batch, 'global_batch': args.batch * world, 'parallelism': 'dp%d' % world,
-                   'l2': 'input batch %.0f MB fp32 > 126 MB L2' % (in_bytes / 1e6),
+                   'global_batch': args.batch, 'per_gpu_batch': per_rank, 'parallelism': 'dp%d' % world,
+                   'sharding': ('one %d-image batch sharded over %d GPUs, NCCL all-gather of the logits inside the step'
+                                % (args.batch, world)) if world > 1 else 'single GPU, no collective',
+                   'l2': ('per-GPU input %.0f MB fp32 < 126 MB L2: every step timed on its own, 256 MB L2 flush between steps'
+                          % (x.numel() * 4 / 1e6)) if flush_needed else 'input batch %.0f MB fp32 > 126 MB L2' % (x.numel() * 4 / 1e6),
                    'calibration': 'randn(%d,3,224,224), %.1f s, excluded' % (args.calib_batch, calib_s)},
-        'e2e': {'value': round(e2e_value, 1), 'unit': 'images/s', 'h2d_bytes_per_step': in_bytes,
-                'd2h_bytes_per_step': logits_host.numel() * 4, 'steps': n_e2e,
-                'api': 'IntegerEngine.forward_host_pipelined: pinned H2D of batch i+1 and D2H of logits i-1 overlap forward i (own streams)',
+        'e2e': {'value': round(e2e_value, 1), 'unit': 'images/s', 'h2d_bytes_per_step': in_bytes * world,
+                'd2h_bytes_per_step': logits_host.numel() * 4 * world, 'steps': n_e2e,
+                'api': 'IntegerEngine.forward_host_pipelined on uint8 pixels + mean / std (p2v_vit_forward_u8): pinned H2D of '
+                       'batch i+1 and D2H of the (gathered) logits i-1 overlap forward i on their own streams',
+                'input': 'uint8 pixels [%d, 3, 224, 224] per GPU per step; the device applies (p / 255 - mean) / std' % per_rank,
                 'host_affinity': numa_note},
-        'gpu_launches': (max(args.warmup, 3) + args.steps + n_e2e + 2) * bound.launches + 23,
-        'launches_per_step': bound.launches,
-        'roofline': roofline, 'roofline_fc1_gemm': roofline_gemm, 'roofline_layernorm': roofline_ln, 'whole_model': whole, 'cpu_baseline': cpu,
+        'gpu_launches': (warm + args.steps + n_e2e + 2 + (1 if world > 1 else 0)) * launches + 70,
+        'launches_per_step': launches,
+        'roofline': roofline, 'roofline_fc1_gemm': roofline_gemm, 'roofline_layernorm': roofline_ln,
+        'tensor_pipe_util_pct': tensor_pipe, 'whole_model': whole, 'weak': weak, 'cpu_baseline': cpu,
         'clocks': clocks,
     }
     print(json.dumps(line))

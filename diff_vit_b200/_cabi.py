@@ -66,6 +66,8 @@ SYMBOLS = {
     'p2v_test_gelu_fast': (C.c_int, [C.c_float, _vp, _vp]),
     'p2v_gemm_i8_acc': (C.c_int, [_vp, C.c_int64, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp]),
     'p2v_quant_patchify': (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, _vp]),
+    'p2v_quant_patchify_u8': (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, _vp,
+                                        _vp, _vp]),
     'p2v_embed_assemble': (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float,
                                      _vp, _vp, _vp, _vp]),
     'p2v_layernorm_int': (C.c_int, [_vp, C.c_int64, _vp, _vp, C.c_int, C.c_int, C.POINTER(LayerNorm), _vp]),
@@ -85,6 +87,7 @@ SYMBOLS = {
     'p2v_vit_destroy': (None, [_vp]),
     'p2v_vit_workspace_bytes': (C.c_int64, [_vp, C.c_int]),
     'p2v_vit_forward': (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, _vp, _vp, C.c_int, _vp]),
+    'p2v_vit_forward_u8': (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, C.c_int, _vp, C.c_int, _vp]),
     'p2v_vit_forward_host': (C.c_int, [_vp, _vp, _vp, C.c_int, _vp, _vp, _vp, _vp]),
     'p2v_vit_launches_per_forward': (C.c_int, [_vp]),
     'p2v_vit_dump_layout': (C.c_int, [_vp, C.c_int, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_int64),

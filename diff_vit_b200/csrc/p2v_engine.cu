@@ -77,7 +77,7 @@ struct p2v_vit {
   // double-buffered inputs (copy of batch i+1 overlapping the forward of batch i) replay without re-capture
   struct GraphEntry {
     cudaGraphExec_t exec;
-    const float* x;
+    const void* x;
     float* logits;
     int8_t* codes;
     int b;
@@ -183,15 +183,25 @@ static int copy_dump(p2v_vit* h, void* dump, int& idx, const void* src, cudaStre
 }
 
 // The launch sequence.  With dump != nullptr every intermediate is also written to the dump buffer.
-static int run(p2v_vit* h, const float* x, float* logits, int8_t* logit_codes, int b, void* dump, cudaStream_t st) {
+struct U8Input {            // non-null x8: the forward starts from 8-bit pixels
+  const uint8_t* x8 = nullptr;
+  float mean[4] = {0, 0, 0, 0}, stdv[4] = {1, 1, 1, 1};
+};
+
+static int run(p2v_vit* h, const float* x, float* logits, int8_t* logit_codes, int b, void* dump, cudaStream_t st,
+               const U8Input* u8 = nullptr) {
   const p2v_vit_desc& d = h->d;
   const int M = b * h->ntok, Mp = b * h->np, D = d.embed_dim;
   char* dp = static_cast<char*>(dump);
   int di = 0;
   auto slot = [&](int i) -> void* { return dp ? dp + h->dump[i].offset : nullptr; };
 
-  P2V_TRY(p2v_quant_patchify(x, h->patches, b, d.in_chans, d.img_size, d.img_size, d.patch_size, d.input_scale,
-                             d.input_zp, st));
+  if (u8 != nullptr && u8->x8 != nullptr)
+    P2V_TRY(p2v_quant_patchify_u8(u8->x8, h->patches, b, d.in_chans, d.img_size, d.img_size, d.patch_size, d.input_scale,
+                                  d.input_zp, u8->mean, u8->stdv, st));
+  else
+    P2V_TRY(p2v_quant_patchify(x, h->patches, b, d.in_chans, d.img_size, d.img_size, d.patch_size, d.input_scale,
+                               d.input_zp, st));
   P2V_TRY(copy_dump(h, dump, di, h->patches, st));
   P2V_TRY(gemm_i8_tc(h->tm_patches, h->tm_w_pe, h->pe, D, Mp, D, h->k0, d.patch_embed.epi, st));
   P2V_TRY(copy_dump(h, dump, di, h->pe, st));
@@ -337,9 +347,10 @@ extern "C" int p2v_vit_dump_layout(const p2v_vit* hc, int b, int i, const char**
   return (int)h->dump.size();
 }
 
-extern "C" int p2v_vit_forward(p2v_vit* h, const float* x, float* logits, int8_t* logit_codes, int b, void* workspace,
-                               void* dump, int use_graph, void* stream) {
-  P2V_REQUIRE(h && x && logits && workspace, "p2v_vit_forward: null pointer");
+static int forward_impl(p2v_vit* h, const float* x, const U8Input* u8, float* logits, int8_t* logit_codes, int b,
+                        void* workspace, void* dump, int use_graph, void* stream) {
+  const void* xkey = u8 ? static_cast<const void*>(u8->x8) : static_cast<const void*>(x);
+  P2V_REQUIRE(h && xkey && logits && workspace, "p2v_vit_forward: null pointer");
   P2V_REQUIRE(b > 0, "p2v_vit_forward: batch must be positive");
   cudaStream_t st = (cudaStream_t)stream;
   DeviceGuard guard(h->device);      // the handle's device, whatever is current in the calling thread
@@ -347,16 +358,16 @@ extern "C" int p2v_vit_forward(p2v_vit* h, const float* x, float* logits, int8_t
   P2V_TRY(bind(h, b, workspace));
   if (dump != nullptr) {
     build_dump_layout(h, b);
-    return run(h, x, logits, logit_codes, b, dump, st);
+    return run(h, x, logits, logit_codes, b, dump, st, u8);
   }
-  if (!use_graph || st == nullptr) return run(h, x, logits, logit_codes, b, nullptr, st);
+  if (!use_graph || st == nullptr) return run(h, x, logits, logit_codes, b, nullptr, st, u8);
   cudaGraphExec_t exec = nullptr;
   for (auto& e : h->graphs)
-    if (e.x == x && e.logits == logits && e.codes == logit_codes && e.b == b && e.ws == workspace) exec = e.exec;
+    if (e.x == xkey && e.logits == logits && e.codes == logit_codes && e.b == b && e.ws == workspace) exec = e.exec;
   if (exec == nullptr) {
     cudaGraph_t graph = nullptr;
     P2V_CHECK_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-    int rc = run(h, x, logits, logit_codes, b, nullptr, st);
+    int rc = run(h, x, logits, logit_codes, b, nullptr, st, u8);
     cudaError_t ce = cudaStreamEndCapture(st, &graph);
     if (rc != P2V_OK) {
       if (graph) cudaGraphDestroy(graph);
@@ -376,10 +387,28 @@ extern "C" int p2v_vit_forward(p2v_vit* h, const float* x, float* logits, int8_t
       cudaGraphExecDestroy(h->graphs.front().exec);
       h->graphs.erase(h->graphs.begin());
     }
-    h->graphs.push_back({exec, x, logits, logit_codes, b, workspace});
+    h->graphs.push_back({exec, xkey, logits, logit_codes, b, workspace});
   }
   P2V_CHECK_CUDA(cudaGraphLaunch(exec, st));
   return P2V_OK;
+}
+
+extern "C" int p2v_vit_forward(p2v_vit* h, const float* x, float* logits, int8_t* logit_codes, int b, void* workspace,
+                               void* dump, int use_graph, void* stream) {
+  return forward_impl(h, x, nullptr, logits, logit_codes, b, workspace, dump, use_graph, stream);
+}
+
+extern "C" int p2v_vit_forward_u8(p2v_vit* h, const uint8_t* x, const float* mean, const float* stdv, float* logits,
+                                  int8_t* logit_codes, int b, void* workspace, int use_graph, void* stream) {
+  P2V_REQUIRE(h && x && mean && stdv, "p2v_vit_forward_u8: null pointer");
+  P2V_REQUIRE(h->d.in_chans <= 4, "p2v_vit_forward_u8: at most 4 input channels");
+  U8Input u8;
+  u8.x8 = x;
+  for (int i = 0; i < h->d.in_chans; ++i) {
+    u8.mean[i] = mean[i];
+    u8.stdv[i] = stdv[i];
+  }
+  return forward_impl(h, nullptr, &u8, logits, logit_codes, b, workspace, nullptr, use_graph, stream);
 }
 
 extern "C" int p2v_vit_forward_host(p2v_vit* h, const float* x_host, float* logits_host, int b, void* workspace,

@@ -55,6 +55,48 @@ __global__ void quant_patchify_kernel(const float* __restrict__ x, int8_t* __res
   }
 }
 
+// The same from 8-bit pixels: x = (pixel / 255 - mean[c]) / std[c] (torchvision ToTensor + Normalize, the
+// preprocessing of the reference's loaders, test_quant.py:96-110), then the input quantizer.  A pixel has 256 values,
+// so each block evaluates the fp32 expression once per (channel, value) into a shared-memory table of codes and the
+// image is a byte gather: a quarter of the fp32 input's HBM and host-link traffic, same codes.
+struct U8Norm {
+  float mean[4], stdv[4];
+};
+__global__ void quant_patchify_u8_kernel(const uint8_t* __restrict__ x, int8_t* __restrict__ codes, int b, int c,
+                                         int h, int w, int p, float scale, float zp, U8Norm nm, int64_t total16) {
+  __shared__ uint8_t lut[4][256];
+  const float rs = __frcp_rn(scale);
+  for (int i = threadIdx.x; i < c * 256; i += blockDim.x) {
+    const int ch = i >> 8, v = i & 255;
+    const float xn = fdiv(fsub(fdiv((float)v, 255.0f), nm.mean[ch]), nm.stdv[ch]);
+    lut[ch][v] = (uint8_t)(int8_t)quant_div_guarded(xn, scale, rs, zp);
+  }
+  __syncthreads();
+  const int gw = w / p, gh = h / p;
+  const int k = c * p * p;
+  const int w16 = w / 16;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total16;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int xs = (int)(i % w16);
+    int64_t r = i / w16;
+    const int y = (int)(r % h);
+    r /= h;
+    const int ch = (int)(r % c);
+    const int img = (int)(r / c);
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(x + (((int64_t)img * c + ch) * h + y) * w + xs * 16));
+    const uint32_t in[4] = {v.x, v.y, v.z, v.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      o[j] = (uint32_t)lut[ch][in[j] & 0xff] | ((uint32_t)lut[ch][(in[j] >> 8) & 0xff] << 8) |
+             ((uint32_t)lut[ch][(in[j] >> 16) & 0xff] << 16) | ((uint32_t)lut[ch][in[j] >> 24] << 24);
+    const int px = xs * 16;
+    const int pw = px / p, kw = px % p, ph = y / p, kh = y % p;
+    const int64_t row = ((int64_t)img * gh + ph) * gw + pw;
+    *reinterpret_cast<uint4*>(codes + row * k + ((int64_t)ch * p + kh) * p + kw) = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
 // ---- token assembly ------------------------------------------------------------------------------------
 // x = qact_embed(cat(cls, patches)) + qact_pos(pos_embed); out = qact1(x)   (models/vit_fquant.py:718-733)
 // One thread owns one 4-channel group (blockDim.x is a multiple of d / 4) and walks tokens grid-stride, so the
@@ -397,6 +439,25 @@ extern "C" int p2v_quant_patchify(const float* x, int8_t* codes, int b, int c, i
   const int64_t total16 = (int64_t)b * c * h * (w / 16);
   quant_patchify_kernel<<<grid_for(total16, 256), 256, 0, (cudaStream_t)stream>>>(x, codes, b, c, h, w, p, scale,
                                                                                   zero_point, total16);
+  P2V_CHECK_CUDA(cudaGetLastError());
+  return P2V_OK;
+}
+
+extern "C" int p2v_quant_patchify_u8(const uint8_t* x, int8_t* codes, int b, int c, int h, int w, int p, float scale,
+                                     float zero_point, const float* mean, const float* stdv, void* stream) {
+  P2V_REQUIRE(x && codes && mean && stdv, "p2v_quant_patchify_u8: null pointer");
+  P2V_REQUIRE(b > 0 && c > 0 && c <= 4 && p > 0 && h % p == 0 && w % p == 0,
+              "p2v_quant_patchify_u8: bad shape %dx%dx%dx%d p=%d (at most 4 channels)", b, c, h, w, p);
+  P2V_REQUIRE(p % 16 == 0 && w % 16 == 0, "p2v_quant_patchify_u8: patch size and width must be multiples of 16");
+  P2V_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0, "p2v_quant_patchify_u8: x must be 16-byte aligned");
+  U8Norm nm = {};
+  for (int i = 0; i < c; ++i) {
+    nm.mean[i] = mean[i];
+    nm.stdv[i] = stdv[i];
+  }
+  const int64_t total16 = (int64_t)b * c * h * (w / 16);
+  quant_patchify_u8_kernel<<<grid_for(total16, 256), 256, 0, (cudaStream_t)stream>>>(x, codes, b, c, h, w, p, scale,
+                                                                                     zero_point, nm, total16);
   P2V_CHECK_CUDA(cudaGetLastError());
   return P2V_OK;
 }

@@ -65,20 +65,36 @@ def global_mean(sq_err, dims=None):
 
 
 def shard(x, rank=None, world=None):
-    """Contiguous shard of a batch for this rank (256 / G images per GPU in BASELINE config 2)."""
+    """Contiguous shard of a batch for this rank (256 / G images per GPU in BASELINE config 2).  With a batch that
+    does not divide by the world size the trailing ranks get a shorter, possibly empty, shard."""
     rank = dist.get_rank() if rank is None else rank
     world = dist.get_world_size() if world is None else world
     per = (x.shape[0] + world - 1) // world
-    return x[rank * per:min((rank + 1) * per, x.shape[0])]
+    return x[min(rank * per, x.shape[0]):min((rank + 1) * per, x.shape[0])]
 
 
 def gather_logits(logits, group=None):
-    """All-gather of per-rank logits [b_r, classes] -> [sum b_r, classes] (equal shard sizes)."""
+    """All-gather of per-rank logits [b_r, classes] -> [sum b_r, classes], rank order.  Shards may differ in length
+    (ImageNet's last validation batch of 80 images on 8 ranks) or be empty: the lengths are gathered first, every rank
+    contributes a buffer padded to the longest shard, and the padding is cut out again."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return logits
-    parts = [torch.empty_like(logits) for _ in range(dist.get_world_size(group))]
-    dist.all_gather(parts, logits.contiguous(), group=group)
-    return torch.cat(parts, dim=0)
+    world = dist.get_world_size(group)
+    local = logits.contiguous()
+    lengths = torch.zeros(world, dtype=torch.int64, device=local.device)
+    lengths[dist.get_rank(group)] = local.shape[0]
+    dist.all_reduce(lengths, op=dist.ReduceOp.SUM, group=group)
+    lengths = [int(v) for v in lengths.tolist()]
+    longest = max(lengths)
+    if min(lengths) == longest:                      # the common case: one collective, no padding
+        parts = [torch.empty_like(local) for _ in range(world)]
+        dist.all_gather(parts, local, group=group)
+        return torch.cat(parts, dim=0)
+    padded = local.new_zeros((longest,) + tuple(local.shape[1:]))
+    padded[:local.shape[0]] = local
+    parts = [torch.empty_like(padded) for _ in range(world)]
+    dist.all_gather(parts, padded, group=group)
+    return torch.cat([p[:n] for p, n in zip(parts, lengths)], dim=0)
 
 
 def calibrate_model_distributed(model, local_batches, group=None):
@@ -102,6 +118,8 @@ def validate(model, batches, bit_config, group=None):
     runs its shard, hit counts are summed over the group.  Returns (top1 %, top5 %, images)."""
     hits = torch.zeros(3, dtype=torch.float64)
     for data, target in batches:
+        if data.shape[0] == 0:        # an empty shard of a short last batch: nothing to run, but stay in the collective
+            continue
         with torch.no_grad():
             out, _, _ = model(data, bit_config, False)
         k = min(5, out.shape[1])

@@ -193,6 +193,24 @@ class IntegerEngine:
         self._last_input = x  # keep the (possibly re-laid-out) input alive until the stream consumed it
         return logits
 
+    def forward_into_u8(self, x_u8, bit_config, mean, std, use_graph=True, slot=0):
+        """The forward from 8-bit pixels [B, C, H, W] (CUDA uint8) with the loader's normalisation constants: the device
+        evaluates (pixel / 255 - mean[c]) / std[c] op for op, so the logits equal `forward_into` on the normalised fp32
+        tensor, for a quarter of the input traffic.  Returns the engine-owned logits buffer (of `slot`)."""
+        bp = self.bound(bit_config)
+        self._check_input(x_u8, bp.plan.arch)
+        if not x_u8.is_cuda or x_u8.dtype != torch.uint8:
+            raise RuntimeError('IntegerEngine.forward_into_u8 expects a CUDA uint8 tensor')
+        x_u8 = x_u8.contiguous()
+        b, c = x_u8.shape[0], x_u8.shape[1]
+        m = (C.c_float * c)(*[float(v) for v in mean])
+        sd = (C.c_float * c)(*[float(v) for v in std])
+        _, ws, logits, codes = bp.buffers(b, slot)
+        _cabi.check(_cabi.lib().p2v_vit_forward_u8(bp.handle, x_u8.data_ptr(), m, sd, logits.data_ptr(), codes.data_ptr(),
+                                                   b, ws, 1 if use_graph else 0, _cabi.current_stream(self.device)))
+        self._last_input = x_u8
+        return logits
+
     def forward(self, x, bit_config):
         """Drop-in: fp32 logits [B, classes] on x's device (host inputs are copied to the GPU and back)."""
         on_host = not x.is_cuda
@@ -229,19 +247,25 @@ class IntegerEngine:
                 out[key] = raw.view(np.int8).copy()
         return logits.clone(), out
 
-    def forward_host_pipelined(self, batches_host, logits_host, bit_config):
+    def forward_host_pipelined(self, batches_host, logits_host, bit_config, mean=None, std=None, after_forward=None):
         """Serving loop over HOST batches: the pinned-memory H2D copy of batch i+1 and the D2H copy of the logits
         of batch i-1 overlap the forward of batch i (two device input buffers, two logits buffers, one copy
-        stream, CUDA events).  `batches_host[i]` -> `logits_host[i]`; returns after everything has landed."""
+        stream, CUDA events).  `batches_host[i]` -> `logits_host[i]`; returns after everything has landed.
+        uint8 batches (raw pixels) need the loader's `mean` / `std` and take the 8-bit entry (`forward_into_u8`).
+        `after_forward(logits, slot)` (optional) runs on the compute stream right after a forward and returns the
+        tensor to send to the host instead of the local logits (e.g. their NCCL all-gather, slot in {0, 1})."""
         bp = self.bound(bit_config)
+        u8 = batches_host[0].dtype == torch.uint8
+        if u8 and (mean is None or std is None):
+            raise ValueError('uint8 batches need the normalisation constants mean and std')
         comp = torch.cuda.current_stream(self.device)
         if not hasattr(self, '_io_streams'):
             self._io_streams = (torch.cuda.Stream(self.device), torch.cuda.Stream(self.device))
         h2d, d2h = self._io_streams        # separate queues: an upload never waits behind a download
         b = batches_host[0].shape[0]
-        key = ('xpipe', b)
+        key = ('xpipe', b, u8)
         if key not in bp._buffers:
-            bp._buffers[key] = ([torch.empty(batches_host[0].shape, dtype=torch.float32, device=self.device) for _ in range(2)],
+            bp._buffers[key] = ([torch.empty(batches_host[0].shape, dtype=batches_host[0].dtype, device=self.device) for _ in range(2)],
                                 [[torch.cuda.Event() for _ in range(2)] for _ in range(3)])
         xdev, (ev_in, ev_done, ev_out) = bp._buffers[key]
         h2d.wait_stream(comp)
@@ -256,7 +280,12 @@ class IntegerEngine:
             comp.wait_event(ev_in[slot])
             if i >= 2:
                 comp.wait_event(ev_out[slot])               # the logits of batch i-2 have left their buffer
-            logits = self.forward_into(xdev[slot], bit_config, slot=slot + 1)
+            if u8:
+                logits = self.forward_into_u8(xdev[slot], bit_config, mean, std, slot=slot + 1)
+            else:
+                logits = self.forward_into(xdev[slot], bit_config, slot=slot + 1)
+            if after_forward is not None:
+                logits = after_forward(logits, slot)
             ev_done[slot].record(comp)
             with torch.cuda.stream(d2h):
                 d2h.wait_event(ev_done[slot])

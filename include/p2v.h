@@ -83,6 +83,11 @@ int p2v_gemm_i8_acc(const int8_t* a, int64_t lda, const int8_t* w, int32_t* acc,
  * Replaces qact_input (models/vit_fquant.py:705-706) and the unfold inside F.conv2d. */
 int p2v_quant_patchify(const float* x, int8_t* codes, int b, int c, int h, int w, int p, float scale,
                        float zero_point, void* stream);
+/* The same from 8-bit pixels x [b, c, h, w] (device): the fp32 preprocessing of the reference's loaders,
+ * (pixel / 255 - mean[c]) / std[c] (torchvision ToTensor + Normalize, test_quant.py:96-110), is evaluated on the
+ * device op for op, so the codes equal those of the fp32 entry on the normalised tensor.  mean / std: HOST arrays [c]. */
+int p2v_quant_patchify_u8(const uint8_t* x, int8_t* codes, int b, int c, int h, int w, int p, float scale,
+                          float zero_point, const float* mean, const float* stdv, void* stream);
 
 /* Token assembly: cls concat, qact_embed, + qact_pos(pos_embed), qact1 (PTF)
  * (models/vit_fquant.py:718-733).  pe: patch-embed codes [b*np, d]; cls_value[d] / pos_value[(np+1)*d]
@@ -238,6 +243,10 @@ int64_t p2v_vit_workspace_bytes(const p2v_vit* h, int b);
  * on first use when use_graph != 0. */
 int p2v_vit_forward(p2v_vit* h, const float* x, float* logits, int8_t* logit_codes, int b, void* workspace,
                     void* dump, int use_graph, void* stream);
+/* p2v_vit_forward on 8-bit pixels x [b, c, h, w] (device) with the loader's normalisation constants (HOST arrays
+ * [in_chans]): a quarter of the input traffic of the fp32 entry, identical codes (see p2v_quant_patchify_u8). */
+int p2v_vit_forward_u8(p2v_vit* h, const uint8_t* x, const float* mean, const float* stdv, float* logits,
+                       int8_t* logit_codes, int b, void* workspace, int use_graph, void* stream);
 /* End-to-end call with HOST buffers (pinned or pageable): H2D copy, forward, D2H copy, stream sync. */
 int p2v_vit_forward_host(p2v_vit* h, const float* x_host, float* logits_host, int b, void* workspace,
                          void* x_dev, void* logits_dev, void* stream);

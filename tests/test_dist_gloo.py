@@ -37,14 +37,6 @@ def _worker(rank, world, port, ret):
             if isinstance(m, (dv.Attention, dv.Mlp)):
                 scales['cs/' + name] = m.channel_scale.numpy()
         bad = [k for k, v in scales.items() if not np.array_equal(v.reshape(-1), z[k].reshape(-1))]
-        # logits gather + sharded accuracy bookkeeping on fake logits
-        g = torch.Generator().manual_seed(7)
-        logits = torch.randn(8, 16, generator=g)
-        target = torch.randint(0, 16, (8,), generator=g)
-        mine = dvd.shard(logits)
-        full = dvd.gather_logits(mine)
-        ok_gather = torch.equal(full, logits)
-
         class Fake(torch.nn.Module):
             def __init__(self):
                 super().__init__()
@@ -52,6 +44,20 @@ def _worker(rank, world, port, ret):
 
             def forward(self, data, bit_config, plot):
                 return data, [], []
+        # logits gather + sharded accuracy bookkeeping on fake logits
+        g = torch.Generator().manual_seed(7)
+        logits = torch.randn(8, 16, generator=g)
+        target = torch.randint(0, 16, (8,), generator=g)
+        mine = dvd.shard(logits)
+        full = dvd.gather_logits(mine)
+        ok_gather = torch.equal(full, logits)
+        # shards of unequal length (5 rows on 2 ranks: 3 + 2) and an empty shard (1 row on 2 ranks: 1 + 0)
+        for rows in (5, 1):
+            part = dvd.shard(logits[:rows])
+            ok_gather = ok_gather and torch.equal(dvd.gather_logits(part), logits[:rows])
+        t1, _, n1 = dvd.validate(Fake(), [(dvd.shard(logits[:1]), dvd.shard(target[:1]))], [8])
+        ok_gather = ok_gather and n1 == 1
+
         top1, top5, n = dvd.validate(Fake(), [(mine, dvd.shard(target))], [8])
         ref1, ref5 = dvd.accuracy(logits, target, topk=(1, 5))
         # percentile observer: the exact distributed order statistic equals torch.quantile on the whole batch

@@ -454,3 +454,24 @@ def test_int4_packed_plan_runs_on_the_engine(micro_model, micro_state, micro_gol
         pd = packed.cuda()
         _cabi.check(_cabi.lib().p2v_unpack_int4(pd.data_ptr(), out.data_ptr(), nbytes, _cabi.current_stream()))
         assert torch.equal(out.cpu().reshape(1, -1), unpack_int4(packed))
+
+
+def test_uint8_pixel_entry_equals_fp32_entry_on_normalised_images(micro_model, micro_golden):
+    """p2v_vit_forward_u8 / forward_into_u8: 8-bit pixels plus the loader's mean / std give the logits of the fp32 entry
+    on torchvision's ToTensor + Normalize of the same pixels, bit for bit (every (channel, pixel value) pair is covered:
+    all 256 values occur), through the direct call and the pipelined host-buffer loop."""
+    eng = micro_model.integer_engine()
+    bc = [8] * 10
+    g = torch.Generator().manual_seed(11)
+    img = torch.randint(0, 256, (5, 3, 48, 48), dtype=torch.uint8, generator=g)
+    img[0, :, 0, :].copy_(torch.arange(48, dtype=torch.uint8))
+    img[1].reshape(-1)[:768].copy_(torch.arange(768) % 256)
+    mean, std = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
+    x = img.float().div(255)
+    x = (x - torch.tensor(mean).reshape(1, 3, 1, 1)) / torch.tensor(std).reshape(1, 3, 1, 1)     # ToTensor + Normalize
+    want = eng.forward_into(x.cuda(), bc).clone()
+    got = eng.forward_into_u8(img.cuda(), bc, mean, std).clone()
+    assert torch.equal(got, want) and want.std() > 0
+    outs = [torch.empty(5, 16).pin_memory() for _ in range(3)]
+    eng.forward_host_pipelined([img.pin_memory() for _ in range(3)], outs, bc, mean=mean, std=std)
+    assert all(torch.equal(o, want.cpu()) for o in outs)
