@@ -283,44 +283,38 @@ __device__ __forceinline__ void sum_piece(const uint32_t (&w)[4], int cnt, uint3
 }
 
 // One element of pass 3: 2^(15-k) as a 16-bit integer from the bracketed 1 / (3e) (see file header).  The exponent
-// field comes out of a multiply-high (FMA pipe): the ALU pipe, which issues a warp instruction every other cycle, is
-// what bounds this kernel.
-template <bool kPeak>
-__device__ __forceinline__ uint32_t prob_one(uint32_t addr, float fsum, float sixth, uint32_t top_addr, uint32_t p_top, uint32_t& guard) {
+// field comes out of a multiply-high (FMA pipe): the ALU pipe issues a warp instruction only every other cycle.
+__device__ __forceinline__ uint32_t prob_one(uint32_t addr, float fsum, float sixth, uint32_t& guard) {
   const float2 r = lds64f(addr);
   const float2 u = ffma2(make_float2(fsum, fsum), r, make_float2(sixth, sixth));
-  guard = __float_as_uint(u.x) ^ __float_as_uint(u.y);
-  uint32_t p = shr_clamp(0x100000u, __umulhi(__float_as_uint(u.x), 512u));   // >> 23
-  if (kPeak) p = addr == top_addr ? p_top : p;   // the row maximum itself: its exact probability
-  return p;
+  guard |= __float_as_uint(u.x) ^ __float_as_uint(u.y);
+  return shr_clamp(0x100000u, __umulhi(__float_as_uint(u.x), 512u));   // 0x100000 >> (bits >> 23)
 }
-// Pass 3 over one piece: the two probability byte planes of its 16 keys (keys >= cnt: 0).  Returns the OR of
-// (low-bracket bits ^ high-bracket bits): a set exponent bit means some element sits next to a step of the code function.
-template <bool kPeak, bool kMask>
-__device__ __forceinline__ uint32_t prob_piece(const uint32_t (&w)[4], int cnt, uint32_t bias, uint32_t base_r, float fsum,
-                                               float sixth, uint32_t p_top, uint32_t (&hi)[4], uint32_t (&lo)[4]) {
+// Pass 3 over one piece of 16 keys: its two probability byte planes.  ONE instantiation serves every piece (the three
+// passes are kept small enough for the instruction caches: a first version with per-case variants of this loop,
+// unrolled over the warp's chunks, was 158 KB of code and starved on instruction fetch); the two special cases are
+// patched afterwards by the caller: keys beyond n (ragged last piece) and the maximum of a peaked row.
+// Returns the OR of (low-bracket bits ^ high-bracket bits): a set exponent bit = some element sits next to a step.
+__device__ __forceinline__ uint32_t prob_piece(const uint32_t (&w)[4], uint32_t bias, uint32_t base_r, float fsum, float sixth,
+                                               uint32_t (&hi)[4], uint32_t (&lo)[4]) {
   uint32_t guard = 0;
-  const uint32_t top_addr = base_r | 0xff00u;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const uint32_t x = w[i] + bias;
-    uint32_t g0, g1, g2, g3;
-    uint32_t p0 = prob_one<kPeak>(tab_addr<0>(x, base_r), fsum, sixth, top_addr, p_top, g0);
-    uint32_t p1 = prob_one<kPeak>(tab_addr<1>(x, base_r), fsum, sixth, top_addr, p_top, g1);
-    uint32_t p2 = prob_one<kPeak>(tab_addr<2>(x, base_r), fsum, sixth, top_addr, p_top, g2);
-    uint32_t p3 = prob_one<kPeak>(tab_addr<3>(x, base_r), fsum, sixth, top_addr, p_top, g3);
-    if (kMask) {   // keys beyond n: probability 0, and their (meaningless) brackets must not trigger the exact path
-      if (4 * i >= cnt) { p0 = 0u; g0 = 0u; }
-      if (4 * i + 1 >= cnt) { p1 = 0u; g1 = 0u; }
-      if (4 * i + 2 >= cnt) { p2 = 0u; g2 = 0u; }
-      if (4 * i + 3 >= cnt) { p3 = 0u; g3 = 0u; }
-    }
-    guard |= (g0 | g1) | (g2 | g3);
+    const uint32_t p0 = prob_one(tab_addr<0>(x, base_r), fsum, sixth, guard);
+    const uint32_t p1 = prob_one(tab_addr<1>(x, base_r), fsum, sixth, guard);
+    const uint32_t p2 = prob_one(tab_addr<2>(x, base_r), fsum, sixth, guard);
+    const uint32_t p3 = prob_one(tab_addr<3>(x, base_r), fsum, sixth, guard);
     const uint32_t a01 = p0 | (p1 << 16), a23 = p2 | (p3 << 16);
     lo[i] = __byte_perm(a01, a23, 0x6420);
     hi[i] = __byte_perm(a01, a23, 0x7531);
   }
   return guard;
+}
+// 0x80 in every byte of v that is 0xff (exact per byte)
+__device__ __forceinline__ uint32_t bytes_ff(uint32_t v) {
+  const uint32_t y = ~v;
+  return ~(((y & 0x7f7f7f7fu) + 0x7f7f7f7fu) | y | 0x7f7f7f7fu);
 }
 
 template <bool kDump>
@@ -496,32 +490,28 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_co
         tc_fence_after_sync();
         stamp(1);
         if (warp_on) {
-          // ---- pass 1 (the only read of the raw scores): codes, four to a word, kept in registers for both later passes;
-          // row extrema of this warp's chunks, then of both halves ----
-          uint32_t cw[4][2][4];                       // [own chunk][16-key piece][word]
+          // ---- pass 1 (the only read of the raw scores): codes, four to a word, parked in the first four columns of their
+          // own 16-column piece; row extrema of this warp's chunks, then of both halves ----
           int mx = (int)0x80000000, mn = 0x7fffffff;
-          // (fully unrolled over the warp's four chunks: the register array needs compile-time indices.  Keeping the loops
-          // rolled by rotating the array instead was measured: the 32 moves per chunk cost more than the instruction
-          // fetch stalls of the larger code.)
-#pragma unroll
-          for (int it = 0; it < 4; ++it) {
-            const int c = hf + 2 * it;
-            if (c < nchunks) {
-#pragma unroll
-              for (int h = 0; h < 2; ++h) {
-                const int col = 32 * c + 16 * h, cnt = n - col;
-                if (cnt > 0) {
-                  uint32_t v[16];
-                  tmem_ld_32x16(tile + col, v);
-                  tmem_ld_wait();
-                  if (cnt >= 16) code_piece<false>(v, 16, mul, c0, cw[it][h], mx, mn);
-                  else code_piece<true>(v, cnt, mul, c0, cw[it][h], mx, mn);
-                }
-              }
+#pragma unroll 1
+          for (int c = hf; c < nchunks; c += 2) {
+            const int cnt0 = n - 32 * c;               // > 0
+            uint32_t v0[16], v1[16], w[4];
+            tmem_ld_32x16(tile + 32 * c, v0);
+            if (cnt0 > 16) tmem_ld_32x16(tile + 32 * c + 16, v1);
+            tmem_ld_wait();
+            if (cnt0 >= 16) code_piece<false>(v0, 16, mul, c0, w, mx, mn);
+            else code_piece<true>(v0, cnt0, mul, c0, w, mx, mn);
+            tmem_st_32x4(tile + 32 * c, w);
+            if (cnt0 > 16) {
+              if (cnt0 >= 32) code_piece<false>(v1, 16, mul, c0, w, mx, mn);
+              else code_piece<true>(v1, cnt0 - 16, mul, c0, w, mx, mn);
+              tmem_st_32x4(tile + 32 * c + 16, w);
             }
           }
           s.x_minmax[pair][hf][lane] = make_int2(mx, mn);
-          pair_barrier(pair);           // ... which also tells that the partner is done reading raw scores: P may be written
+          tmem_ld_wait_st();
+          pair_barrier(pair);
           {
             const int2 o = s.x_minmax[pair][hf ^ 1][lane];
             mx = max(mx, o.x);
@@ -538,17 +528,17 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_co
 
           // ---- pass 2: exact row sum of the integer exp ----
           double acc[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll
-          for (int it = 0; it < 4; ++it) {
-            const int c = hf + 2 * it;
-            if (c < nchunks) {
-#pragma unroll
-              for (int h = 0; h < 2; ++h) {
-                const int cnt = n - (32 * c + 16 * h);
-                if (cnt >= 16) sum_piece<false>(cw[it][h], 16, bias, base_e, acc);
-                else if (cnt > 0) sum_piece<true>(cw[it][h], cnt, bias, base_e, acc);
-              }
-            }
+#pragma unroll 1
+          for (int c = hf; c < nchunks; c += 2) {
+            const int cnt0 = n - 32 * c;
+            uint32_t w0[4], w1[4];
+            tmem_ld_32x4(tile + 32 * c, w0);
+            if (cnt0 > 16) tmem_ld_32x4(tile + 32 * c + 16, w1);
+            tmem_ld_wait();
+            if (cnt0 >= 16) sum_piece<false>(w0, 16, bias, base_e, acc);
+            else sum_piece<true>(w0, cnt0, bias, base_e, acc);
+            if (cnt0 >= 32) sum_piece<false>(w1, 16, bias, base_e, acc);
+            else if (cnt0 > 16) sum_piece<true>(w1, cnt0 - 16, bias, base_e, acc);
           }
           const double part = (acc[0] + acc[1]) + (acc[2] + acc[3]);     // integers < 2^53: exact in any order
           s.x_sum[pair][hf][lane] = part;
@@ -558,22 +548,35 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_co
           // u = S / (3e) + 1/6 is evaluated scaled by 2^-120 (exact), which puts its exponent field into 5 .. 31:
           // a shift count, 2^(15-k) = 0x100000 >> field
           const float fsum_s = __fmul_rn(fsum, __uint_as_float((127u - 120u) << 23));
-          // the maximum itself: exact code; a row whose maximum holds most of the mass leaves the regular step pattern
+          // A row whose maximum holds more than 2/3 of the mass (code 0) leaves the regular step pattern of the code
+          // function at that one element: patched below, in the warps that have such a row
           const int k_top = softmax_log_code(fsum, s.lut[0], 16);
-          const uint32_t p_top = k_top >= 16 ? 0u : (0x8000u >> k_top);
-          const bool peakw = __any_sync(0xffffffffu, k_top < 2);
+          const bool peakw = __any_sync(0xffffffffu, k_top == 0);
 
-          // ---- pass 3: probabilities 2^(15-k) as two byte planes, written to TMEM as the A operand of P V: chunk c to
-          // columns 8c.. (high) and 208 + 8c.. / 56 + 8(c - 4).. (low) - raw score columns nobody reads any more ----
-#pragma unroll
+          // ---- pass 3: probabilities 2^(15-k) as two byte planes, written to TMEM as the A operand of P V ----
+          // The planes of chunk c go to columns 8c.. (high) and 208 + 8c.. / 56 + 8(c - 4).. (low): columns of chunks
+          // 0, 1 and 2, whose code words (columns 0-3, 16-19 of each chunk) the pair is still reading.  Chunks 0 / 2
+          // belong to the even warp of the pair, chunk 1 to the odd one, so a pair barrier after each warp has loaded
+          // its first and its second chunk keeps every write behind the reads of BOTH warps (P(1), P(3) -> chunk 0 and
+          // P(4), P(6) -> chunk 1 after barrier one; P(5) -> chunk 2 after barrier two).
+#pragma unroll 1
           for (int it = 0; it < 4; ++it) {
             const int c = hf + 2 * it;
-            if (c >= nchunks) continue;
+            if (c >= nchunks) {
+              if (it < 2) pair_barrier(pair);
+              continue;
+            }
+            uint32_t wv[2][4];
+            const int cnt0 = n - 32 * c;
+            tmem_ld_32x4(tile + 32 * c, wv[0]);
+            if (cnt0 > 16) tmem_ld_32x4(tile + 32 * c + 16, wv[1]);
+            tmem_ld_wait();
+            if (it < 2) pair_barrier(pair);
             uint32_t hi[8], lo[8];                    // the chunk's two planes: words 0-3 keys 0-15, words 4-7 keys 16-31
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-              const int cnt = n - (32 * c + 16 * h);
-              uint32_t (&w)[4] = cw[it][h];
+              const int cnt = min(cnt0 - 16 * h, 16);
+              uint32_t (&w)[4] = wv[h];
               uint32_t (&ph)[4] = *reinterpret_cast<uint32_t(*)[4]>(&hi[4 * h]);
               uint32_t (&pl)[4] = *reinterpret_cast<uint32_t(*)[4]>(&lo[4 * h]);
               if (cnt <= 0) {
@@ -581,29 +584,41 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_co
                 for (int x = 0; x < 4; ++x) ph[x] = pl[x] = 0u;
                 continue;
               }
-              uint32_t guard;
-              if (cnt >= 16) guard = peakw ? prob_piece<true, false>(w, 16, bias, base_r, fsum_s, sixth, p_top, ph, pl)
-                                           : prob_piece<false, false>(w, 16, bias, base_r, fsum_s, sixth, p_top, ph, pl);
-              else guard = prob_piece<true, true>(w, cnt, bias, base_r, fsum_s, sixth, p_top, ph, pl);
-              const bool redo = __any_sync(0xffffffffu, (guard & 0x7f800000u) != 0u);
+              const uint32_t guard = prob_piece(w, bias, base_r, fsum_s, sixth, ph, pl);
+              bool redo = (guard & 0x7f800000u) != 0u;
+              if (cnt < 16) {     // ragged piece: keys beyond n have probability 0 and no say in the guard
+#pragma unroll
+                for (int x = 0; x < 4; ++x) {
+                  const int left = cnt - 4 * x;
+                  const uint32_t m = left >= 4 ? 0xffffffffu : (left <= 0 ? 0u : (1u << (8 * left)) - 1u);
+                  ph[x] &= m;
+                  pl[x] &= m;
+                }
+              }
+              if (peakw && k_top == 0) {   // this row's maximum (index byte 0xff, unique): probability 2^15, not 2^14
+#pragma unroll
+                for (int x = 0; x < 4; ++x) {
+                  const uint32_t top = bytes_ff(w[x] + bias), fill = (top >> 7) * 255u;
+                  ph[x] = (ph[x] & ~fill) | top;
+                  pl[x] &= ~fill;
+                }
+              }
+              redo = __any_sync(0xffffffffu, redo);
               if (redo || kDump) {
                 // redo (rare): some element within 2^-20 of a step of the code function: all elements of the piece again
                 // with the exact IEEE-division formula
                 const int col = 32 * c + 16 * h;
                 int8_t* dsc = kDump ? a.dump_scores + ((int64_t)item * n + row) * n + col : nullptr;
                 uint8_t* dsm = kDump ? a.dump_softmax + ((int64_t)item * n + row) * n + col : nullptr;
-#pragma unroll 1
+#pragma unroll
                 for (int x = 0; x < 4; ++x) {
                   uint32_t p4[4];
-                  const uint32_t wx = x == 0 ? w[0] : (x == 1 ? w[1] : (x == 2 ? w[2] : w[3]));
-                  const uint32_t px_l = x == 0 ? pl[0] : (x == 1 ? pl[1] : (x == 2 ? pl[2] : pl[3]));
-                  const uint32_t px_h = x == 0 ? ph[0] : (x == 1 ? ph[1] : (x == 2 ? ph[2] : ph[3]));
 #pragma unroll
                   for (int e = 0; e < 4; ++e) {
-                    const int g = (int)((wx >> (8 * e)) & 0xffu);
+                    const int g = (int)((w[x] >> (8 * e)) & 0xffu);
                     const int j = 4 * x + e;
                     if (redo) p4[e] = j < cnt ? tc_exact_prob16(fsum, s.lut[cmaxb - min(g, cmaxb)]) : 0u;
-                    else p4[e] = ((px_l >> (8 * e)) & 0xffu) | (((px_h >> (8 * e)) & 0xffu) << 8);
+                    else p4[e] = ((pl[x] >> (8 * e)) & 0xffu) | (((ph[x] >> (8 * e)) & 0xffu) << 8);
                     if (kDump && valid && j < cnt) {
                       dsc[j] = (int8_t)(g - 128);
                       dsm[j] = (uint8_t)(p4[e] ? __clz(p4[e]) - 16 : 16);
@@ -611,10 +626,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_co
                   }
                   if (redo) {
                     const uint32_t a01 = p4[0] | (p4[1] << 16), a23 = p4[2] | (p4[3] << 16);
-                    const uint32_t nl = __byte_perm(a01, a23, 0x6420), nh = __byte_perm(a01, a23, 0x7531);
-#pragma unroll
-                    for (int y = 0; y < 4; ++y)
-                      if (y == x) { pl[y] = nl; ph[y] = nh; }
+                    pl[x] = __byte_perm(a01, a23, 0x6420);
+                    ph[x] = __byte_perm(a01, a23, 0x7531);
                   }
                 }
               }
