@@ -134,8 +134,13 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 // two adjacent outputs: the operations whose operands are registers anyway go through the packed instructions, the
-// polynomial keeps the scalar immediate-operand FFMA form
-__device__ __forceinline__ void gelu_code_fast2(const float (&y)[2], const float (&half_rso)[2], bool& ok, float (&tq)[2]) {
+// polynomial keeps the scalar immediate-operand FFMA form.  tq: the value on the output grid; lo / hi: the same moved
+// down / up by the error bound 1.5e-6 |0.5 y rso|.  The caller packs lo and hi to int8 codes: where they agree no
+// rounding boundary (and no saturation edge) lies inside the bound, so the reference expression rounds to that code
+// too; where they differ the element is redone with gelu_erf.  (The first version tested |tq - RNE(tq)| against the
+// bound per element: five instructions per output against 1.75 for the two extra FFMA2 halves, the second pack and
+// the word compare.)
+__device__ __forceinline__ void gelu_code_fast2(const float (&y)[2], const float (&half_rso)[2], float (&lo)[2], float (&hi)[2]) {
   const float2 y2 = make_float2(y[0], y[1]);
   const float2 x2 = fmul2(y2, make_float2(0.70710678118654752440f, 0.70710678118654752440f));
   float e[2];
@@ -154,11 +159,11 @@ __device__ __forceinline__ void gelu_code_fast2(const float (&y)[2], const float
   }
   const float2 hr = fmul2(y2, make_float2(half_rso[0], half_rso[1]));
   const float2 t2 = ffma2(hr, make_float2(e[0], e[1]), hr);
-  const float2 rr = fadd2(fadd2(t2, make_float2(12582912.0f, 12582912.0f)), make_float2(-12582912.0f, -12582912.0f));
-  const float2 df = ffma2(rr, make_float2(-1.0f, -1.0f), t2);   // tq - RNE(tq), exact
-  ok = ok & (fabsf(fabsf(df.x) - 0.5f) >= fmul(fabsf(hr.x), 1.5e-6f)) & (fabsf(fabsf(df.y) - 0.5f) >= fmul(fabsf(hr.y), 1.5e-6f));
-  tq[0] = t2.x;
-  tq[1] = t2.y;
+  const float2 ah = make_float2(fabsf(hr.x), fabsf(hr.y));
+  const float2 l2 = ffma2(ah, make_float2(-1.5e-6f, -1.5e-6f), t2);
+  const float2 h2 = ffma2(ah, make_float2(1.5e-6f, 1.5e-6f), t2);
+  lo[0] = l2.x; lo[1] = l2.y;
+  hi[0] = h2.x; hi[1] = h2.y;
 }
 
 // Epilogue of 16 consecutive columns of one output row (one thread).  ch: this accumulator stage's
@@ -223,16 +228,18 @@ __device__ __forceinline__ void epilogue16(const uint32_t (&acc)[16], const floa
       for (int e = 0; e < 4; ++e) y4[e] = gelu_erf(y4[e]);
     }
     if (kGeluPot) {
-      bool ok = true;
+      float lo4[4], hi4[4];
 #pragma unroll
       for (int e = 0; e < 4; e += 2) {   // rso[] holds rso / 2 here
         const float yy[2] = {y4[e], y4[e + 1]}, hh[2] = {rso[e], rso[e + 1]};
-        float tt[2];
-        gelu_code_fast2(yy, hh, ok, tt);
-        r4[e] = tt[0];
-        r4[e + 1] = tt[1];
+        float l2[2], h2[2];
+        gelu_code_fast2(yy, hh, l2, h2);
+        lo4[e] = l2[0]; lo4[e + 1] = l2[1];
+        hi4[e] = h2[0]; hi4[e + 1] = h2[1];
+        r4[e] = h2[0];
+        r4[e + 1] = h2[1];
       }
-      if (!ok) {
+      if (pack_sat4(lo4[0], lo4[1], lo4[2], lo4[3]) != pack_sat4(hi4[0], hi4[1], hi4[2], hi4[3])) {   // rare (~1e-3 of the groups)
 #pragma unroll
         for (int e = 0; e < 4; ++e) r4[e] = fmul(gelu_erf(y4[e]), fmul(rso[e], 2.0f));
       }
@@ -791,12 +798,16 @@ __global__ void gelu_fast_sweep_kernel(float rso, unsigned long long* __restrict
   for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < (1ull << 31); i += stride) {
     const float yy[2] = {__uint_as_float((uint32_t)(2 * i)), __uint_as_float((uint32_t)(2 * i + 1))};
     const float hh[2] = {0.5f * rso, 0.5f * rso};
-    bool ok = true;   // shared by the pair, as in the epilogue: a rejected partner sends both to the reference path
-    float tq[2];
-    gelu_code_fast2(yy, hh, ok, tq);
+    float lo[2], tq[2];
+    gelu_code_fast2(yy, hh, lo, tq);
+    // accepted as the epilogue accepts: the low and the high end of the error interval pack to the same codes (the
+    // epilogue compares groups of four; a pair here is at least as strict per element)
+    const bool ok = pack_sat4(lo[0], lo[1], 0.f, 0.f) == pack_sat4(tq[0], tq[1], 0.f, 0.f);
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
-      if (!isfinite(yy[k])) continue;
+      // |y| < 2^64: far beyond any |acc| < 2^31 times a scale below 1 plus a bias; above it 0.5 y rso can overflow to
+      // infinity, whose error interval is not a number
+      if (!isfinite(yy[k]) || fabsf(yy[k]) >= 1.8446744e19f) continue;
       const float ref = fmul(gelu_erf(yy[k]), rso);
       const int cf = max(-128, min(127, __float2int_rn(fminf(fmaxf(tq[k], -1e6f), 1e6f))));
       const int cr = max(-128, min(127, __float2int_rn(fminf(fmaxf(ref, -1e6f), 1e6f))));
