@@ -9,6 +9,8 @@ from .ptq import BIT_TYPE_DICT, BIT_TYPE_LIST, BitType, QAct, QConv2d, QIntLayer
 from .vit_fquant import (Attention, Block, VisionTransformer, deit_base_patch16_224, deit_small_patch16_224,
                          deit_tiny_patch16_224, vit_base_patch16_224, vit_large_patch16_224)
 from .layers_quant import Mlp, PatchEmbed
+from .swin_quant import (SwinTransformer, swin_base_patch4_window7_224, swin_small_patch4_window7_224,
+                         swin_tiny_patch4_window7_224)
 
 _MODELS = {
     'deit_tiny': deit_tiny_patch16_224,
@@ -16,11 +18,14 @@ _MODELS = {
     'deit_base': deit_base_patch16_224,
     'vit_base': vit_base_patch16_224,
     'vit_large': vit_large_patch16_224,
+    'swin_tiny': swin_tiny_patch4_window7_224,
+    'swin_small': swin_small_patch4_window7_224,
+    'swin_base': swin_base_patch4_window7_224,
 }
 
 
 def str2model(name):
-    """reference: test_quant.py:56-68 (Swin entries are an extension not built yet)."""
+    """reference: test_quant.py:56-68."""
     return _MODELS[name]
 
 
