@@ -162,8 +162,10 @@ static int bind(p2v_vit* h, int b, void* ws) {
   if ((rc = make_tmap_kmajor(&h->tm_cls, h->cls, b, D, D))) return rc;
   h->bound_b = b;
   h->bound_ws = ws;
-  for (auto& e : h->graphs) cudaGraphExecDestroy(e.exec);   // tensor maps changed: captured launches are stale
-  h->graphs.clear();
+  // Captured graphs of other (batch, workspace) bindings stay valid: a captured launch carries its tensor maps by value
+  // (__grid_constant__ kernel parameters) and its buffers by address, and the cache is keyed on (x, logits, codes,
+  // batch, workspace).  A validation loop whose last batch is shorter, or two alternating batch sizes, re-binds here
+  // without throwing the other binding's graphs away.
   return P2V_OK;
 }
 
@@ -383,7 +385,7 @@ static int forward_impl(p2v_vit* h, const float* x, const U8Input* u8, float* lo
       set_error("cudaGraphInstantiate failed: %s", cudaGetErrorString(ce));
       return P2V_ERR_CUDA;
     }
-    if (h->graphs.size() >= 8) {
+    if (h->graphs.size() >= 16) {
       cudaGraphExecDestroy(h->graphs.front().exec);
       h->graphs.erase(h->graphs.begin());
     }

@@ -214,8 +214,17 @@ class IntegerEngine:
     def forward(self, x, bit_config):
         """Drop-in: fp32 logits [B, classes] on x's device (host inputs are copied to the GPU and back)."""
         on_host = not x.is_cuda
-        xd = x.to(self.device, non_blocking=True) if on_host else x
-        out = self.forward_into(xd, bit_config).clone()
+        bp = self.bound(bit_config)
+        self._check_input(x, bp.plan.arch)
+        # the caller's tensor lives at a new address on most calls; the captured graph is keyed on its input address,
+        # so the batch is copied into an engine-owned staging buffer (one per batch size) and the graph is replayed,
+        # instead of paying a stream capture + instantiation (milliseconds on the host) per call
+        key = ('xstage', x.shape[0])
+        if key not in bp._buffers:
+            bp._buffers[key] = torch.empty(tuple(x.shape), dtype=torch.float32, device=self.device)
+        stage = bp._buffers[key]
+        stage.copy_(x, non_blocking=True)
+        out = self.forward_into(stage, bit_config).clone()
         return out.cpu() if on_host else out
 
     def forward_dump(self, x, bit_config):
