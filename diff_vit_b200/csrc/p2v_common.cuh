@@ -122,7 +122,7 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity
         : "r"(smem_u32(bar)), "r"(parity)
         : "memory");
     if (done) break;
-    __nanosleep(128);
+    __nanosleep(512);
   }
 }
 
