@@ -63,6 +63,7 @@ SYMBOLS = {
     'p2v_gemm_i8': (C.c_int, [_vp, C.c_int64, _vp, _vp, C.c_int64, C.c_int, C.c_int, C.c_int, C.POINTER(Epilogue), _vp]),
     'p2v_gemm_i8_simt': (C.c_int, [_vp, C.c_int64, _vp, _vp, C.c_int64, C.c_int, C.c_int, C.c_int, C.POINTER(Epilogue), _vp]),
     'p2v_gemm_set_mode': (C.c_int, [C.c_int]),
+    'p2v_set_pdl': (C.c_int, [C.c_int]),
     'p2v_test_gelu_fast': (C.c_int, [C.c_float, _vp, _vp]),
     'p2v_gemm_i8_acc': (C.c_int, [_vp, C.c_int64, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp]),
     'p2v_quant_patchify': (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, _vp]),
@@ -114,6 +115,8 @@ def lib():
             fn = getattr(handle, name)
             fn.restype = res
             fn.argtypes = args
+        if os.environ.get('P2V_PDL') is not None:   # A/B hook, see p2v_set_pdl in include/p2v.h
+            handle.p2v_set_pdl(int(os.environ['P2V_PDL']))
         _lib = handle
     return _lib
 

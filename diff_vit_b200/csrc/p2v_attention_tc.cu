@@ -329,6 +329,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_co
   uint8_t* const stage_ptr[2] = {win + a0, win + kRegionCAddr};
   uint8_t* const ostage = win + a0 + kOffOstage;
   TcTail& s = *reinterpret_cast<TcTail*>(win + kRegionCAddr + kStageBytes);
+  pdl_launch_dependents();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n = a.n;
   const int ntiles = n > 128 ? 2 : 1;
@@ -384,6 +385,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_co
   }
   __syncthreads();
   tc_fence_after_sync();
+  pdl_wait();   // tables, barriers and the TMEM bias above are static; q / k / v are the previous kernel's output
 
   if (warp == kTcProducerWarp) {
     // ---- TMA producer -----------------------------------------------------------------------------------------------
@@ -790,9 +792,9 @@ int attention_tc_launch(const int8_t* qkv, int8_t* out, int b, int n, int heads,
   a.skew = g_tc_skew;
   const int grid = a.items < kNumSMs ? a.items : kNumSMs;
   if (p->dump_scores != nullptr)
-    attention_tc_kernel<true><<<grid, kTcThreads, kTcSmemBytes, st>>>(tq128, tq32, tq16, tk, tv, to, a);
+    P2V_CHECK_CUDA(launch_pdl(4, attention_tc_kernel<true>, dim3(grid), dim3(kTcThreads), kTcSmemBytes, st, tq128, tq32, tq16, tk, tv, to, a));
   else
-    attention_tc_kernel<false><<<grid, kTcThreads, kTcSmemBytes, st>>>(tq128, tq32, tq16, tk, tv, to, a);
+    P2V_CHECK_CUDA(launch_pdl(4, attention_tc_kernel<false>, dim3(grid), dim3(kTcThreads), kTcSmemBytes, st, tq128, tq32, tq16, tk, tv, to, a));
   P2V_CHECK_CUDA(cudaGetLastError());
   return P2V_OK;
 }

@@ -41,6 +41,50 @@ inline bool needs_configure(const unsigned long long& done, int* device) {
 }
 inline void mark_configured(unsigned long long& done, int device) { done |= 1ull << (device & 63); }
 
+// ---- programmatic dependent launch -----------------------------------------------------------------
+// The forward is ~90 dependent launches on one stream.  With full stream serialisation every boundary costs the
+// drain of the previous grid plus the next kernel's own prologue (barrier init, TMEM allocation, tensor-map
+// prefetch, per-channel constants, softmax tables: 2-4 us of a 25-120 us kernel, most of a 10 us one).  Launched
+// with cudaLaunchAttributeProgrammaticStreamSerialization a kernel's CTAs may be placed on SMs the previous grid has
+// already left; they run their prologue - which touches only static data - and block in pdl_wait() until the
+// previous grid has completed and its writes are visible.  Every kernel launched this way calls
+// pdl_launch_dependents() first thing and pdl_wait() before its first access to activations.  Inside a captured
+// graph the attribute becomes a programmatic edge.  p2v_set_pdl(0) turns the attribute off (test hook).
+bool pdl_enabled(int kind);   // kind: 1 = GEMM, 2 = LayerNorm, 4 = attention (bits of p2v_set_pdl)
+#if defined(__CUDACC__)
+template <class... KArgs, class... Args>
+inline cudaError_t launch_pdl(int kind, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled(kind) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// Loads of activations in such kernels: never __ldg.  ld.global.nc promises data that is constant for the kernel's
+// lifetime - which now overlaps the producer's - and, worse, the compiler treats it as an invariant load that it may
+// hoist above pdl_wait() (seen: LayerNorm read rows the previous GEMM had not written yet).  These are volatile, so
+// they keep their order relative to the wait, and go through L2 only (the data is read once).
+__device__ __forceinline__ uint32_t ld_act_u32(const void* p) {
+  uint32_t v;
+  asm volatile("ld.global.u32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ uint4 ld_act_v4(const void* p) {
+  uint4 v;
+  asm volatile("ld.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+#endif
+
 #if defined(__CUDACC__)
 // ---- small device helpers ------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {

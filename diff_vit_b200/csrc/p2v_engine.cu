@@ -26,6 +26,9 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+static int g_pdl = 7;
+bool pdl_enabled(int kind) { return (g_pdl & kind) != 0; }
+
 int make_tmap_kmajor(CUtensorMap* map, const void* ptr, int64_t rows, int64_t k, int64_t ld);
 int gemm_configure();
 int attention_configure_once();
@@ -266,6 +269,11 @@ static int run(p2v_vit* h, const float* x, float* logits, int8_t* logit_codes, i
 }
 
 extern "C" const char* p2v_last_error(void) { return g_error; }
+
+extern "C" int p2v_set_pdl(int enabled) {
+  g_pdl = enabled;
+  return P2V_OK;
+}
 extern "C" int p2v_version(void) { return 100; }
 
 extern "C" int p2v_check_device(int device) {

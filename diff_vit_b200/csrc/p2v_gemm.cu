@@ -210,7 +210,7 @@ __device__ __forceinline__ void epilogue16(const uint32_t (&acc)[16], const floa
     if (res_staged != nullptr) {
       resw[0] = res_staged->x; resw[1] = res_staged->y; resw[2] = res_staged->z; resw[3] = res_staged->w;
     } else if (vec) {
-      const uint4 r4 = __ldg(reinterpret_cast<const uint4*>(g.epi.residual + off));
+      const uint4 r4 = ld_act_v4(g.epi.residual + off);
       resw[0] = r4.x; resw[1] = r4.y; resw[2] = r4.z; resw[3] = r4.w;
     } else {
 #pragma unroll
@@ -398,7 +398,7 @@ __device__ __forceinline__ void epilogue_block(const uint32_t (&v0)[16], const u
       const int idx = tq + 128 * i, rr = idx >> 3, ck = idx & 7;
       uint4 v = make_uint4(0, 0, 0, 0);
       if (row0 + rr < g.m && col0 + ck * 16 < g.n)
-        v = __ldg(reinterpret_cast<const uint4*>(g.epi.residual + (int64_t)(row0 + rr) * g.ld_out + col0 + ck * 16));
+        v = ld_act_v4(g.epi.residual + (int64_t)(row0 + rr) * g.ld_out + col0 + ck * 16);
       *reinterpret_cast<uint4*>(stage + rr * kStagePitch + ck * 16) = v;
     }
     quarter_barrier(quarter);
@@ -440,13 +440,13 @@ template <uint32_t FLAGS>
 __device__ __forceinline__ bool prefetch_residual16(const GemmArgs& g, int row, int col, uint4& r) {
   if ((FLAGS & EPI_PLAIN) && (FLAGS & EPI_RESIDUAL)) {
     if (row >= g.m) return false;
-    r = __ldg(reinterpret_cast<const uint4*>(g.epi.residual + (int64_t)row * g.ld_out + col));
+    r = ld_act_v4(g.epi.residual + (int64_t)row * g.ld_out + col);
     return true;
   }
   if (!(FLAGS & EPI_RESIDUAL) || row >= g.m || col + 16 > g.n || (g.ld_out & 15) != 0 || (col & 15) != 0 ||
       (reinterpret_cast<uintptr_t>(g.epi.residual) & 15) != 0)
     return false;
-  r = __ldg(reinterpret_cast<const uint4*>(g.epi.residual + (int64_t)row * g.ld_out + col));
+  r = ld_act_v4(g.epi.residual + (int64_t)row * g.ld_out + col);
   return true;
 }
 
@@ -458,8 +458,8 @@ __device__ __forceinline__ bool prefetch_residual(const GemmArgs& g, int row, in
       (reinterpret_cast<uintptr_t>(g.epi.residual) & 15) != 0)
     return false;
   const uint4* rp = reinterpret_cast<const uint4*>(g.epi.residual + (int64_t)row * g.ld_out + col);
-  r0 = __ldg(rp);
-  r1 = __ldg(rp + 1);
+  r0 = ld_act_v4(rp);
+  r1 = ld_act_v4(rp + 1);
   return true;
 }
 
@@ -481,6 +481,7 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   // align by pointer arithmetic, not through an integer: the compiler then still knows these are shared-memory
   // addresses (LDS / STS instead of generic LD / ST plus window-base arithmetic on every epilogue constant load)
   GemmSmem& s = *reinterpret_cast<GemmSmem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
+  pdl_launch_dependents();
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int tiles_m = (g.m + kBlockM - 1) / kBlockM;
@@ -512,6 +513,7 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   // Tiles are walked n-fastest so that CTAs running at the same time share A tiles through L2.
   if (warp == 0) {
     if (elect_one()) {
+      pdl_wait();   // A is the previous kernel's output
       uint32_t stage = 0, phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int m0 = (tile / tiles_n) * kBlockM, n0 = (tile % tiles_n) * kBlockN;
@@ -563,6 +565,7 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       load_channels<FLAGS, kChanCols>(s.chan, g.epi, 0, g.n, etid);
       asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
     }
+    pdl_wait();   // residual codes are read, and out may still be read by the previous kernel
     uint32_t acc = 0, acc_phase = 0;
     uint32_t stage_turn = 0;   // which of the quarter's two staging tiles the next block uses
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -664,6 +667,7 @@ gemm_i8_bs_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                   const GemmArgs g, const BsPlan plan) {
   extern __shared__ uint8_t smem_raw[];
   BsSmem& s = *reinterpret_cast<BsSmem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
+  pdl_launch_dependents();
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int tiles_m = (g.m + kBlockM - 1) / kBlockM;
@@ -708,6 +712,7 @@ gemm_i8_bs_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         mbar_expect_tx(&s.b_full, (uint32_t)(num_kb * nsub * kTileBytes));
         for (int kb = 0; kb < num_kb; ++kb)
           for (int h = 0; h < nsub; ++h) tma_load_2d(s.b[kb][h], &tmap_b, &s.b_full, kb * kBlockK, n0 + h * kBlockN);
+        pdl_wait();   // the weights above are static; A is the previous kernel's output
         uint32_t stage = 0, phase = 0;
         for (int tile = local; tile < tiles_m; tile += cnt) {
           for (int kb = 0; kb < num_kb; ++kb) {
@@ -748,6 +753,7 @@ gemm_i8_bs_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       const int quarter = ew & 3, cgroup = ew >> 2;
       load_channels<FLAGS, kBsSlabCols>(s.chan, g.epi, n0, g.n, (int)threadIdx.x - 128);
       asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+      pdl_wait();   // residual codes are read, and out may still be read by the previous kernel
       uint32_t it = 0;
       uint32_t stage_turn = 0;   // which of the quarter's two staging tiles the next block uses
       const bool staged = can_stage<FLAGS>(g);
@@ -997,13 +1003,11 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArg
   BsPlan plan;
   // weight-stationary pays off once every CTA re-uses its slab for several row tiles
   if (g_gemm_mode != 1 && (g_gemm_mode == 2 || tiles >= 2 * kNumSMs) && make_bs_plan(g.n, g.k, kNumSMs, &plan)) {
-    gemm_i8_bs_kernel<FLAGS><<<kNumSMs, kGemmThreads, kBsSmemBytes, st>>>(ta, tb, g, plan);
-    P2V_CHECK_CUDA(cudaGetLastError());
+    P2V_CHECK_CUDA(launch_pdl(1, gemm_i8_bs_kernel<FLAGS>, dim3(kNumSMs), dim3(kGemmThreads), kBsSmemBytes, st, ta, tb, g, plan));
     return P2V_OK;
   }
   const int grid = tiles < kNumSMs ? tiles : kNumSMs;
-  gemm_i8_tc_kernel<FLAGS><<<grid, kGemmThreads, smem, st>>>(ta, tb, g);
-  P2V_CHECK_CUDA(cudaGetLastError());
+  P2V_CHECK_CUDA(launch_pdl(1, gemm_i8_tc_kernel<FLAGS>, dim3(grid), dim3(kGemmThreads), smem, st, ta, tb, g));
   return P2V_OK;
 }
 

@@ -235,6 +235,7 @@ template <int G, bool FULL, bool DUMP>
 __global__ void __launch_bounds__(256, 2)
 layernorm_int_pot_kernel(const int8_t* __restrict__ in, int64_t in_row_stride, int8_t* __restrict__ out,
                          int32_t* __restrict__ ln_codes, int rows, int d, const p2v_layernorm p) {
+  pdl_launch_dependents();
   const int lane = threadIdx.x & 31;
   const int warps_total = gridDim.x * (blockDim.x >> 5);
   const int groups = d >> 2;
@@ -260,13 +261,14 @@ layernorm_int_pot_kernel(const int8_t* __restrict__ in, int64_t in_row_stride, i
     }
   }
   const float scale_over_c = fdiv(p.in_scale1, (float)d);   // row-independent part of ln_row_stats
+  pdl_wait();   // everything above is static; the rows are the previous kernel's output
   // software pipeline: the next row's codes are in flight while this row is normalised
   uint32_t next_w[G];
   int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
 #pragma unroll
   for (int g = 0; g < G; ++g) {
     const int grp = g * 32 + lane;
-    next_w[g] = (row < rows && (FULL || grp < groups)) ? __ldg(reinterpret_cast<const uint32_t*>(in + (int64_t)row * in_row_stride + grp * 4)) : 0u;
+    next_w[g] = (row < rows && (FULL || grp < groups)) ? ld_act_u32(in + (int64_t)row * in_row_stride + grp * 4) : 0u;
   }
   for (; row < rows; row += warps_total) {
     uint32_t cur_w[G];
@@ -275,7 +277,7 @@ layernorm_int_pot_kernel(const int8_t* __restrict__ in, int64_t in_row_stride, i
     for (int g = 0; g < G; ++g) {
       const int grp = g * 32 + lane;
       cur_w[g] = next_w[g];
-      next_w[g] = (nrow < rows && (FULL || grp < groups)) ? __ldg(reinterpret_cast<const uint32_t*>(in + (int64_t)nrow * in_row_stride + grp * 4)) : 0u;
+      next_w[g] = (nrow < rows && (FULL || grp < groups)) ? ld_act_u32(in + (int64_t)nrow * in_row_stride + grp * 4) : 0u;
     }
     float xq[G][4];
     int sum = 0, sumsq = 0;   // |x| <= 1024, d <= 128 G: per-lane partial sums stay far below 2^31; padded groups add 0
@@ -495,10 +497,10 @@ extern "C" int p2v_layernorm_int(const int8_t* in, int64_t in_row_stride, int8_t
 #define P2V_LN_LAUNCH(G_)                                                                                          \
   do {                                                                                                             \
     const bool full = d == 128 * (G_);                                                                             \
-    if (full && ln_codes) layernorm_int_pot_kernel<G_, true, true><<<pgrid, warps * 32, 0, st>>>(in, in_row_stride, out, ln_codes, rows, d, *p);        \
-    else if (full) layernorm_int_pot_kernel<G_, true, false><<<pgrid, warps * 32, 0, st>>>(in, in_row_stride, out, ln_codes, rows, d, *p);            \
-    else if (ln_codes) layernorm_int_pot_kernel<G_, false, true><<<pgrid, warps * 32, 0, st>>>(in, in_row_stride, out, ln_codes, rows, d, *p);        \
-    else layernorm_int_pot_kernel<G_, false, false><<<pgrid, warps * 32, 0, st>>>(in, in_row_stride, out, ln_codes, rows, d, *p);                     \
+    if (full && ln_codes) P2V_CHECK_CUDA(launch_pdl(2, layernorm_int_pot_kernel<G_, true, true>, dim3(pgrid), dim3(warps * 32), 0, st, in, in_row_stride, out, ln_codes, rows, d, *p));        \
+    else if (full) P2V_CHECK_CUDA(launch_pdl(2, layernorm_int_pot_kernel<G_, true, false>, dim3(pgrid), dim3(warps * 32), 0, st, in, in_row_stride, out, ln_codes, rows, d, *p));            \
+    else if (ln_codes) P2V_CHECK_CUDA(launch_pdl(2, layernorm_int_pot_kernel<G_, false, true>, dim3(pgrid), dim3(warps * 32), 0, st, in, in_row_stride, out, ln_codes, rows, d, *p));        \
+    else P2V_CHECK_CUDA(launch_pdl(2, layernorm_int_pot_kernel<G_, false, false>, dim3(pgrid), dim3(warps * 32), 0, st, in, in_row_stride, out, ln_codes, rows, d, *p));                     \
   } while (0)
     if (groups == 1) P2V_LN_LAUNCH(1);
     else if (groups == 2) P2V_LN_LAUNCH(2);

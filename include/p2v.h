@@ -70,6 +70,11 @@ int p2v_gemm_i8_simt(const int8_t* a, int64_t lda, const int8_t* w, int8_t* out,
 /* Kernel selection for p2v_gemm_i8 (test hook): 0 = automatic, 1 = operand-streaming kernel only,
  * 2 = weight-stationary kernel whenever k <= 384. */
 int p2v_gemm_set_mode(int mode);
+/* Programmatic dependent launch of the GEMM, LayerNorm and attention kernels (on by default): a kernel's CTAs may be
+ * placed, and run their prologue, while the previous kernel of the stream drains; they wait for its completion before
+ * touching activations (csrc/p2v_common.cuh launch_pdl).  0 restores fully serialised launches (test / A-B hook;
+ * graphs captured earlier keep the setting they were captured with). */
+int p2v_set_pdl(int enabled);
 /* Test hook: sweeps all 2^32 fp32 inputs through the fc1 epilogue's fast erf-GELU (csrc/p2v_gemm.cu gelu_code_fast2)
  * for one power-of-two 1/s_out and accumulates into counts[3] (device, pre-zeroed): accepted elements whose int8
  * code differs from RNE(gelu_erf(y) / s_out) - must stay 0 -, guard rejections and inputs among |y| < 8. */
