@@ -9,6 +9,7 @@ from .ptq import BIT_TYPE_DICT, BIT_TYPE_LIST, BitType, QAct, QConv2d, QIntLayer
 from .vit_fquant import (Attention, Block, VisionTransformer, deit_base_patch16_224, deit_small_patch16_224,
                          deit_tiny_patch16_224, vit_base_patch16_224, vit_large_patch16_224)
 from .layers_quant import Mlp, PatchEmbed
+from .weights import build_model, load_weights_from_npz
 from .swin_quant import (SwinTransformer, swin_base_patch4_window7_224, swin_small_patch4_window7_224,
                          swin_tiny_patch4_window7_224)
 

@@ -343,22 +343,25 @@ class VisionTransformer(nn.Module):
         return all(b != -1 for b in bit_config)
 
 
-def _factory(embed_dim, depth, num_heads, input_quant=True):
+def _factory(short_name, embed_dim, depth, num_heads, input_quant=True):
     def build(pretrained=False, quant=False, calibrate=False, cfg=None, **kwargs):
+        """pretrained: False, True (the reference's checkpoint, taken from the torch hub cache: nothing is downloaded)
+        or the path of a .pth / .npz checkpoint (weights.load_pretrained)."""
+        model = VisionTransformer(patch_size=16, embed_dim=embed_dim, depth=depth, num_heads=num_heads,
+                                  mlp_ratio=4, qkv_bias=True, norm_layer=partial(QIntLayerNorm, eps=1e-6),
+                                  quant=quant, calibrate=calibrate, input_quant=input_quant, cfg=cfg, **kwargs)
         if pretrained:
-            raise RuntimeError('pretrained checkpoints need network access (torch.hub / GCS); '
-                               'load a state_dict with the reference key names instead')
-        return VisionTransformer(patch_size=16, embed_dim=embed_dim, depth=depth, num_heads=num_heads,
-                                 mlp_ratio=4, qkv_bias=True, norm_layer=partial(QIntLayerNorm, eps=1e-6),
-                                 quant=quant, calibrate=calibrate, input_quant=input_quant, cfg=cfg, **kwargs)
+            from .weights import load_pretrained
+            load_pretrained(model, short_name, pretrained)
+        return model
     return build
 
 
 # reference: models/vit_fquant.py:802-933
-deit_tiny_patch16_224 = _factory(192, 12, 3)
-deit_small_patch16_224 = _factory(384, 12, 6)
-deit_base_patch16_224 = _factory(768, 12, 12)
-vit_base_patch16_224 = _factory(768, 12, 12)
-vit_large_patch16_224 = _factory(1024, 24, 16, input_quant=False)
+deit_tiny_patch16_224 = _factory('deit_tiny', 192, 12, 3)
+deit_small_patch16_224 = _factory('deit_small', 384, 12, 6)
+deit_base_patch16_224 = _factory('deit_base', 768, 12, 12)
+vit_base_patch16_224 = _factory('vit_base', 768, 12, 12)
+vit_large_patch16_224 = _factory('vit_large', 1024, 24, 16, input_quant=False)
 for _n in __all__:
     globals()[_n].__name__ = _n
