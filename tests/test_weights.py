@@ -89,3 +89,21 @@ def test_build_model_alias(tmp_path, monkeypatch):
         dv.build_model('resnet50', Pretrained=False)
     with pytest.raises(RuntimeError, match='never downloads'):
         dv.build_model('deit_small_patch16_224')         # Pretrained=True is the reference's default
+
+
+def test_model_dequant_clears_what_the_reference_clears(micro_golden):
+    """model_dequant() (reference: models/vit_fquant.py:680-683) clears `quant` on QConv2d / QLinear / QAct /
+    QIntSoftmax and nothing else: QIntLayerNorm stays in 'int' mode, as in the reference.  Here it must also switch the
+    fused engine off, and model_quant() must bring everything back."""
+    from conftest import build_micro
+    model = build_micro(micro_golden)
+    dv.calibrate_model(model, [torch.from_numpy(micro_golden['x_calib'])])
+    flagged = [m for m in model.modules() if isinstance(m, (dv.QConv2d, dv.QLinear, dv.QAct, dv.QIntSoftmax))]
+    norms = [m for m in model.modules() if isinstance(m, dv.QIntLayerNorm)]
+    assert model._int_active and all(m.quant for m in flagged) and all(m.mode == 'int' for m in norms)
+    model.model_dequant()
+    assert not model._int_active and model._engine is None
+    assert not any(m.quant for m in flagged)
+    assert all(m.mode == 'int' for m in norms)
+    model.model_quant()
+    assert model._int_active and all(m.quant for m in flagged)
