@@ -20,6 +20,7 @@
 
 #include "p2v_common.cuh"
 #include "p2v_math.cuh"
+#include "p2v_requant.cuh"
 
 namespace p2v {
 
@@ -58,62 +59,6 @@ struct GemmArgs {
   p2v_epilogue epi;
   int32_t* raw_acc;  // test hook: dump accumulators instead of codes
 };
-
-// RNE + saturate + pack of four fp32 values into four int8 (two F2IP.S8.F32 on sm_100)
-__device__ __forceinline__ uint32_t pack_sat4(float v0, float v1, float v2, float v3) {
-  // cvt.pack d, a, b, c: d[7:0] = sat(b), d[15:8] = sat(a), d[31:16] = c[15:0]
-  uint32_t hi, r;
-  const int i0 = __float2int_rn(v0), i1 = __float2int_rn(v1), i2 = __float2int_rn(v2), i3 = __float2int_rn(v3);
-  asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(hi) : "r"(i3), "r"(i2), "r"(0));
-  asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(i1), "r"(i0), "r"(hi));
-  return r;
-}
-
-// RNE(fl(y / s) + zp), the unclamped code of a quantizer with a non-power-of-two scale, without paying an
-// IEEE division per element: t = y * fl(1/s) + zp is within a few ulp of the exact operand of the
-// rounding, so rint(t) can differ from the exact result only when t lies within kTieGuard of a
-// half-integer; only those elements (~0.02 %) take the exact division.  For |t| >= 512 both paths
-// saturate to the same int8 code, so the absolute guard is sufficient: below 128.5 the operand t = y * fl(1/s)
-// is within 1.5 ulp(128) = 2.3e-5 of the exactly divided one, and the guard is 5x that.
-constexpr float kTieGuard = 0.0001220703125f;  // 2^-13
-__device__ __noinline__ float div_round_exact(float y, float s, float zp) { return rintf(fadd(fdiv(y, s), zp)); }
-
-// Round-half-even on the FMA pipe: (t + 1.5 * 2^23) - 1.5 * 2^23 is RNE(t) for |t| < 2^22.  Larger |t| come back
-// as some large value of the same sign, which saturates to the same int8 code as RNE(t) would.  (FRND runs on
-// the conversion unit, which ncu showed ~40 % busy in every GEMM epilogue.)
-__device__ __forceinline__ float rne_small(float t) { return fsub(fadd(t, 12582912.0f), 12582912.0f); }
-__device__ __forceinline__ float div_round(float y, float s, float rs, float zp) {
-  const float t = fadd(fmul(y, rs), zp);
-  float r = rne_small(t);
-  if (fabsf(fabsf(fsub(t, r)) - 0.5f) < kTieGuard) r = div_round_exact(y, s, zp);   // rare: keeps the hot loop small
-  return r;
-}
-
-// Four at a time: the common path is branch-free so the four dependency chains interleave; one rarely
-// taken branch per group re-does the flagged elements exactly.
-__device__ __forceinline__ void div_round4(const float (&y)[4], const float (&s)[4], const float (&rs)[4], float zp,
-                                           float (&r)[4]) {
-  // element pairs on the packed fp32 instructions (each half rounds like the scalar _rn op)
-  const float2 zp2 = make_float2(zp, zp), kMagic = make_float2(12582912.0f, 12582912.0f);
-  const float2 kMagicNeg = make_float2(-12582912.0f, -12582912.0f), kNegOne = make_float2(-1.0f, -1.0f);
-  uint32_t flags = 0;
-#pragma unroll
-  for (int e = 0; e < 4; e += 2) {
-    // (a contraction of this mul + add into one fma moves t by at most one ulp, far inside the tie guard)
-    const float2 t = fadd2(fmul2(make_float2(y[e], y[e + 1]), make_float2(rs[e], rs[e + 1])), zp2);
-    const float2 rr = fadd2(fadd2(t, kMagic), kMagicNeg);      // rne_small
-    const float2 df = ffma2(rr, kNegOne, t);                       // t - r, exact
-    r[e] = rr.x;
-    r[e + 1] = rr.y;
-    flags |= (fabsf(fabsf(df.x) - 0.5f) < kTieGuard) ? (1u << e) : 0u;
-    flags |= (fabsf(fabsf(df.y) - 0.5f) < kTieGuard) ? (2u << e) : 0u;
-  }
-  if (flags) {
-#pragma unroll
-    for (int e = 0; e < 4; ++e)
-      if (flags & (1u << e)) r[e] = div_round_exact(y[e], s[e], zp);
-  }
-}
 
 __device__ __forceinline__ float clamp_code(float r) { return fminf(fmaxf(r, -128.f), 127.f); }
 
@@ -312,11 +257,22 @@ __device__ __forceinline__ void epilogue16(const uint32_t (&acc)[16], const floa
     }
   }
   if (!kPlain && !(FLAGS & EPI_RESIDUAL) && g.epi.out_f32 != nullptr) {
+    float* fo = g.epi.out_f32 + (int64_t)row * g.n + col0;
+    // n % 4 == 0 (the 1000-class head): whole float4 stores, 64 contiguous bytes per row instead of 16 scalar stores
+    // that each touch 32 rows (the head GEMM took 30 us of which 10 were these stores)
+    const bool f4 = ((g.n & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.epi.out_f32) & 15) == 0);
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      if (j < ncols) {
-        const float q = clamp_code(rintf(code[j]));
-        g.epi.out_f32[(int64_t)row * g.n + col0 + j] = fmul(fsub(q, g.epi.out_zp), ch[CH_SO][c + j]);
+    for (int j4 = 0; j4 < 16; j4 += 4) {
+      float f[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        f[e] = fmul(fsub(clamp_code(rintf(code[j4 + e])), g.epi.out_zp), ch[CH_SO][c + j4 + e]);
+      if (f4) {
+        if (j4 < ncols) *reinterpret_cast<float4*>(fo + j4) = make_float4(f[0], f[1], f[2], f[3]);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (j4 + e < ncols) fo[j4 + e] = f[e];
       }
     }
   }
@@ -326,6 +282,12 @@ __device__ __forceinline__ void epilogue16(const uint32_t (&acc)[16], const floa
                    pack_sat4(code[8], code[9], code[10], code[11]), pack_sat4(code[12], code[13], code[14], code[15]));
     if (out_staged != nullptr) *out_staged = packed;
     else *reinterpret_cast<uint4*>(g.out + off) = packed;
+  } else if (((g.ld_out | g.n) & 3) == 0 && (reinterpret_cast<uintptr_t>(g.out) & 3) == 0) {
+    // rows are only 4-byte aligned (n = 1000): packed words, ncols is a multiple of 4
+#pragma unroll
+    for (int j4 = 0; j4 < 16; j4 += 4)
+      if (j4 < ncols)
+        *reinterpret_cast<uint32_t*>(g.out + off + j4) = pack_sat4(code[j4], code[j4 + 1], code[j4 + 2], code[j4 + 3]);
   } else {
 #pragma unroll
     for (int j = 0; j < 16; ++j)

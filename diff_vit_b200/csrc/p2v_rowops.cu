@@ -3,6 +3,7 @@
 // All fp32 steps follow the reference's op order through p2v_math.cuh.
 #include "p2v_common.cuh"
 #include "p2v_math.cuh"
+#include "p2v_requant.cuh"
 
 namespace p2v {
 
@@ -30,23 +31,28 @@ __global__ void quant_patchify_kernel(const float* __restrict__ x, int8_t* __res
   const int k = c * p * p;
   const int w16 = w / 16;
   const float rs = __frcp_rn(scale);
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total16;
-       i += (int64_t)gridDim.x * blockDim.x) {
-    const int xs = (int)(i % w16);
-    int64_t r = i / w16;
-    const int y = (int)(r % h);
+  // 32-bit index arithmetic (total16 < 2^31 is checked at launch): three 64-bit divisions per 16 pixels cost more
+  // than the conversion of those pixels (ncu: 19 instructions per pixel before, most of them division sequences)
+  const int n16 = (int)total16;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += gridDim.x * blockDim.x) {
+    const int xs = i % w16;
+    int r = i / w16;
+    const int y = r % h;
     r /= h;
-    const int ch = (int)(r % c);
-    const int img = (int)(r / c);
+    const int ch = r % c;
+    const int img = r / c;
     const float4* src = reinterpret_cast<const float4*>(x + (((int64_t)img * c + ch) * h + y) * w + xs * 16);
     float4 v[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) v[j] = __ldg(src + j);
     uint32_t o[4];
+    const float s4[4] = {scale, scale, scale, scale}, rs4[4] = {rs, rs, rs, rs};
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      o[j] = pack4i(quant_div_guarded(v[j].x, scale, rs, zp), quant_div_guarded(v[j].y, scale, rs, zp),
-                    quant_div_guarded(v[j].z, scale, rs, zp), quant_div_guarded(v[j].w, scale, rs, zp));
+    for (int j = 0; j < 4; ++j) {   // four pixels per guarded rounding, packed fp32 + one saturating pack (p2v_requant.cuh)
+      const float y4[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+      float r4[4];
+      div_round4(y4, s4, rs4, zp, r4);
+      o[j] = pack_sat4(r4[0], r4[1], r4[2], r4[3]);
     }
     const int px = xs * 16;
     const int pw = px / p, kw = px % p, ph = y / p, kh = y % p;
@@ -75,14 +81,14 @@ __global__ void quant_patchify_u8_kernel(const uint8_t* __restrict__ x, int8_t* 
   const int gw = w / p, gh = h / p;
   const int k = c * p * p;
   const int w16 = w / 16;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total16;
-       i += (int64_t)gridDim.x * blockDim.x) {
-    const int xs = (int)(i % w16);
-    int64_t r = i / w16;
-    const int y = (int)(r % h);
+  const int n16 = (int)total16;   // 32-bit index arithmetic, as in quant_patchify_kernel
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += gridDim.x * blockDim.x) {
+    const int xs = i % w16;
+    int r = i / w16;
+    const int y = r % h;
     r /= h;
-    const int ch = (int)(r % c);
-    const int img = (int)(r / c);
+    const int ch = r % c;
+    const int img = r / c;
     const uint4 v = __ldg(reinterpret_cast<const uint4*>(x + (((int64_t)img * c + ch) * h + y) * w + xs * 16));
     const uint32_t in[4] = {v.x, v.y, v.z, v.w};
     uint32_t o[4];
@@ -116,30 +122,35 @@ embed_assemble_kernel(const int8_t* __restrict__ pe, int8_t* __restrict__ out, i
   const float4 cl4 = *reinterpret_cast<const float4*>(cls_value + c0);
   const float cls[4] = {cl4.x, cl4.y, cl4.z, cl4.w};
   const float embed_rs = __frcp_rn(embed_scale);
+  const float es4[4] = {embed_scale, embed_scale, embed_scale, embed_scale}, ers4[4] = {embed_rs, embed_rs, embed_rs, embed_rs};
+  auto clamp_q = [](float r) { return fminf(fmaxf(r, -128.f), 127.f); };
   // 32-bit token arithmetic (b * (np + 1) < 2^31 is checked at launch): a 64-bit modulo per token costs more than
   // the whole element math
   const int ntok = (int)tokens, np1 = np + 1;
   for (int tok = blockIdx.x * tok_per_block + threadIdx.x / d4; tok < ntok; tok += gridDim.x * tok_per_block) {
     const int img = tok / np1;
     const int t = tok - img * np1;
-    int q[4];
     uint32_t word = 0;
     if (t > 0) word = __ldg(reinterpret_cast<const uint32_t*>(pe + ((int64_t)img * np + (t - 1)) * d + c0));
     const float4 ps4 = __ldg(reinterpret_cast<const float4*>(pos_value + (int64_t)t * d + c0));
     const float pos[4] = {ps4.x, ps4.y, ps4.z, ps4.w};
+    float xe[4];
+    if (t == 0) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      float xe;
-      if (t == 0) {
-        xe = cls[j];
-      } else {
-        const float pv = fmul(fsub((float)(int8_t)((word >> (8 * j)) & 0xff), pe_zp), pe_scale);
-        const int qe = quant_div_guarded(pv, embed_scale, embed_rs, embed_zp);
-        xe = fmul(fsub((float)qe, embed_zp), embed_scale);
-      }
-      q[j] = quant_div_guarded(fadd(xe, pos[j]), so[j], rso[j], 0.f);
+      for (int j = 0; j < 4; ++j) xe[j] = cls[j];
+    } else {   // patch-embedding codes -> qact_embed codes -> values, four channels per guarded rounding
+      float pv[4], qe[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) pv[j] = fmul(fsub((float)(int8_t)((word >> (8 * j)) & 0xff), pe_zp), pe_scale);
+      div_round4(pv, es4, ers4, embed_zp, qe);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) xe[j] = fmul(fsub(clamp_q(qe[j]), embed_zp), embed_scale);
     }
-    *reinterpret_cast<uint32_t*>(out + (int64_t)tok * d + c0) = pack4i(q[0], q[1], q[2], q[3]);
+    float sum[4], q[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) sum[j] = fadd(xe[j], pos[j]);
+    div_round4(sum, so, rso, 0.f, q);
+    *reinterpret_cast<uint32_t*>(out + (int64_t)tok * d + c0) = pack_sat4(q[0], q[1], q[2], q[3]);
   }
 }
 
@@ -439,6 +450,7 @@ extern "C" int p2v_quant_patchify(const float* x, int8_t* codes, int b, int c, i
               c, h, w, p);
   P2V_REQUIRE(p % 16 == 0 && w % 16 == 0, "p2v_quant_patchify: patch size and width must be multiples of 16");
   const int64_t total16 = (int64_t)b * c * h * (w / 16);
+  P2V_REQUIRE(total16 < (1ll << 31) - (int64_t)kNumSMs * 16 * 256, "p2v_quant_patchify: batch too large for 32-bit pixel indexing");
   quant_patchify_kernel<<<grid_for(total16, 256), 256, 0, (cudaStream_t)stream>>>(x, codes, b, c, h, w, p, scale,
                                                                                   zero_point, total16);
   P2V_CHECK_CUDA(cudaGetLastError());
@@ -458,6 +470,7 @@ extern "C" int p2v_quant_patchify_u8(const uint8_t* x, int8_t* codes, int b, int
     nm.stdv[i] = stdv[i];
   }
   const int64_t total16 = (int64_t)b * c * h * (w / 16);
+  P2V_REQUIRE(total16 < (1ll << 31) - (int64_t)kNumSMs * 16 * 256, "p2v_quant_patchify_u8: batch too large for 32-bit pixel indexing");
   quant_patchify_u8_kernel<<<grid_for(total16, 256), 256, 0, (cudaStream_t)stream>>>(x, codes, b, c, h, w, p, scale,
                                                                                      zero_point, nm, total16);
   P2V_CHECK_CUDA(cudaGetLastError());
