@@ -79,7 +79,7 @@ struct TcTail {                                                  // at kRegionCA
   double x_sum[8][2][32];
   alignas(8) uint64_t full[kTcStages];
   uint64_t empty[kTcStages];
-  uint64_t s_full[2], p_ready[2], o_full[2], s_free[2];
+  uint64_t s_full[2], o_full[2];
   uint32_t tmem_base;
 };
 constexpr uint32_t kTcSmemEnd = kRegionCAddr + kStageBytes + (uint32_t)sizeof(TcTail);
@@ -156,11 +156,15 @@ __device__ __forceinline__ void tmem_fill_32x8(uint32_t taddr, uint32_t c) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(taddr), "r"(c) : "memory");
 }
 __device__ __forceinline__ void pair_barrier(int pair) { asm volatile("bar.sync %0, 64;" ::"r"(1 + pair) : "memory"); }
-// Hand-over from a tile's MMA warp to its eight softmax warps: the MMA warp watches the mbarrier its tcgen05.commit
-// arrives on, then releases the softmax warps through a named barrier, on which they block in hardware.  (Waiting on
-// the mbarrier directly, every softmax warp came back from try_wait every few hundred cycles: ncu counted a fifth of
-// all issued instructions in those loops, on the schedulers that also run the working warps.)
-constexpr int kNbS = 9, kNbO = 11;      // + tile; ids 1..8 are the pair barriers
+// Hand-overs between a tile's MMA warp and its eight softmax warps go through named barriers, on which the waiting
+// side blocks in hardware.  (Waiting on mbarriers, the waiting warps came back from try_wait every few hundred
+// cycles or less: ncu counted a fifth of all issued instructions in the softmax warps' loops in the first version,
+// and later still 11 % - 3.3 M polls per launch - in the MMA warps' wait for the probabilities, on two of the four
+// schedulers.)  Per item and tile four hand-overs follow each other strictly: S ready (MMA -> softmax), P written
+// (softmax -> MMA), O ready (MMA -> softmax), region handed back (softmax -> MMA).  Two barrier ids per tile are enough:
+// kNbToSoft for the two the MMA warp arrives on and the softmax warps wait on, kNbToMma for the two the other way
+// round - a thread can only reach the second use of an id after the first one has completed.
+constexpr int kNbToSoft = 9, kNbToMma = 11;      // + tile; ids 1..8 are the pair barriers
 __device__ __forceinline__ void tile_barrier_wait(int id) { asm volatile("bar.sync %0, 288;" ::"r"(id) : "memory"); }
 __device__ __forceinline__ void tile_barrier_release(int id) { asm volatile("bar.arrive %0, 288;" ::"r"(id) : "memory"); }
 __device__ __forceinline__ void tmem_ld_32x32_nowait(uint32_t taddr, uint32_t (&v)[32]) { tmem_ld_32x32(taddr, v); }
@@ -347,9 +351,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_co
     }
     for (int t = 0; t < 2; ++t) {
       mbar_init(&s.s_full[t], 1);
-      mbar_init(&s.p_ready[t], 8);
       mbar_init(&s.o_full[t], 1);
-      mbar_init(&s.s_free[t], 8);
     }
     fence_mbar_init();
   }
@@ -421,9 +423,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_co
         const int st = i & 1;
         const uint32_t sa = (st ? kRegionCAddr : a0);
         if (lane == 0) {
-          // S of item i: its operands have landed, and the tile's TMEM region was handed back (bias restored)
+          // S of item i: its operands have landed (the tile's TMEM region was handed back at the end of the last round)
           mbar_wait(&s.full[st], (i >> 1) & 1);
-          if (i > 0) mbar_wait(&s.s_free[t], (i - 1) & 1);
           tc_fence_after_sync();
           const uint64_t dq = umma_desc_sw64(sa + kOffQ + t * 8192), dk = umma_desc_sw64(sa + kOffK);
           tc_mma_i8(tile, dq, dk, idesc_s, 1u);                 // accumulates onto the 1.5 * 2^23 bias
@@ -434,10 +435,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_co
           tc_fence_before_sync();
         }
         __syncwarp();
-        tile_barrier_release(kNbS + t);
+        tile_barrier_release(kNbToSoft + t);
+        tile_barrier_wait(kNbToMma + t);   // P V of item i: all eight warps of the tile have written their probability planes
         if (lane == 0) {
-          // P V of item i: all eight warps of the tile have written their probability planes
-          mbar_wait(&s.p_ready[t], i & 1);
           tc_fence_after_sync();
           const uint64_t dv = umma_desc_sw64(sa + kOffV);
           for (int ks = 0; ks < nchunks; ++ks) {
@@ -453,7 +453,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_co
           tc_fence_before_sync();
         }
         __syncwarp();
-        tile_barrier_release(kNbO + t);
+        tile_barrier_release(kNbToSoft + t);
+        tile_barrier_wait(kNbToMma + t);   // epilogue done, accumulator bias restored: the region is free for the next S
+        tc_fence_after_sync();
       }
     }
   } else if (warp < kTcSoftWarps) {
@@ -488,7 +490,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_co
           const long long t0 = clock64();
           while (clock64() - t0 < a.skew) __nanosleep(256);
         }
-        tile_barrier_wait(kNbS + t);
+        tile_barrier_wait(kNbToSoft + t);
         tc_fence_after_sync();
         stamp(1);
         if (warp_on) {
@@ -640,12 +642,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_co
           tmem_ld_wait_st();
         }
         tc_fence_before_sync();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&s.p_ready[t]);
+        tile_barrier_release(kNbToMma + t);
         stamp(4);
 
         // ---- epilogue: O = (O_hi << 8) + O_lo -> RNE shift to the qact2 grid -> int8, out through a TMA store ----
-        tile_barrier_wait(kNbO + t);
+        tile_barrier_wait(kNbToSoft + t);
         tc_fence_after_sync();
         stamp(5);
         if (warp_on) {
@@ -688,9 +689,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_co
         for (int c = hf * (kTcMaxN / 2); c < (hf + 1) * (kTcMaxN / 2); c += 8) tmem_fill_32x8(tile + c, kMagic);
         tmem_ld_wait_st();
         tc_fence_before_sync();
-        __syncwarp();
         stamp(7);
-        if (lane == 0) mbar_arrive(&s.s_free[t]);
+        tile_barrier_release(kNbToMma + t);
       }
       if (hf == 0 && lane == 0) tma_store_wait_all();
     }
