@@ -401,7 +401,7 @@ __device__ __forceinline__ bool can_stage(const GemmArgs& g) {
 template <uint32_t FLAGS>
 __device__ __forceinline__ bool prefetch_residual16(const GemmArgs& g, int row, int col, uint4& r) {
   if ((FLAGS & EPI_PLAIN) && (FLAGS & EPI_RESIDUAL)) {
-    if (row >= g.m) return false;
+    if (row >= g.m || col >= g.n) return false;   // n % 16 == 0: a chunk lies entirely inside or outside the row
     r = ld_act_v4(g.epi.residual + (int64_t)row * g.ld_out + col);
     return true;
   }
