@@ -475,3 +475,27 @@ def test_uint8_pixel_entry_equals_fp32_entry_on_normalised_images(micro_model, m
     outs = [torch.empty(5, 16).pin_memory() for _ in range(3)]
     eng.forward_host_pipelined([img.pin_memory() for _ in range(3)], outs, bc, mean=mean, std=std)
     assert all(torch.equal(o, want.cpu()) for o in outs)
+
+
+def test_programmatic_dependent_launch_changes_nothing_but_the_schedule(tiny_model):
+    """p2v_set_pdl (include/p2v.h): with the launch attribute off every kernel starts after the previous one has
+    drained; with it on a kernel's prologue overlaps that drain and its first access to activations waits
+    (griddepcontrol.wait).  Same logits either way, eager and through a freshly captured graph."""
+    from diff_vit_b200 import _cabi as cabi
+    from diff_vit_b200.engine import IntegerEngine
+    model = tiny_model.cuda()
+    g = torch.Generator(device='cuda').manual_seed(7)
+    x = torch.randn(24, 3, 224, 224, device='cuda', generator=g)
+    bits = [8] * 50
+    out = {}
+    try:
+        for mode in (0, 7):
+            cabi.check(cabi.lib().p2v_set_pdl(mode))
+            eng = IntegerEngine(model)                       # graphs are captured under the current setting
+            eager, _ = eng.forward_dump(x, bits)
+            replayed = [eng.forward_into(x, bits).clone() for _ in range(3)]
+            assert all(torch.equal(r, eager) for r in replayed)
+            out[mode] = eager
+    finally:
+        cabi.check(cabi.lib().p2v_set_pdl(7))
+    assert torch.equal(out[0], out[7])
