@@ -242,7 +242,9 @@ __device__ __forceinline__ int sext_byte(uint32_t w, int j) {
 }
 
 // G = 4-channel groups per lane.  FULL: d == 128 * G (no partial group).  DUMP: also write the unclamped LN codes.
-template <int G, bool FULL, bool DUMP>
+// SM: the per-channel constants live in shared memory (4 x 128 G floats, dynamic) instead of registers - for
+// d > 384 (DeiT-B / ViT-B: 768), where 16 G constant registers per lane no longer fit beside the row.
+template <int G, bool FULL, bool DUMP, bool SM = false>
 __global__ void __launch_bounds__(256, 2)
 layernorm_int_pot_kernel(const int8_t* __restrict__ in, int64_t in_row_stride, int8_t* __restrict__ out,
                          int32_t* __restrict__ ln_codes, int rows, int d, const p2v_layernorm p) {
@@ -250,12 +252,26 @@ layernorm_int_pot_kernel(const int8_t* __restrict__ in, int64_t in_row_stride, i
   const int lane = threadIdx.x & 31;
   const int warps_total = gridDim.x * (blockDim.x >> 5);
   const int groups = d >> 2;
-  float go[G][4], bo[G][4], pm[G][4];
-  int mk[G][4];
+  constexpr int GR = SM ? 1 : G;     // register copies only without SM
+  float go[GR][4], bo[GR][4], pm[GR][4];
+  int mk[GR][4];
+  extern __shared__ __align__(16) float ln_const[];   // SM: go | bo | pm | mask, 128 G entries each, zero beyond d
+  if (SM) {
+    for (int c = threadIdx.x; c < 128 * G; c += blockDim.x) {
+      const bool in_range = c < d;
+      const float rs = in_range ? p.ln_out_rscale[c] : 0.f;
+      ln_const[c] = in_range ? fmul(p.gamma[c], rs) : 0.f;
+      ln_const[128 * G + c] = in_range ? fmul(p.beta[c], rs) : 0.f;
+      ln_const[2 * 128 * G + c] = in_range ? p.post_mul[c] : 0.f;
+      ln_const[3 * 128 * G + c] = in_range ? p.in_mask[c] : 0.f;
+    }
+    __syncthreads();
+  }
 #pragma unroll
-  for (int g = 0; g < G; ++g) {
+  for (int g = 0; g < GR; ++g) {
     const int grp = g * 32 + lane;
-    if (FULL || grp < groups) {
+    if (SM) {
+    } else if (FULL || grp < groups) {
       const int c0 = grp * 4;
       const float4 ga = *reinterpret_cast<const float4*>(p.gamma + c0);
       const float4 be = *reinterpret_cast<const float4*>(p.beta + c0);
@@ -294,10 +310,18 @@ layernorm_int_pot_kernel(const int8_t* __restrict__ in, int64_t in_row_stride, i
     int sum = 0, sumsq = 0;   // |x| <= 1024, d <= 128 G: per-lane partial sums stay far below 2^31; padded groups add 0
 #pragma unroll
     for (int g = 0; g < G; ++g) {
+      int mg[4];
+      if (SM) {
+        const float4 m4 = *reinterpret_cast<const float4*>(ln_const + 3 * 128 * G + (g * 32 + lane) * 4);
+        mg[0] = (int)m4.x; mg[1] = (int)m4.y; mg[2] = (int)m4.z; mg[3] = (int)m4.w;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) mg[j] = mk[SM ? 0 : g][j];
+      }
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         // one PRMT sign-extends byte j (selector nibble 8 | j replicates its msb)
-        const int v = sext_byte(cur_w[g], j) * mk[g][j];
+        const int v = sext_byte(cur_w[g], j) * mg[j];
         xq[g][j] = (float)v;
         sum += v;
         sumsq += v * v;
@@ -314,11 +338,22 @@ layernorm_int_pot_kernel(const int8_t* __restrict__ in, int64_t in_row_stride, i
     for (int g = 0; g < G; ++g) {
       const int grp = g * 32 + lane;
       if (FULL || grp < groups) {
-        float v[4], code[4];
+        float v[4], code[4], gg[4], bb[4], pp[4];
+        if (SM) {
+          const float4 g4 = *reinterpret_cast<const float4*>(ln_const + grp * 4);
+          const float4 b4 = *reinterpret_cast<const float4*>(ln_const + 128 * G + grp * 4);
+          const float4 p4 = *reinterpret_cast<const float4*>(ln_const + 2 * 128 * G + grp * 4);
+          gg[0] = g4.x; gg[1] = g4.y; gg[2] = g4.z; gg[3] = g4.w;
+          bb[0] = b4.x; bb[1] = b4.y; bb[2] = b4.z; bb[3] = b4.w;
+          pp[0] = p4.x; pp[1] = p4.y; pp[2] = p4.z; pp[3] = p4.w;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) { gg[j] = go[SM ? 0 : g][j]; bb[j] = bo[SM ? 0 : g][j]; pp[j] = pm[SM ? 0 : g][j]; }
+        }
         bool ok = true;
 #pragma unroll
         for (int j = 0; j < 4; j += 2) {
-          const float x2[2] = {xq[g][j], xq[g][j + 1]}, g2[2] = {go[g][j], go[g][j + 1]}, b2[2] = {bo[g][j], bo[g][j + 1]};
+          const float x2[2] = {xq[g][j], xq[g][j + 1]}, g2[2] = {gg[j], gg[j + 1]}, b2[2] = {bb[j], bb[j + 1]};
           float c2[2];
           ln_code_fast2(x2, st, g2, b2, ok, c2);
           code[j] = c2[0];
@@ -326,7 +361,7 @@ layernorm_int_pot_kernel(const int8_t* __restrict__ in, int64_t in_row_stride, i
         }
         if (!ok) {   // rare: a dyadic exponent outside [0, 31] before clamping, or a huge offset
 #pragma unroll
-          for (int j = 0; j < 4; ++j) code[j] = ln_code_folded(xq[g][j], st, go[g][j], bo[g][j]);
+          for (int j = 0; j < 4; ++j) code[j] = ln_code_folded(xq[g][j], st, gg[j], bb[j]);
         }
 #pragma unroll
         for (int j = 0; j < 4; j += 2) {
@@ -335,7 +370,7 @@ layernorm_int_pot_kernel(const int8_t* __restrict__ in, int64_t in_row_stride, i
             ln_codes[(int64_t)row * d + grp * 4 + j + 1] = (int)code[j + 1];
           }
           // code * 2^k is exact: one rounding, like mul then add
-          const float2 v2 = ffma2(make_float2(code[j], code[j + 1]), make_float2(pm[g][j], pm[g][j + 1]),
+          const float2 v2 = ffma2(make_float2(code[j], code[j + 1]), make_float2(pp[j], pp[j + 1]),
                                        make_float2(p.post_zp, p.post_zp));
           v[j] = v2.x;
           v[j + 1] = v2.y;
@@ -515,11 +550,20 @@ extern "C" int p2v_layernorm_int(const int8_t* in, int64_t in_row_stride, int8_t
     else if (ln_codes) P2V_CHECK_CUDA(launch_pdl(2, layernorm_int_pot_kernel<G_, false, true>, dim3(pgrid), dim3(warps * 32), 0, st, in, in_row_stride, out, ln_codes, rows, d, *p));        \
     else P2V_CHECK_CUDA(launch_pdl(2, layernorm_int_pot_kernel<G_, false, false>, dim3(pgrid), dim3(warps * 32), 0, st, in, in_row_stride, out, ln_codes, rows, d, *p));                     \
   } while (0)
+#define P2V_LN_LAUNCH_SM(G_)                                                                                       \
+  do {                                                                                                             \
+    const size_t smem = 4 * 128 * (G_) * sizeof(float);                                                            \
+    if (ln_codes) P2V_CHECK_CUDA(launch_pdl(2, layernorm_int_pot_kernel<G_, false, true, true>, dim3(pgrid), dim3(warps * 32), smem, st, in, in_row_stride, out, ln_codes, rows, d, *p)); \
+    else P2V_CHECK_CUDA(launch_pdl(2, layernorm_int_pot_kernel<G_, false, false, true>, dim3(pgrid), dim3(warps * 32), smem, st, in, in_row_stride, out, ln_codes, rows, d, *p));        \
+  } while (0)
     if (groups == 1) P2V_LN_LAUNCH(1);
     else if (groups == 2) P2V_LN_LAUNCH(2);
     else if (groups == 3) P2V_LN_LAUNCH(3);
+    else if (groups <= 4) P2V_LN_LAUNCH_SM(4);
+    else if (groups <= 6) P2V_LN_LAUNCH_SM(6);      // d = 768: DeiT-B / ViT-B
+    else P2V_LN_LAUNCH_SM(8);                       // d <= 1024
 #undef P2V_LN_LAUNCH
-    else layernorm_int_kernel<true><<<grid, warps * 32, 0, st>>>(in, in_row_stride, out, ln_codes, rows, d, *p);
+#undef P2V_LN_LAUNCH_SM
   } else {
     P2V_REQUIRE(p->post_div1, "p2v_layernorm_int: non-pot path needs post_div1");
     layernorm_int_kernel<false><<<grid, warps * 32, 0, st>>>(in, in_row_stride, out, ln_codes, rows, d, *p);

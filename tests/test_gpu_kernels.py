@@ -142,7 +142,8 @@ def _ln_plan(rng, d, pot):
                          post_div1=t(cs2), post_div2=float(s_out), post_zp=0.0, in_scale1=float(base), pot=int(pot))
 
 
-@pytest.mark.parametrize('rows,d,stride_rows', [(197 * 3, 384, 1), (64, 192, 1), (33, 128, 1), (5, 768, 1), (4, 384, 197)])
+@pytest.mark.parametrize('rows,d,stride_rows', [(197 * 3, 384, 1), (64, 192, 1), (33, 128, 1), (5, 768, 1), (4, 384, 197),
+                                                (700, 768, 1), (300, 1024, 1), (90, 512, 1), (75, 640, 1), (3, 768, 197)])
 @pytest.mark.parametrize('pot', [True, False])
 def test_layernorm_int_matches_host_arithmetic(cabi, rows, d, stride_rows, pot):
     rng = np.random.default_rng(rows + d + pot)
