@@ -116,7 +116,9 @@ def main():
             x = torch.randn(args.val_batchsize // world, 3, 224, 224, device=device, generator=gen)
             with torch.no_grad():
                 ref = model(x, [8] * n_layers, False)[0] if args.quant else model(x)[0]
-            val.append((x, ref.float().cpu().topk(1, 1, True, True)[1].squeeze(1)))   # same tie-breaking as accuracy()
+            # quantized logits tie often; accuracy() ranks with topk(5), whose first column can differ from topk(1)'s
+            # pick among tied maxima, so the labels are taken from the very same call
+            val.append((x, ref.float().cpu().topk(min(5, ref.shape[1]), 1, True, True)[1][:, 0].contiguous()))
     else:
         loader = imagenet_loader(args.data, 'val', family, args.val_batchsize, args.num_workers)
         val = ((dvd.shard(x).to(device), dvd.shard(y)) for x, y in loader) if world > 1 else \
