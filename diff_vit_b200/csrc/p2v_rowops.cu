@@ -222,7 +222,8 @@ __device__ __forceinline__ void ln_code_fast2(const float (&xq)[2], const LnRow&
   // bo - u go with two roundings as in the reference: packed product, scalar subtractions (a packed add fed by a
   // packed mul gets contracted into one FFMA2 by ptxas, explicit .rn or not)
   const float2 ug = fmul2(make_float2(row.u, row.u), g2);
-  const float2 b = make_float2(fsub(bo[0], ug.x), fsub(bo[1], ug.y));
+  // bo - ug as ug * (-1) + bo: one packed instruction, one rounding of the already rounded product
+  const float2 b = ffma2(ug, make_float2(-1.0f, -1.0f), make_float2(bo[0], bo[1]));
   const float2 Bq = fadd2(ffma2(b, make_float2(u2f(p0), u2f(p1)), kMagic), kMagicNeg);
   ok = ok & (ex0 - 0x33800000u < 0x10000000u) & (ex1 - 0x33800000u < 0x10000000u) &
        (fabsf(Bq.x) <= 2097152.0f) & (fabsf(Bq.y) <= 2097152.0f);
