@@ -145,9 +145,12 @@ def _ln_plan(rng, d, pot):
 @pytest.mark.parametrize('rows,d,stride_rows', [(197 * 3, 384, 1), (64, 192, 1), (33, 128, 1), (5, 768, 1), (4, 384, 197),
                                                 (700, 768, 1), (300, 1024, 1), (90, 512, 1), (75, 640, 1), (3, 768, 197)])
 @pytest.mark.parametrize('pot', [True, False])
-def test_layernorm_int_matches_host_arithmetic(cabi, rows, d, stride_rows, pot):
+@pytest.mark.parametrize('big_masks', [False, True], ids=['masks_le_8', 'masks_to_64'])
+def test_layernorm_int_matches_host_arithmetic(cabi, rows, d, stride_rows, pot, big_masks):
     rng = np.random.default_rng(rows + d + pot)
     p = _ln_plan(rng, d, pot)
+    if big_masks:   # beyond the PTF range {1, 2, 4, 8}: the kernel must fall back from fp32 to integer row statistics
+        p.in_mask = p.in_mask * torch.from_numpy((2.0 ** rng.integers(0, 4, size=d)).astype(np.float32))
     x = _rand_i8(rng, rows * stride_rows, d)
     x[0] = 127
     x[0, ::2] = -128                                     # maximal variance row
