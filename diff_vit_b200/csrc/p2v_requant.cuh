@@ -36,29 +36,34 @@ __device__ __forceinline__ float div_round(float y, float s, float rs, float zp)
   return r;
 }
 
-// Four at a time: the common path is branch-free so the four dependency chains interleave; one rarely
-// taken branch per group re-does the flagged elements exactly.
+// Four at a time: the common path is branch-free so the four dependency chains interleave; one rarely taken branch
+// per group re-does the flagged elements exactly.  The tie test of the group is one comparison: with df = t - RNE(t)
+// in [-1/2, 1/2], q = df^2 - 1/4 = -(1/2 - |df|)(1/2 + |df|) is within kTieGuard of zero whenever |df| is within
+// kTieGuard of 1/2 (and hardly ever otherwise), so "min |q| over the group < kTieGuard" flags a superset of the
+// per-element test |(|df| - 1/2)| < kTieGuard at 1.4 instead of 3.3 instructions per element (one packed FMA per
+// pair, a three-input minimum per group).
 __device__ __forceinline__ void div_round4(const float (&y)[4], const float (&s)[4], const float (&rs)[4], float zp,
                                            float (&r)[4]) {
   // element pairs on the packed fp32 instructions (each half rounds like the scalar _rn op)
   const float2 zp2 = make_float2(zp, zp), kMagic = make_float2(12582912.0f, 12582912.0f);
   const float2 kMagicNeg = make_float2(-12582912.0f, -12582912.0f), kNegOne = make_float2(-1.0f, -1.0f);
-  uint32_t flags = 0;
+  float2 df[2];
 #pragma unroll
   for (int e = 0; e < 4; e += 2) {
     // (a contraction of this mul + add into one fma moves t by at most one ulp, far inside the tie guard)
     const float2 t = fadd2(fmul2(make_float2(y[e], y[e + 1]), make_float2(rs[e], rs[e + 1])), zp2);
     const float2 rr = fadd2(fadd2(t, kMagic), kMagicNeg);      // rne_small
-    const float2 df = ffma2(rr, kNegOne, t);                       // t - r, exact
+    df[e >> 1] = ffma2(rr, kNegOne, t);                            // t - r, exact
     r[e] = rr.x;
     r[e + 1] = rr.y;
-    flags |= (fabsf(fabsf(df.x) - 0.5f) < kTieGuard) ? (1u << e) : 0u;
-    flags |= (fabsf(fabsf(df.y) - 0.5f) < kTieGuard) ? (2u << e) : 0u;
   }
-  if (flags) {
+  const float2 q0 = ffma2(df[0], df[0], make_float2(-0.25f, -0.25f)), q1 = ffma2(df[1], df[1], make_float2(-0.25f, -0.25f));
+  if (fminf(fminf(fabsf(q0.x), fabsf(q0.y)), fminf(fabsf(q1.x), fabsf(q1.y))) < kTieGuard) {
+    // rare
+    const float d4[4] = {df[0].x, df[0].y, df[1].x, df[1].y};
 #pragma unroll
     for (int e = 0; e < 4; ++e)
-      if (flags & (1u << e)) r[e] = div_round_exact(y[e], s[e], zp);
+      if (!(fabsf(fabsf(d4[e]) - 0.5f) >= kTieGuard)) r[e] = div_round_exact(y[e], s[e], zp);
   }
 }
 
