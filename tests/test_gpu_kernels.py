@@ -121,6 +121,33 @@ def test_gemm_epilogues_match_host_arithmetic(cabi, gemm_mode, impl, pot, gelu, 
                 np.testing.assert_array_equal(aux.cpu().numpy(), want_aux)
 
 
+@pytest.mark.parametrize('pot', [True, False])
+@pytest.mark.parametrize('m,n,k', [(6304, 384, 1536), (6304, 384, 384), (197 * 40, 384, 768), (300, 384, 384)])
+def test_gemm_residual_small_m_automatic_kernel_choice(cabi, pot, m, n, k):
+    """Automatic kernel choice (p2v_gemm_set_mode(0)) at the shard sizes of the multi-GPU runs (32 images: M = 6304,
+    150 tiles of 128 x 128 on 148 SMs) and around them, plain launches of the residual epilogue: same codes as the
+    host arithmetic, bit for bit.  (A 128 x 192-tile kernel that does these shapes in one round was measured at
+    11.25 vs 11.14 us for fc2 and 7.5 vs 8.0 us for proj and not kept.)"""
+    rng = np.random.default_rng(m + n + k + pot)
+    a, w = _rand_i8(rng, m, k), _rand_i8(rng, n, k, lo=-100, hi=100)
+    lp = _epilogue_case(rng, n, pot, False, True)
+    lp.w = torch.from_numpy(w)
+    res = _rand_i8(rng, m, n)
+    want, _, _ = hostmath.gemm_epilogue(a, lp, residual=res, want_f32=True)
+    dev = lambda t: (torch.from_numpy(t) if isinstance(t, np.ndarray) else t).cuda().contiguous()
+    keep = dict(a=dev(a), w=dev(w), acc=dev(lp.acc_scale), bias=dev(lp.bias), os=dev(lp.out_scale), ors=dev(lp.out_rscale),
+                rs=dev(lp.res_scale), o2=dev(lp.out2_scale), res=dev(res))
+    out = torch.zeros(m, n, dtype=torch.int8, device='cuda')
+    e = cabi.Epilogue()
+    e.acc_scale, e.bias, e.out_scale, e.out_rscale = (keep[x].data_ptr() for x in ('acc', 'bias', 'os', 'ors'))
+    e.flags = lp.flags | cabi.EPI_RESIDUAL
+    e.res_scale, e.out2_scale, e.residual = keep['rs'].data_ptr(), keep['o2'].data_ptr(), keep['res'].data_ptr()
+    cabi.check(cabi.lib().p2v_gemm_set_mode(0))
+    cabi.check(cabi.lib().p2v_gemm_i8(keep['a'].data_ptr(), k, keep['w'].data_ptr(), out.data_ptr(), n, m, n, k, C.byref(e), _stream()))
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(out.cpu().numpy(), want)
+
+
 def _ln_plan(rng, d, pot):
     from diff_vit_b200.plan import LayerNormPlan
     base = np.float32(0.0123)
