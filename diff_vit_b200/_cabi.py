@@ -34,6 +34,15 @@ class Attention(C.Structure):
                 ('in_zp', C.c_float), ('lut_sig_bits', C.c_int32), ('force_legacy', C.c_int32)]
 
 
+class WindowAttention(C.Structure):
+    _fields_ = [('perm', _vp), ('region', _vp), ('bias', _vp), ('exp_lut', _vp), ('lut_n', C.c_int32),
+                ('n', C.c_int32), ('heads', C.c_int32), ('windows', C.c_int32), ('tokens', C.c_int32),
+                ('channels', C.c_int32), ('qshift', C.c_int32), ('qscale', C.c_float), ('acc_scale', C.c_double),
+                ('a1_scale', C.c_float), ('a1_rscale', C.c_float), ('a2_rscale', C.c_float), ('mask_int', C.c_int32),
+                ('out_unit', C.c_float), ('out_rscale', C.c_float), ('softmax_levels', C.c_int32),
+                ('dump_a1', _vp), ('dump_a2', _vp), ('dump_softmax', _vp)]
+
+
 class LinearDesc(C.Structure):
     _fields_ = [('w', _vp), ('n', C.c_int32), ('k', C.c_int32), ('epi', Epilogue)]
 
@@ -80,6 +89,9 @@ SYMBOLS = {
     'p2v_softmax_log_int_f32': (C.c_int, [_vp, _vp, _vp, C.c_int64, C.c_int, C.c_float, C.c_float, C.c_float,
                                           C.c_float, C.c_int, C.c_int, _vp]),
     'p2v_requant_eltwise': (C.c_int, [_vp, _vp, _vp, C.c_int64, C.c_int, _vp, _vp, _vp, C.c_float, _vp]),
+    'p2v_window_attention_int': (C.c_int, [_vp, _vp, C.c_int, C.POINTER(WindowAttention), _vp]),
+    'p2v_gather_row_segments': (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp]),
+    'p2v_avgpool_requant': (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, _vp]),
     'p2v_unpack_int4': (C.c_int, [_vp, _vp, C.c_int64, _vp]),
     'p2v_select_histogram': (C.c_int, [_vp, C.c_int64, C.c_uint32, C.c_uint32, C.c_int, _vp, _vp]),
     'p2v_observe_minmax': (C.c_int, [_vp, C.c_int64, C.c_int, C.c_int, _vp, _vp, _vp]),

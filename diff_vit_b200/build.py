@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libp2vit_b200.so')
 SOURCES = ['p2v_engine.cu', 'p2v_gemm.cu', 'p2v_rowops.cu', 'p2v_attention.cu', 'p2v_attention_tc.cu', 'p2v_observe.cu',
-           'p2v_modules.cu']
+           'p2v_modules.cu', 'p2v_swin.cu']
 # -fmad=false: every fused multiply-add of these kernels is written explicitly (__fmaf_rn / __ffma2_rn); the compiler
 # must not contract the separately rounded mul + add pairs of the reference's op order (it does contract the packed
 # __fmul2_rn + __fadd2_rn intrinsics otherwise)

@@ -160,7 +160,7 @@ embed_assemble_kernel(const int8_t* __restrict__ pe, int8_t* __restrict__ out, i
 // of the warp.  Power-of-two output grids (every minmax-calibrated model) fold 1/s_out into gamma and
 // beta: fl(t*gamma) * 2^-e == fl(t * (gamma * 2^-e)), so the folded form rounds exactly like the
 // reference's (t * gamma) / s_out and (beta - u * gamma) / s_out.
-constexpr int kLnMaxGroups = 8;  // d <= 1024
+constexpr int kLnMaxGroups = 12;  // d <= 1536 (general kernel; the register-resident power-of-two kernel serves d <= 1024)
 
 __device__ __forceinline__ uint32_t pack_sat4f(float v0, float v1, float v2, float v3) {
   uint32_t hi, r;
@@ -469,6 +469,9 @@ __global__ void fake_quant_f32_kernel(const float* __restrict__ x, float* __rest
   }
 }
 
+int quant_patchify_small_launch(const float* x, int8_t* codes, int b, int c, int h, int w, int p, float scale,
+                                float zero_point, cudaStream_t st);   // p2v_swin.cu
+
 static int grid_for(int64_t work, int block) {
   int64_t g = (work + block - 1) / block;
   const int64_t cap = (int64_t)kNumSMs * 16;
@@ -484,7 +487,8 @@ extern "C" int p2v_quant_patchify(const float* x, int8_t* codes, int b, int c, i
   P2V_REQUIRE(x && codes, "p2v_quant_patchify: null pointer");
   P2V_REQUIRE(b > 0 && c > 0 && p > 0 && h % p == 0 && w % p == 0, "p2v_quant_patchify: bad shape %dx%dx%dx%d p=%d", b,
               c, h, w, p);
-  P2V_REQUIRE(p % 16 == 0 && w % 16 == 0, "p2v_quant_patchify: patch size and width must be multiples of 16");
+  if (p % 16 != 0 || w % 16 != 0)   // small patches (Swin: 4 x 4): four pixels per thread, csrc/p2v_swin.cu
+    return quant_patchify_small_launch(x, codes, b, c, h, w, p, scale, zero_point, (cudaStream_t)stream);
   const int64_t total16 = (int64_t)b * c * h * (w / 16);
   P2V_REQUIRE(total16 < (1ll << 31) - (int64_t)kNumSMs * 16 * 256, "p2v_quant_patchify: batch too large for 32-bit pixel indexing");
   quant_patchify_kernel<<<grid_for(total16, 256), 256, 0, (cudaStream_t)stream>>>(x, codes, b, c, h, w, p, scale,
@@ -539,7 +543,10 @@ extern "C" int p2v_layernorm_int(const int8_t* in, int64_t in_row_stride, int8_t
   const int warps = 8;
   const int grid = (rows + warps - 1) / warps;
   cudaStream_t st = (cudaStream_t)stream;
-  if (p->pot) {
+  if (p->pot && d > 1024) {   // wider than the register / shared-memory resident kernel (Swin's last PatchMerging: 4 x 384)
+    P2V_REQUIRE(p->ln_out_rscale && p->post_mul, "p2v_layernorm_int: pot path needs ln_out_rscale and post_mul");
+    layernorm_int_kernel<true><<<grid, warps * 32, 0, st>>>(in, in_row_stride, out, ln_codes, rows, d, *p);
+  } else if (p->pot) {
     P2V_REQUIRE(p->ln_out_rscale && p->post_mul, "p2v_layernorm_int: pot path needs ln_out_rscale and post_mul");
     const int groups = (d / 4 + 31) / 32;
     const int pgrid = grid < kNumSMs * 2 ? grid : kNumSMs * 2;   // persistent warps (2 resident CTAs per SM, 119 registers: three CTAs at 80 registers spilled and were slower): constants stay in registers

@@ -13,14 +13,19 @@ SmoothQuant pair, FLOPs / weight distances collected like the ViT graph does.
 families.  bit_config layout: [patch embed] + per stage (per block [qkv, proj, fc1, fc2] ... + [reduction] where the
 stage downsamples) + [head].
 
-After ``model_quant()`` every Q-module runs its own sm_100a operator on CUDA tensors (diff_vit_b200/standalone.py:
-fake-quant, integer LayerNorm, log-int-softmax kernels; the fp32 products are the library GEMMs the reference itself
-calls).  The fused integer engine (tcgen05 GEMMs, TMEM attention) covers the ViT / DeiT family only; a windowed
-variant of the attention kernel (49 tokens, head dim 32, bias table and shift mask between the two re-quantisations)
-is the open item of this file.
+After ``model_quant()`` the model-level forward of a CUDA tensor runs on the integer engine
+(diff_vit_b200/swin_engine.py): int8 codes from the patch embedding to the head, tcgen05 GEMMs with fused
+re-quantisation / GELU / residual epilogues, the integer LayerNorm and the window attention kernel (49 tokens, head
+dimension 32, bias table and shift mask between the two re-quantisations; csrc/p2v_swin.cu).  With a forward hook on a
+submodule, ``per_module = True``, a ``-1`` in ``bit_config`` or a configuration the engine does not cover (float
+scales, zero points) every Q-module runs its own sm_100a operator instead (diff_vit_b200/standalone.py: fake-quant,
+integer LayerNorm, log-int-softmax kernels; fp32 library GEMMs for the products, as the reference itself computes
+them) - the analysis path, an order of magnitude slower.
 """
 import torch
 from torch import nn
+
+from torch.nn.modules import module as _module_globals
 
 from .layers_quant import DropPath, Mlp, PatchEmbed, to_2tuple, trunc_normal_
 from .ptq import QAct, QConv2d, QIntLayerNorm, QIntSoftmax, QLinear
@@ -268,6 +273,11 @@ class SwinTransformer(nn.Module):
         self.input_quant = input_quant
         self.cfg = cfg
         self.quant = quant
+        self.per_module = False      # True: every Q-module runs its own operator even without hooks
+        self._engine = None
+        self._engine_off = None      # why the integer engine refused this model (NotImplementedError text)
+        self._int_active = bool(quant)
+        self._submodules = None
         if input_quant:
             self.qact_input = QAct(**_act_kw(cfg, quant, calibrate))
         self.patch_embed = PatchEmbed(img_size=img_size, patch_size=patch_size, in_chans=in_chans,
@@ -336,12 +346,61 @@ class SwinTransformer(nn.Module):
             for m in self.modules():
                 if type(m) is QIntLayerNorm:
                     m.mode = 'int'
+        self._int_active = True
+        self._drop_engine()
 
     def model_dequant(self):
         self._set_flag('quant', False)
+        self._int_active = False
+        self._drop_engine()
 
     def model_open_calibrate(self):
         self._set_flag('calibrate', True)
+        self._drop_engine()       # scales are about to change
+
+    # -- the integer engine ---------------------------------------------------------------------------------------------
+    def _drop_engine(self):
+        self._engine = None
+        self._engine_off = None
+
+    def _apply(self, fn, *args, **kwargs):
+        out = super()._apply(fn, *args, **kwargs)
+        self._drop_engine()       # .to() / .cuda(): plans live on one device
+        return out
+
+    def load_state_dict(self, *args, **kwargs):
+        out = super().load_state_dict(*args, **kwargs)
+        self._drop_engine()
+        return out
+
+    def integer_engine(self):
+        """The sm_100a execution engine bound to this model's calibrated state (built lazily)."""
+        if self._engine is None:
+            from .swin_engine import SwinIntegerEngine
+            self._engine = SwinIntegerEngine(self)
+        return self._engine
+
+    def _hooked(self):
+        if self.per_module:
+            return True
+        if self._submodules is None:
+            self._submodules = [m for m in self.modules() if m is not self]
+        if _module_globals._global_forward_hooks or _module_globals._global_forward_pre_hooks:
+            return True
+        return any(m._forward_hooks or m._forward_pre_hooks for m in self._submodules)
+
+    def _integer_forward(self, x, bits):
+        """Logits from the integer engine, or None when this call stays on the per-module path."""
+        if not (self.quant and self._int_active and torch.is_tensor(x) and x.is_cuda and self.input_quant
+                and self.absolute_pos_embed is None and self.cfg.INT_NORM and self.cfg.INT_SOFTMAX):
+            return None
+        if self._engine_off is not None or any(b == -1 for b in bits) or self._hooked():
+            return None
+        try:
+            return self.integer_engine().forward(x, bits)
+        except NotImplementedError as e:      # float scales, zero points, ...: documented scope of swin_engine.py
+            self._engine_off = str(e)
+            return None
 
     def model_open_last_calibrate(self):
         self._set_flag('last_calibrate', True)
@@ -381,12 +440,37 @@ class SwinTransformer(nn.Module):
         if len(bits) < n:
             raise IndexError('bit_config has %d entries, the model has %d quantized layers' % (len(bits), n))
         FLOPs, global_distance = [], []
+        logits = self._integer_forward(x, bits[:n])
+        if logits is not None:
+            return logits if bit_config is None and plot is None else (logits, self.flops(), [])
         x = self.forward_features(x, FLOPs, global_distance, bits)
         c = x.shape[1]
         x = self.head(x, global_distance, bits[n - 1])
         FLOPs.append(c * x.shape[1])
         x = self.act_out(x)
         return x if bit_config is None and plot is None else (x, FLOPs, global_distance)
+
+
+def _swin_flops(self):
+    """The per-layer MAC list a per-module forward accumulates (patch embed, per block qkv / proj / fc1 / fc2, the
+    reductions, head)."""
+    pe = self.patch_embed
+    out = [pe.proj.in_channels * pe.patch_size[0] * pe.patch_size[0] * self.embed_dim * pe.grid_size[0] * pe.grid_size[1]]
+    for layer in self.layers:
+        for blk in layer.blocks:
+            n, c = blk.window_size * blk.window_size, blk.dim
+            out += [n * c * 3 * c, n * c * c]
+            t = blk.input_resolution[0] * blk.input_resolution[1]
+            hid = blk.mlp.fc1.out_features
+            out += [t * c * hid, t * hid * c]
+        if layer.downsample is not None:
+            t = layer.input_resolution[0] * layer.input_resolution[1] // 4
+            out.append(t * 4 * layer.dim * 2 * layer.dim)
+    out.append(self.num_features * self.num_classes)
+    return out
+
+
+SwinTransformer.flops = _swin_flops
 
 
 def _factory(embed_dim, depths, num_heads):

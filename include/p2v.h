@@ -85,7 +85,8 @@ int p2v_gemm_i8_acc(const int8_t* a, int64_t lda, const int8_t* w, int32_t* acc,
 
 /* Input QAct + im2col for a stride-P patch convolution: x fp32 [b, c, h, w] ->
  * codes int8 [b*(h/p)*(w/p), c*p*p], K order (c, kh, kw) = conv weight.reshape(out, -1).
- * Replaces qact_input (models/vit_fquant.py:705-706) and the unfold inside F.conv2d. */
+ * Replaces qact_input (models/vit_fquant.py:705-706) and the unfold inside F.conv2d.  p: a multiple of 4
+ * (16-pixel vector path when p and w are multiples of 16, 4-pixel path otherwise: Swin's 4 x 4 patches). */
 int p2v_quant_patchify(const float* x, int8_t* codes, int b, int c, int h, int w, int p, float scale,
                        float zero_point, void* stream);
 /* The same from 8-bit pixels x [b, c, h, w] (device): the fp32 preprocessing of the reference's loaders,
@@ -163,6 +164,46 @@ int p2v_attention_tc_set_skew(int cycles);
  * per channel of the innermost (inner == 1) or of an outer dimension.  models/ptq/layers.py:207-220. */
 int p2v_fake_quant_f32(const float* x, float* out, int8_t* codes, int64_t outer, int channels, int64_t inner,
                        const float* scale, const float* zero_point, int qmin, int qmax, void* stream);
+
+/* ---- Swin (BASELINE config 5): windowed attention and the data movement around it -------------------------- */
+/* Fused integer window attention of one Swin layer (W-MSA / SW-MSA): per (window, head), n = ws^2 <= 64 tokens,
+ * head dimension 32,
+ *   S = (q * 32^-1/2) k^T  ->  qact_attn1  ->  + relative position bias (qact_table codes)  ->  qact2
+ *     ->  - 100 where the shifted-window mask separates row and key  ->  log-int-softmax  ->  P V  ->  qact3.
+ * Replaces WindowAttention.forward between its qact1 and qact3 (models/swin_quant.py:188-215) together with the
+ * roll / window_partition / window_reverse around it (models/swin_quant.py:362-385): rows are loaded and stored
+ * through `perm`, the composition of the cyclic shift and the window partition, so qkv [images * tokens, 3 * channels]
+ * (per row [3][heads][32]) and out [images * tokens, channels] stay in token order.  All quantizers symmetric and on
+ * power-of-two grids (the minmax observer); the fp32 scaling of q is reproduced exactly (csrc/p2v_swin.cu). */
+typedef struct p2v_window_attention {
+  const int32_t* perm;     /* [windows * n] token (inside its image) of window w's i-th row                            */
+  const uint8_t* region;   /* [windows * n] region id of the shift mask (swin_quant.py:317-340); NULL without a shift   */
+  const float* bias;       /* [heads][n (key)][n (row)] dequantized qact_table entry of the pair's relative position    */
+  const float* exp_lut;    /* [lut_n] integer exp of d = rowmax - x (layers.py:334-358); d >= lut_n reads the last one  */
+  int32_t lut_n;
+  int32_t n, heads, windows, tokens, channels;   /* tokens = windows * n per image, channels = heads * 32              */
+  int32_t qshift;          /* fl32(code * qscale) * 2^qshift is an integer below 2^31 for every int8 code              */
+  float qscale;            /* head_dim^-1/2 as fp32 (swin_quant.py:83,190)                                             */
+  double acc_scale;        /* s_qkv^2 * 2^-qshift                                                                      */
+  float a1_scale, a1_rscale;   /* qact_attn1 grid and its exact reciprocal                                             */
+  float a2_rscale;         /* 1 / s of qact2                                                                           */
+  int32_t mask_int;        /* 100 / s of qact2 (an integer)                                                            */
+  float out_unit;          /* 2^-15 * s_qkv: the value of one unit of sum_j 2^(15 - k_j) v_j                           */
+  float out_rscale;        /* 1 / s of qact3                                                                           */
+  int32_t softmax_levels;  /* 2^bits = 16                                                                              */
+  int8_t* dump_a1;         /* optional [images * windows][heads][n][n]: qact_attn1 codes                               */
+  int8_t* dump_a2;         /* optional, same shape: qact2 codes (before the mask)                                      */
+  uint8_t* dump_softmax;   /* optional, same shape: log2 codes (softmax_levels = probability 0)                        */
+} p2v_window_attention;
+int p2v_window_attention_int(const int8_t* qkv, int8_t* out, int images, const p2v_window_attention* p, void* stream);
+/* out[img][r][s * seg_bytes ...] = in[img][idx[r * segs + s]][0 .. seg_bytes): the x0 / x1 / x2 / x3 concat of
+ * PatchMerging (models/swin_quant.py:449-456) as one byte gather.  seg_bytes: multiple of 16. */
+int p2v_gather_row_segments(const int8_t* in, int8_t* out, const int32_t* idx, int images, int rows_in, int rows_out,
+                            int segs, int seg_bytes, void* stream);
+/* AdaptiveAvgPool1d(1) over the tokens of in [images, tokens, channels] (codes on the power-of-two grid in_scale)
+ * followed by qact3 (models/swin_quant.py:810-813): out [images, channels]. */
+int p2v_avgpool_requant(const int8_t* in, int8_t* out, int images, int tokens, int channels, float in_scale,
+                        float out_scale, float out_zp, void* stream);
 
 /* ---- the operators on their own, fp32 in / fp32 out (module-level use) -------------------------------- */
 /* QIntLayerNorm.forward in mode 'int' (models/ptq/layers.py:255-289) on dequantized fp32 rows x [rows, d]:

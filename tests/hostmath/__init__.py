@@ -112,3 +112,115 @@ def run_plan(plan, x):
     lc, _, logits = gemm_epilogue(cls, plan.head, want_f32=True)
     codes['act/act_out'] = lc
     return logits, codes
+
+
+# ---- Swin (diff_vit_b200.swin_engine plans) ---------------------------------------------------------------------------
+def window_attention(qkv, images, p):
+    """The integer formulation of csrc/p2v_swin.cu window_attention_kernel in numpy (fp32 / int64 / fp64 steps as in
+    the kernel).  qkv int8 [images * tokens, 3 * channels] in token order -> (out int8 [images * tokens, channels],
+    qact_attn1 codes, qact2 codes, log2 codes; the three in window order [images * windows, heads, n, n])."""
+    f32 = np.float32
+    n, heads, nw, L, Cc = p.n, p.heads, p.windows, p.tokens, p.channels
+    perm = p.perm.numpy().astype(np.int64)
+    x = qkv.reshape(images, L, 3, heads, 32)[:, perm].reshape(images, nw, n, 3, heads, 32)
+    q, k, v = (x[:, :, :, i].transpose(0, 1, 3, 2, 4).astype(np.int64) for i in range(3))      # [img, w, head, n, 32]
+    m = ((q.astype(f32) * f32(p.qscale)).astype(f32).astype(np.float64) * 2.0 ** p.qshift).astype(np.int64)
+    acc = np.einsum('bwhic,bwhjc->bwhij', m, k)
+    s = (acc.astype(np.float64) * p.acc_scale).astype(f32)
+    c1 = np.clip(np.rint(s * f32(p.a1_rscale)), -128, 127).astype(f32)
+    bias = p.bias.numpy().transpose(0, 2, 1)[None, None]                                           # [1, 1, head, row, key]
+    t = (c1 * f32(p.a1_scale)).astype(f32) + bias.astype(f32)
+    a2 = np.clip(np.rint(t.astype(f32) * f32(p.a2_rscale)), -128, 127).astype(np.int64)
+    xm = a2.copy()
+    if p.region is not None:
+        rid = p.region.numpy().reshape(nw, n).astype(np.int64)
+        masked = rid[:, :, None] != rid[:, None, :]                                                # [w, row, key]
+        xm = xm - masked[None, :, None] * p.mask_int
+    d = np.minimum(xm.max(-1, keepdims=True) - xm, p.exp_lut.numel() - 1)
+    e = p.exp_lut.numpy().astype(f32)[d]
+    fsum = e.astype(np.float64).sum(-1, keepdims=True).astype(f32)
+    r = np.rint(fsum / e).astype(f32)
+    mant, ex = np.frexp(r)                    # r = mant * 2^ex, mant in [0.5, 1)
+    big = ex.astype(np.int64) - 1
+    kk = np.maximum(big + (mant >= 0.75), 0)
+    kk = np.minimum(kk, p.levels)
+    prob = np.where(kk >= p.levels, 0, np.int64(0x8000) >> np.minimum(kk, 15))
+    o = np.einsum('bwhij,bwhjc->bwhic', prob, v)
+    val = (o.astype(f32) * f32(p.out_unit)).astype(f32)
+    code = np.clip(np.rint(val * f32(p.out_rscale)), -128, 127).astype(np.int8)                    # [img, w, head, n, 32]
+    out = np.empty((images, L, heads, 32), np.int8)
+    out[:, perm] = code.transpose(0, 1, 3, 2, 4).reshape(images, nw * n, heads, 32)
+    shape = (images * nw, heads, n, n)
+    return out.reshape(images * L, Cc), c1.astype(np.int8).reshape(shape), a2.astype(np.int8).reshape(shape), \
+        kk.astype(np.uint8).reshape(shape)
+
+
+def requant(a, a_scale, out_scale):
+    f32 = np.float32
+    v = (a.astype(f32) * _f(a_scale)[None, :]).astype(f32)
+    return np.clip(np.rint((v / _f(out_scale)[None, :]).astype(f32)), -128, 127).astype(np.int8)
+
+
+def run_swin_plan(plan, x):
+    """x: float32 numpy [b, c, h, w].  Returns (logits fp32, {golden-style key: codes}) - the launch sequence of
+    diff_vit_b200.swin_engine.SwinIntegerEngine._run on the host."""
+    a = plan.arch
+    b, P, cin = x.shape[0], a['patch_size'], a['in_chans']
+    g = a['img_size'] // P
+    L, Cd = g * g, a['embed_dim']
+    codes = {}
+    xin = np.empty(x.shape, np.int8)
+    xc = np.ascontiguousarray(x, dtype=np.float32)
+    lib().hm_quant(_p(xc), _p(xin), C.c_int64(xc.size), C.c_float(plan.input_scale), C.c_float(plan.input_zp))
+    codes['act/qact_input'] = xin
+    patches = np.ascontiguousarray(xin.reshape(b, cin, g, P, g, P).transpose(0, 2, 4, 1, 3, 5).reshape(b * L, -1))
+    pe, _, _ = gemm_epilogue(patches, plan.patch_embed)
+    codes['act/patch_embed.qact_before_norm'] = pe
+    xs, ln = layernorm(pe, Cd, b * L, Cd, plan.pe_norm)
+    codes['ln/patch_embed.norm'], codes['act/patch_embed.qact'] = ln, xs
+    for si, st in enumerate(plan.stages):
+        H, W = st.res
+        L, Cd = H * W, st.dim
+        rows = b * L
+        for bi, blk in enumerate(st.blocks):
+            pre = 'layers.%d.blocks.%d' % (si, bi)
+            ap = blk.attn
+            perm = ap.perm.numpy().astype(np.int64)
+            win = lambda t, c: t.reshape(b, L, c)[:, perm].reshape(b * ap.windows, ap.n, c)
+            y, ln = layernorm(xs, Cd, rows, Cd, blk.norm1)
+            codes['ln/' + pre + '.norm1'], codes['act/' + pre + '.qact1'] = ln, y
+            qkv, _, _ = gemm_epilogue(y, blk.qkv)
+            codes['act/' + pre + '.attn.qact1'] = win(qkv, 3 * Cd)
+            att, c1, c2, sm = window_attention(qkv, b, ap)
+            codes['act/' + pre + '.attn.qact_attn1'], codes['act/' + pre + '.attn.qact2'] = c1, c2
+            codes['act/' + pre + '.attn.qact_table'] = ap.table_codes.numpy()
+            codes['softmax/' + pre + '.attn.log_int_softmax'] = sm
+            codes['act/' + pre + '.attn.qact3'] = win(att, Cd)
+            x1, aux, _ = gemm_epilogue(att, blk.proj, residual=xs)
+            codes['act/' + pre + '.attn.qact4'], codes['act/' + pre + '.qact2'] = win(aux, Cd), x1
+            y2, ln = layernorm(x1, Cd, rows, Cd, blk.norm2)
+            codes['ln/' + pre + '.norm2'], codes['act/' + pre + '.qact3'] = ln, y2
+            m0 = requant(y2, blk.requant_in, blk.requant_out)
+            codes['act/' + pre + '.mlp.qact0'] = m0
+            hid, _, _ = gemm_epilogue(m0, blk.fc1)
+            codes['act/' + pre + '.mlp.qact1'] = hid
+            xs, aux, _ = gemm_epilogue(hid, blk.fc2, residual=x1)
+            codes['act/' + pre + '.mlp.qact2'], codes['act/' + pre + '.qact4'] = aux, xs
+        if st.merge is not None:
+            pre = 'layers.%d.downsample' % si
+            idx = st.merge.idx.numpy().astype(np.int64)
+            cat = np.ascontiguousarray(xs.reshape(b, L, Cd)[:, idx].reshape(b * (L // 4), 4 * Cd))
+            y, ln = layernorm(cat, 4 * Cd, b * (L // 4), 4 * Cd, st.merge.norm)
+            codes['ln/' + pre + '.norm'], codes['act/' + pre + '.qact1'] = ln, y
+            xs, _, _ = gemm_epilogue(y, st.merge.reduction)
+            codes['act/' + pre + '.qact2'] = xs
+            L, Cd = L // 4, 2 * Cd
+    y, ln = layernorm(xs, Cd, b * L, Cd, plan.norm)
+    codes['ln/norm'], codes['act/qact2'] = ln, y
+    s = y.reshape(b, L, Cd).astype(np.int64).sum(1)
+    mean = ((s.astype(np.float32) * np.float32(plan.pool_in_scale)).astype(np.float32) / np.float32(L)).astype(np.float32)
+    pooled = np.clip(np.rint((mean / np.float32(plan.pool_out_scale)).astype(np.float32)), -128, 127).astype(np.int8)
+    codes['act/qact3'] = pooled
+    lc, _, logits = gemm_epilogue(pooled, plan.head, want_f32=True)
+    codes['act/act_out'] = lc
+    return logits, codes

@@ -1,0 +1,68 @@
+"""The Swin integer plan (diff_vit_b200.swin_engine.build_swin_plan) executed on the host with the kernels' own scalar
+arithmetic (tests/hostmath: GEMM epilogues and LayerNorm from csrc/p2v_math.cuh, the window attention kernel's integer
+formulation restated in numpy) against the reference's golden codes of the micro Swin and against the oracle.  Pins the
+plan builder - window permutations, shift-mask regions, relative-position bias, the exact fixed-point q scaling, the
+2 x 2 merge gather - on a CPU-only box; the GPU tests then prove the kernels."""
+import numpy as np
+import pytest
+import torch
+
+import hostmath
+from diff_vit_b200.swin_engine import build_swin_plan, num_linear_layers, window_permutation, shift_regions
+from diff_vit_b200.swin_quant import extract_swin_state, shift_attention_mask
+from oracle import swin_fakequant_forward as sorc
+from test_swin_golden import swin_golden, swin_model  # noqa: F401  (fixtures)
+
+
+def test_window_permutation_and_regions_match_the_reference_ops():
+    for res, ws, shift in (((14, 14), 7, 0), ((14, 14), 7, 3), ((56, 56), 7, 3), ((7, 7), 7, 0)):
+        perm = window_permutation(res, ws, shift).long()
+        x = torch.arange(res[0] * res[1], dtype=torch.float32).view(1, res[0], res[1], 1)
+        if shift:
+            x = torch.roll(x, shifts=(-shift, -shift), dims=(1, 2))
+        want = sorc._window_partition(x, ws).reshape(-1)
+        assert torch.equal(perm.float(), want)
+        assert sorted(perm.tolist()) == list(range(res[0] * res[1]))
+        reg = shift_regions(res, ws, shift)
+        mask = shift_attention_mask(res, ws, shift)
+        if shift == 0:
+            assert reg is None and mask is None
+        else:
+            r = reg.view(-1, ws * ws).long()
+            assert torch.equal((r[:, :, None] != r[:, None, :]).float() * -100.0, mask.permute(0, 2, 1))
+            assert torch.equal((r[:, None, :] != r[:, :, None]).float() * -100.0, mask)
+
+
+@pytest.mark.parametrize('tag', ['w8', 'w4'])
+def test_swin_micro_plan_on_the_host_vs_reference_golden_and_oracle(swin_model, swin_golden, tag):
+    z = swin_golden
+    state = extract_swin_state(swin_model)
+    n = num_linear_layers(state['arch'])
+    bits = [8] * n if tag == 'w8' else [4] * n
+    plan = build_swin_plan(state, bits)
+    x = z['x_eval']
+    logits, codes = hostmath.run_swin_plan(plan, x)
+    # layer by layer on identical inputs, against the oracle with exact accumulation (the q * 32^-1/2 product is not
+    # on an integer grid: an fp32 BLAS adds summation-order noise the integer engine does not have)
+    want, ref = sorc.forward(state, torch.from_numpy(x), bits, capture=True, accum='fp64',
+                             override={k: v for k, v in codes.items()})
+    assert len(ref) >= 70
+    total = 0
+    for k, r in ref.items():
+        assert k in codes, k
+        g = codes[k].astype(np.int64).reshape(r.shape)
+        np.testing.assert_array_equal(g, r.numpy().astype(np.int64), err_msg=k)
+        total += g.size
+    assert total > 500000
+    np.testing.assert_array_equal(want.numpy(), logits)
+    if tag == 'w8' and 'w8/logits' in z.files:
+        # free-running against the reference's own run (fp32 BLAS accumulation): the first block and the logits
+        for k in ('act/qact_input', 'act/patch_embed.qact', 'ln/layers.0.blocks.0.norm1', 'act/layers.0.blocks.0.attn.qact1',
+                  'act/layers.0.blocks.0.attn.qact_attn1', 'act/layers.0.blocks.0.attn.qact2',
+                  'softmax/layers.0.blocks.0.attn.log_int_softmax', 'act/layers.0.blocks.0.attn.qact3',
+                  'act/layers.0.blocks.0.qact2', 'act/layers.0.blocks.0.qact4'):
+            g = z['w8/' + k].astype(np.int64)
+            d = np.abs(codes[k].astype(np.int64).reshape(g.shape) - g)
+            assert d.max() <= 1 and (d != 0).mean() <= 1e-3, k
+        lsb = float(state['act']['act_out'][0])
+        assert np.abs(logits - z['w8/logits']).max() <= 2 * lsb
