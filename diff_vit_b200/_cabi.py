@@ -25,7 +25,7 @@ class Epilogue(C.Structure):
 class LayerNorm(C.Structure):
     _fields_ = [('in_mask', _vp), ('gamma', _vp), ('beta', _vp), ('ln_out_scale', _vp), ('ln_out_rscale', _vp),
                 ('post_mul', _vp), ('post_div1', _vp), ('post_div2', C.c_float), ('post_zp', C.c_float),
-                ('in_scale1', C.c_float), ('pot', C.c_int)]
+                ('in_scale1', C.c_float), ('pot', C.c_int), ('pre_clamp', C.c_int)]
 
 
 class Attention(C.Structure):
@@ -35,9 +35,11 @@ class Attention(C.Structure):
 
 
 class WindowAttention(C.Structure):
-    _fields_ = [('perm', _vp), ('region', _vp), ('bias', _vp), ('exp_lut', _vp), ('lut_n', C.c_int32),
+    _fields_ = [('perm', _vp), ('region', _vp), ('bias', _vp), ('exp_lut', _vp), ('r3', _vp), ('qerr', _vp),
+                ('lut_n', C.c_int32),
                 ('n', C.c_int32), ('heads', C.c_int32), ('windows', C.c_int32), ('tokens', C.c_int32),
                 ('channels', C.c_int32), ('qshift', C.c_int32), ('qscale', C.c_float), ('acc_scale', C.c_double),
+                ('qk_scale', C.c_float), ('err_mul', C.c_float),
                 ('a1_scale', C.c_float), ('a1_rscale', C.c_float), ('a2_rscale', C.c_float), ('mask_int', C.c_int32),
                 ('out_unit', C.c_float), ('out_rscale', C.c_float), ('softmax_levels', C.c_int32),
                 ('dump_a1', _vp), ('dump_a2', _vp), ('dump_softmax', _vp)]

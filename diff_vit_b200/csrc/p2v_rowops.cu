@@ -364,12 +364,16 @@ layernorm_int_pot_kernel(const int8_t* __restrict__ in, int64_t in_row_stride, i
 #pragma unroll
           for (int j = 0; j < 4; ++j) code[j] = ln_code_folded(xq[g][j], st, gg[j], bb[j]);
         }
+        if (DUMP) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) ln_codes[(int64_t)row * d + grp * 4 + j] = (int)code[j];
+        }
+        if (p.pre_clamp) {   // an int8 QAct on the LayerNorm's own grid sits in front of the re-gridding (Swin)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) code[j] = fminf(fmaxf(code[j], -128.f), 127.f);
+        }
 #pragma unroll
         for (int j = 0; j < 4; j += 2) {
-          if (DUMP) {
-            ln_codes[(int64_t)row * d + grp * 4 + j] = (int)code[j];
-            ln_codes[(int64_t)row * d + grp * 4 + j + 1] = (int)code[j + 1];
-          }
           // code * 2^k is exact: one rounding, like mul then add
           const float2 v2 = ffma2(make_float2(code[j], code[j + 1]), make_float2(pp[j], pp[j + 1]),
                                        make_float2(p.post_zp, p.post_zp));
@@ -440,8 +444,9 @@ layernorm_int_kernel(const int8_t* __restrict__ in, int64_t in_row_stride, int8_
       int q[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const float code = ln_code<POT>(xq[g][j], st, gam[j], bet[j], osc[j], ors[j]);
+        float code = ln_code<POT>(xq[g][j], st, gam[j], bet[j], osc[j], ors[j]);
         if (ln_codes != nullptr) ln_codes[(int64_t)row * d + c0 + j] = (int)code;
+        if (p.pre_clamp) code = fminf(fmaxf(code, -128.f), 127.f);
         float v;
         if (POT) {
           v = rne(fadd(fmul(code, pm[j]), p.post_zp));

@@ -28,6 +28,7 @@ namespace p2v {
 
 constexpr int kWaMaxN = 64;     // tokens per window
 constexpr int kWaHeadDim = 32;  // every Swin variant of the reference: C / heads = 32
+constexpr int kWaVtStride = 36; // words per 4-key group of V^T: 16-byte aligned rows, <= 2-way bank conflicts on the fill
 
 __device__ __forceinline__ uint32_t pack4_sat_s8(int a, int b, int c, int d) {
   uint32_t hi, r;
@@ -36,12 +37,50 @@ __device__ __forceinline__ uint32_t pack4_sat_s8(int a, int b, int c, int d) {
   return r;
 }
 __device__ __forceinline__ int sx8(uint32_t w, int j) { return (int)(int8_t)((w >> (8 * j)) & 0xffu); }
+// c + sum of (unsigned byte of a) * (signed byte of b)
+__device__ __forceinline__ int dp4a_us(uint32_t a, uint32_t b, int c) {
+  int d;
+  asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
 
+// The reference's score of one (row, key) pair, exactly: sum_c fl32(q_c * qscale) * k_c in 64-bit fixed point, one
+// rounding to fp32.  Only rows' keys whose fast evaluation lands next to a rounding tie of qact_attn1 come here.
+__device__ __noinline__ float wa_exact_score(uint4 q0, uint4 q1, const uint32_t* krow, float qscale, int qshift,
+                                             double acc_scale) {
+  const uint32_t qw[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+  const float unit = __uint_as_float((uint32_t)(127 + qshift) << 23);   // 2^qshift
+  long long acc = 0;
+#pragma unroll
+  for (int x = 0; x < 8; ++x) {
+    const uint32_t kw = krow[x];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      // fl32(code * qscale) * 2^qshift: an integer below 2^31 (see the file header), so the conversion is exact
+      const int m = __float2int_rn(fmul(fmul((float)sx8(qw[x], e), qscale), unit));
+      acc += (long long)m * sx8(kw, e);
+    }
+  }
+  return __double2float_rn(__dmul_rn(__ll2double_rn(acc), acc_scale));
+}
+
+__device__ __noinline__ int wa_exact_code(float fsum, float e, int levels) { return softmax_log_code(fsum, e, levels); }
+
+// Fast paths with exact fall-backs (both return the reference's codes; tests/test_gpu_swin.py compares every code of
+// every layer with the oracle):
+//   * score: S' = (sum_c q_c k_c) * (qscale * s^2) with the integer product from eight dp4a.  It differs from the exact
+//     S by at most sum_c |fl32(q_c qscale) - q_c qscale| * 128 * s^2 - a per-row bound taken from the 256-entry table
+//     `qerr` in the prologue -, so RNE(S' / s_a1) is the exact code unless S' / s_a1 lies within that bound (plus the
+//     fp32 rounding of S' itself) of a half-integer; those pairs (~1e-4) are redone by wa_exact_score.
+//   * log2 code: k = exponent(fma(sum, 1 / (3e), 1/6)) + 2 evaluated for a low and a high bracket of 1 / (3e)
+//     (+-2^-20, table `r3`); where the two exponents differ, or k <= 1 (the irregular first step of the code
+//     function), the pair takes softmax_log_code's IEEE division (see p2v_attention_tc.cu for the argument).
 __global__ void __launch_bounds__(kWaMaxN)
 window_attention_kernel(const int8_t* __restrict__ qkv, int8_t* __restrict__ out, const p2v_window_attention a) {
-  __shared__ int ks[kWaMaxN][kWaHeadDim];
-  __shared__ int vs[kWaMaxN][kWaHeadDim];
-  __shared__ int8_t xs[kWaMaxN][kWaMaxN];   // [key][row]: thread `row` only ever touches its own column
+  __shared__ __align__(16) uint32_t kp[kWaMaxN][8];             // K rows, packed int8
+  __shared__ __align__(16) uint32_t vt[kWaMaxN / 4][kWaVtStride];   // V^T: word [g][c] = v[4g .. 4g + 3][c]
+  __shared__ int8_t xs[kWaMaxN][kWaMaxN];                        // [key][row] qact2 codes: thread `row` owns its column
+  __shared__ uint16_t ds[kWaMaxN][kWaMaxN];                      // [key][row] distance to the row maximum (clamped)
   __shared__ uint8_t rid[kWaMaxN];
   const int n = a.n, C = a.channels;
   const int head = blockIdx.x % a.heads;
@@ -50,30 +89,40 @@ window_attention_kernel(const int8_t* __restrict__ qkv, int8_t* __restrict__ out
   const int i = threadIdx.x;
   const bool valid = i < n;
   int64_t src_row = 0;
-  int M[kWaHeadDim];
+  uint32_t qw[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  float guard = 0.f;
   if (valid) {
     src_row = (int64_t)img * a.tokens + a.perm[w * n + i];
     const int8_t* base = qkv + src_row * (3 * (int64_t)C) + head * kWaHeadDim;
-    const float unit = __uint_as_float((uint32_t)(127 + a.qshift) << 23);   // 2^qshift
+    float err = 0.f;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const uint4 q4 = *reinterpret_cast<const uint4*>(base + 16 * h);
       const uint4 k4 = *reinterpret_cast<const uint4*>(base + C + 16 * h);
       const uint4 v4 = *reinterpret_cast<const uint4*>(base + 2 * C + 16 * h);
-      const uint32_t qw[4] = {q4.x, q4.y, q4.z, q4.w}, kw[4] = {k4.x, k4.y, k4.z, k4.w}, vw[4] = {v4.x, v4.y, v4.z, v4.w};
+      const uint32_t vw[4] = {v4.x, v4.y, v4.z, v4.w};
+      qw[4 * h] = q4.x; qw[4 * h + 1] = q4.y; qw[4 * h + 2] = q4.z; qw[4 * h + 3] = q4.w;
+      *reinterpret_cast<uint4*>(&kp[i][4 * h]) = k4;
 #pragma unroll
       for (int x = 0; x < 4; ++x) {
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const int c = 16 * h + 4 * x + e;
-          // fl32(code * c32) * 2^qshift: an integer below 2^31 (see the file header), so the conversion is exact
-          M[c] = __float2int_rn(fmul(fmul((float)sx8(qw[x], e), a.qscale), unit));
-          ks[i][c] = sx8(kw[x], e);
-          vs[i][c] = sx8(vw[x], e);
+          reinterpret_cast<uint8_t*>(&vt[i >> 2][c])[i & 3] = (uint8_t)((vw[x] >> (8 * e)) & 0xffu);
+          err += __ldg(a.qerr + ((qw[4 * h + x] >> (8 * e)) & 0xffu));     // indexed by the code's byte pattern
         }
       }
     }
+    // |S' - S| / s_a1 <= err * 128 * s^2 / s_a1 (= err * err_mul); + 2^-14 for the roundings of S' itself (|t| < 2^9)
+    guard = fadd(fmul(err, a.err_mul), 6.103515625e-05f);
     rid[i] = a.region != nullptr ? a.region[w * n + i] : (uint8_t)0;
+  } else {
+    // keys beyond n: zero rows, so the dp4a groups of the P V loop can run over whole groups of four
+    *reinterpret_cast<uint4*>(&kp[i][0]) = make_uint4(0, 0, 0, 0);
+    *reinterpret_cast<uint4*>(&kp[i][4]) = make_uint4(0, 0, 0, 0);
+#pragma unroll
+    for (int c = 0; c < kWaHeadDim; ++c) reinterpret_cast<uint8_t*>(&vt[i >> 2][c])[i & 3] = 0;
+    rid[i] = 0;
   }
   __syncthreads();
   if (!valid) return;
@@ -81,53 +130,74 @@ window_attention_kernel(const int8_t* __restrict__ qkv, int8_t* __restrict__ out
   const int64_t dump_row = ((int64_t)(wg * a.heads + head) * n + i) * n;
   const float* bias_h = a.bias + (int64_t)head * n * n;
   const int my_rid = rid[i];
-  // ---- scores: exact product, the two re-quantisations, row maximum of the masked codes ----
+  // ---- scores: integer product, the two re-quantisations, row maximum of the masked codes ----
   int mx = INT_MIN;
+#pragma unroll 2
   for (int j = 0; j < n; ++j) {
-    long long acc = 0;
-#pragma unroll
-    for (int c = 0; c < kWaHeadDim; c += 4) {
-      const int4 kk = *reinterpret_cast<const int4*>(&ks[j][c]);
-      acc += (long long)M[c] * kk.x;
-      acc += (long long)M[c + 1] * kk.y;
-      acc += (long long)M[c + 2] * kk.z;
-      acc += (long long)M[c + 3] * kk.w;
-    }
-    const float s = __double2float_rn(__dmul_rn(__ll2double_rn(acc), a.acc_scale));   // one rounding
-    const float c1 = fminf(fmaxf(rintf(fmul(s, a.a1_rscale)), -128.f), 127.f);        // qact_attn1
-    const float t = fadd(fmul(c1, a.a1_scale), __ldg(bias_h + j * n + i));              // + bias (dequantized table entry)
-    const int x = (int)fminf(fmaxf(rintf(fmul(t, a.a2_rscale)), -128.f), 127.f);       // qact2
+    const uint4 k0 = *reinterpret_cast<const uint4*>(&kp[j][0]);
+    const uint4 k1 = *reinterpret_cast<const uint4*>(&kp[j][4]);
+    int acc = __dp4a((int)qw[0], (int)k0.x, 0);
+    acc = __dp4a((int)qw[1], (int)k0.y, acc);
+    acc = __dp4a((int)qw[2], (int)k0.z, acc);
+    acc = __dp4a((int)qw[3], (int)k0.w, acc);
+    acc = __dp4a((int)qw[4], (int)k1.x, acc);
+    acc = __dp4a((int)qw[5], (int)k1.y, acc);
+    acc = __dp4a((int)qw[6], (int)k1.z, acc);
+    acc = __dp4a((int)qw[7], (int)k1.w, acc);
+    float t = fmul(fmul((float)acc, a.qk_scale), a.a1_rscale);
+    float r = rintf(t);
+    if (fabsf(fsub(fabsf(fsub(t, r)), 0.5f)) < guard)       // next to a rounding tie: the exact product decides
+      r = rintf(fmul(wa_exact_score(make_uint4(qw[0], qw[1], qw[2], qw[3]), make_uint4(qw[4], qw[5], qw[6], qw[7]), &kp[j][0], a.qscale, a.qshift, a.acc_scale), a.a1_rscale));
+    const float c1 = fminf(fmaxf(r, -128.f), 127.f);                                      // qact_attn1
+    const float tb = fadd(fmul(c1, a.a1_scale), __ldg(bias_h + j * n + i));                // + bias (dequantized table entry)
+    const int x = (int)fminf(fmaxf(rintf(fmul(tb, a.a2_rscale)), -128.f), 127.f);         // qact2
     xs[j][i] = (int8_t)x;
     if (a.dump_a1 != nullptr) a.dump_a1[dump_row + j] = (int8_t)c1;
     if (a.dump_a2 != nullptr) a.dump_a2[dump_row + j] = (int8_t)x;
-    const int xm = x - (rid[j] != my_rid ? a.mask_int : 0);
-    mx = max(mx, xm);
+    mx = max(mx, x - (rid[j] != my_rid ? a.mask_int : 0));
   }
-  // ---- row sum of the integer exp ----
+  // ---- row sum of the integer exp; the distances are kept for the last pass ----
   const int dmax = a.lut_n - 1;
   double sum = 0.0;
+#pragma unroll 4
   for (int j = 0; j < n; ++j) {
     const int xm = (int)xs[j][i] - (rid[j] != my_rid ? a.mask_int : 0);
-    sum += (double)__ldg(a.exp_lut + min(mx - xm, dmax));
+    const int d = min(mx - xm, dmax);
+    ds[j][i] = (uint16_t)d;
+    sum += (double)__ldg(a.exp_lut + d);
   }
   const float fsum = __double2float_rn(sum);
-  // ---- log2 codes, P V ----
-  int O[kWaHeadDim];
+  // ---- log2 codes -> probabilities 2^(15-k) as two byte planes, four keys to a word; P V by dp4a against V^T ----
+  int oh[kWaHeadDim], ol[kWaHeadDim];
 #pragma unroll
-  for (int c = 0; c < kWaHeadDim; ++c) O[c] = 0;
-  for (int j = 0; j < n; ++j) {
-    const int xm = (int)xs[j][i] - (rid[j] != my_rid ? a.mask_int : 0);
-    const float e = __ldg(a.exp_lut + min(mx - xm, dmax));
-    const int k = softmax_log_code(fsum, e, a.softmax_levels);
-    if (a.dump_softmax != nullptr) a.dump_softmax[dump_row + j] = (uint8_t)k;
-    const int p = k >= a.softmax_levels ? 0 : (0x8000 >> k);
+  for (int c = 0; c < kWaHeadDim; ++c) oh[c] = ol[c] = 0;
+  const int levels = a.softmax_levels;
+  for (int g = 0; 4 * g < n; ++g) {
+    uint32_t ph = 0, pl = 0;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int j = 4 * g + e;
+      if (j < n) {
+        const int d = ds[j][i];
+        const float2 r3 = __ldg(reinterpret_cast<const float2*>(a.r3) + d);
+        const float ulo = ffma(fsum, r3.x, 0.16666667f), uhi = ffma(fsum, r3.y, 0.16666667f);
+        int k = (int)((__float_as_uint(ulo) >> 23) & 0xffu) - 125;
+        const int khi = (int)((__float_as_uint(uhi) >> 23) & 0xffu) - 125;
+        if (k != khi || k <= 1) k = wa_exact_code(fsum, __ldg(a.exp_lut + d), levels);
+        k = min(k, levels);
+        if (a.dump_softmax != nullptr) a.dump_softmax[dump_row + j] = (uint8_t)k;
+        const uint32_t p = k >= levels ? 0u : (0x8000u >> k);
+        ph |= (p >> 8) << (8 * e);
+        pl |= (p & 0xffu) << (8 * e);
+      }
+    }
 #pragma unroll
     for (int c = 0; c < kWaHeadDim; c += 4) {
-      const int4 vv = *reinterpret_cast<const int4*>(&vs[j][c]);
-      O[c] += p * vv.x;
-      O[c + 1] += p * vv.y;
-      O[c + 2] += p * vv.z;
-      O[c + 3] += p * vv.w;
+      const uint4 vv = *reinterpret_cast<const uint4*>(&vt[g][c]);
+      oh[c] = dp4a_us(ph, vv.x, oh[c]);         ol[c] = dp4a_us(pl, vv.x, ol[c]);
+      oh[c + 1] = dp4a_us(ph, vv.y, oh[c + 1]); ol[c + 1] = dp4a_us(pl, vv.y, ol[c + 1]);
+      oh[c + 2] = dp4a_us(ph, vv.z, oh[c + 2]); ol[c + 2] = dp4a_us(pl, vv.z, ol[c + 2]);
+      oh[c + 3] = dp4a_us(ph, vv.w, oh[c + 3]); ol[c + 3] = dp4a_us(pl, vv.w, ol[c + 3]);
     }
   }
   // ---- qact3 and the store, back through the permutation ----
@@ -137,7 +207,8 @@ window_attention_kernel(const int8_t* __restrict__ qkv, int8_t* __restrict__ out
     int q[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      const float val = fmul(__int2float_rn(O[4 * x + e]), a.out_unit);    // the fp32 value of (attn @ v): one rounding
+      const int o = oh[4 * x + e] * 256 + ol[4 * x + e];
+      const float val = fmul(__int2float_rn(o), a.out_unit);    // the fp32 value of (attn @ v): one rounding
       q[e] = (int)rintf(fmul(val, a.out_rscale));
     }
     w8[x] = pack4_sat_s8(q[0], q[1], q[2], q[3]);
@@ -223,11 +294,13 @@ using namespace p2v;
 
 extern "C" int p2v_window_attention_int(const int8_t* qkv, int8_t* out, int images, const p2v_window_attention* p,
                                         void* stream) {
-  P2V_REQUIRE(qkv && out && p && p->perm && p->bias && p->exp_lut, "p2v_window_attention_int: null pointer");
+  P2V_REQUIRE(qkv && out && p && p->perm && p->bias && p->exp_lut && p->r3 && p->qerr,
+              "p2v_window_attention_int: null pointer");
   P2V_REQUIRE(images > 0 && p->n > 0 && p->n <= kWaMaxN && p->heads > 0 && p->windows > 0,
               "p2v_window_attention_int: bad shape images=%d n=%d heads=%d windows=%d", images, p->n, p->heads, p->windows);
   P2V_REQUIRE(p->channels == p->heads * kWaHeadDim, "p2v_window_attention_int: channels=%d is not heads * 32", p->channels);
   P2V_REQUIRE(p->tokens == p->windows * p->n, "p2v_window_attention_int: tokens=%d is not windows * n", p->tokens);
+  P2V_REQUIRE(p->lut_n <= 65536, "p2v_window_attention_int: table of %d entries (at most 65536)", p->lut_n);
   P2V_REQUIRE(p->lut_n >= 1 && p->qshift >= 0 && p->qshift <= 60 && p->softmax_levels >= 1 && p->softmax_levels <= 16,
               "p2v_window_attention_int: bad table / shift / levels");
   P2V_REQUIRE((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,

@@ -124,6 +124,7 @@ class LayerNormPlan:
     post_zp: float
     in_scale1: float
     pot: int
+    pre_clamp: int = 0         # the LN code passes an int8 QAct of its own grid before the re-gridding (Swin)
 
 
 @dataclass
@@ -409,7 +410,10 @@ def _unflatten(z, prefix):
         return [_unflatten(z, '%s/%d' % (prefix, i)) for i in range(int(z[prefix + '/__len__']))]
     if prefix + '/__class__' in z:
         cls = _PLAN_CLASSES[str(z[prefix + '/__class__'])]
-        return cls(**{f: _unflatten(z, prefix + '/' + f) for f in cls.__dataclass_fields__})
+        import dataclasses
+        have = lambda f: any(k == prefix + '/' + f or k.startswith(prefix + '/' + f + '/') for k in z)
+        return cls(**{f.name: _unflatten(z, prefix + '/' + f.name) for f in dataclasses.fields(cls)
+                      if have(f.name) or f.default is dataclasses.MISSING})    # fields newer than the file keep defaults
     a = z[prefix]
     if a.ndim == 0:
         return a.item()

@@ -10,7 +10,7 @@ the head; the cyclic shift and the window partition are index permutations insid
 
 Per block (models/swin_quant.py:345-399, WindowAttention.forward :177-221, Mlp models/layers_quant.py:304-346):
   LN1 + qact1  ->  qkv GEMM + attn.qact1  ->  window attention (.. qact3)  ->  proj GEMM + qact4 + shortcut + qact2
-  ->  LN2 + qact3  ->  / SmoothQuant scale + mlp.qact0  ->  fc1 GEMM + GELU + qact1  ->  fc2 GEMM + qact2 + residual + qact4
+  ->  LN2 + qact3 + / SmoothQuant scale + mlp.qact0 (one launch)  ->  fc1 GEMM + GELU + qact1  ->  fc2 GEMM + qact2 + residual + qact4
 
 Scope: symmetric quantizers on power-of-two grids for the layer-wise activations (the minmax observer of config 5);
 anything else raises NotImplementedError and the model keeps its per-module path.
@@ -139,12 +139,23 @@ class _SwinBuilder(_Builder):
         m = (codes * np.float32(qscale)).astype(np.float32).astype(np.float64) * 2.0 ** qshift
         if not (np.all(m == np.rint(m)) and np.abs(m).max() < 2.0 ** 31):
             raise NotImplementedError('q scaling %g does not fit the fixed-point product' % qscale)
+        # the fast score path's error table: |fl32(code * qscale) - code * qscale| per code BYTE, rounded up
+        cb = np.arange(256)
+        cv = np.where(cb < 128, cb, cb - 256).astype(np.float64)
+        exact = cv * float(np.float32(qscale))
+        t32 = (cv.astype(np.float32) * np.float32(qscale)).astype(np.float32).astype(np.float64)
+        qerr = torch.from_numpy(np.nextafter(np.abs(t32 - exact).astype(np.float32), np.float32(np.inf)) *
+                                (np.abs(t32 - exact) > 0))
+        lut = swin_exp_lut(torch.tensor(s2))
+        r = 1.0 / (3.0 * lut.double())
+        r3 = torch.stack([(r * (1.0 - 2.0 ** -20)).float(), (r * (1.0 + 2.0 ** -20)).float()], -1).contiguous()
         mask = 100.0 / s2
         if mask != int(mask):
             raise NotImplementedError('%s: 100 / qact2 scale is not an integer' % pre)
         return NS(perm=window_permutation(res, ws, shift), region=shift_regions(res, ws, shift),
                   bias=bias.permute(2, 1, 0).contiguous(),               # [head][key][row]
-                  table_codes=tq.to(torch.int32), exp_lut=swin_exp_lut(torch.tensor(s2)),
+                  table_codes=tq.to(torch.int32), exp_lut=lut, r3=r3, qerr=qerr.float().contiguous(),
+                  qk_scale=qscale * s1 * s1, err_mul=128.0 * s1 * s1 / sa,
                   n=n, heads=heads, windows=(res[0] // ws) * (res[1] // ws), tokens=res[0] * res[1], channels=dim,
                   qshift=qshift, qscale=qscale, acc_scale=s1 * s1 * 2.0 ** -qshift, a1_scale=sa, a1_rscale=1.0 / sa,
                   a2_rscale=1.0 / s2, mask_int=int(mask), out_unit=2.0 ** -15 * s1, out_rscale=1.0 / s3,
@@ -156,16 +167,21 @@ class _SwinBuilder(_Builder):
         s3 = self.pot_scalar(pre + '.qact3')
         s0 = self.pot_scalar(pre + '.mlp.qact0')
         d = cs.numel()
+        # LN2 + qact3 + (/ channel_scale) + mlp.qact0 as ONE LayerNorm launch: the LN code is clamped to int8 (qact3 has
+        # the LayerNorm's own grid) and re-gridded by s3 / (cs[c] * s0) - a power of two when the SmoothQuant scales are
+        # (multiply, exact); otherwise the kernel's division path divides by cs[c] and by s0 like the reference
+        norm2 = self.ln_plan(self.act(pre + '.qact2')[0], P[pre + '.norm2.weight'], P[pre + '.norm2.bias'], pre + '.qact3')
+        norm2.pre_clamp = 1
+        norm2.post_mul = (s3 / (cs.reshape(-1) * s0)).contiguous()
+        norm2.post_div1, norm2.post_div2 = cs.reshape(-1).contiguous().clone(), s0
+        norm2.pot = int(bool(norm2.pot) and is_pot(cs))
         return NS(
             norm1=self.ln_plan(self.act(in_name)[0], P[pre + '.norm1.weight'], P[pre + '.norm1.bias'], pre + '.qact1'),
             qkv=self.linear(pre + '.attn.qkv', P[pre + '.attn.qkv.weight'], bits[0], pre + '.qact1', pre + '.attn.qact1'),
             attn=self.window_attention(pre + '.attn', heads, res, ws, shift),
             proj=self.linear(pre + '.attn.proj', P[pre + '.attn.proj.weight'], bits[1], pre + '.attn.qact3',
                              pre + '.attn.qact4', residual=(in_name, pre + '.qact2')),
-            norm2=self.ln_plan(self.act(pre + '.qact2')[0], P[pre + '.norm2.weight'], P[pre + '.norm2.bias'], pre + '.qact3'),
-            # y / channel_scale -> mlp.qact0: codes of qact3 times s3, divided by cs[c] * s0 (s0 a power of two, so the
-            # two divisions of the reference are one)
-            requant_in=torch.full((d,), s3), requant_out=(cs.reshape(-1) * s0).contiguous(),
+            norm2=norm2,
             fc1=self.linear(pre + '.mlp.fc1', P[pre + '.mlp.fc1.weight'] * cs.reshape(1, -1), bits[2], pre + '.mlp.qact0',
                             pre + '.mlp.qact1', gelu=True),
             fc2=self.linear(pre + '.mlp.fc2', P[pre + '.mlp.fc2.weight'], bits[3], pre + '.mlp.qact1', pre + '.mlp.qact2',
@@ -234,7 +250,7 @@ class _Bound:
         self.stages = []
         for st in plan.stages:
             blocks = [NS(norm1=self.ln(b.norm1), qkv=self.linear(b.qkv), attn=self.attn(b.attn), proj=self.linear(b.proj),
-                         norm2=self.ln(b.norm2), requant_in=self.up(b.requant_in), requant_out=self.up(b.requant_out),
+                         norm2=self.ln(b.norm2),
                          fc1=self.linear(b.fc1), fc2=self.linear(b.fc2), plan=b) for b in st.blocks]
             merge = None
             if st.merge is not None:
@@ -269,11 +285,13 @@ class _Bound:
         d.ln_out_scale, d.ln_out_rscale = self.p(p.ln_out_scale), self.p(p.ln_out_rscale)
         d.post_mul, d.post_div1 = self.p(p.post_mul), self.p(p.post_div1)
         d.post_div2, d.post_zp, d.in_scale1, d.pot = p.post_div2, p.post_zp, p.in_scale1, p.pot
+        d.pre_clamp = int(getattr(p, 'pre_clamp', 0))
         return d
 
     def attn(self, a):
         d = _cabi.WindowAttention()
         d.perm, d.region, d.bias, d.exp_lut = self.p(a.perm), self.p(a.region), self.p(a.bias), self.p(a.exp_lut)
+        d.r3, d.qerr, d.qk_scale, d.err_mul = self.p(a.r3), self.p(a.qerr), a.qk_scale, a.err_mul
         d.lut_n = a.exp_lut.numel()
         d.n, d.heads, d.windows, d.tokens, d.channels = a.n, a.heads, a.windows, a.tokens, a.channels
         d.qshift, d.qscale, d.acc_scale = a.qshift, a.qscale, a.acc_scale
@@ -409,19 +427,15 @@ class SwinIntegerEngine:
                     put('act/' + pre + '.attn.qact3', win(att, Cd))
                     put('act/' + pre + '.attn.qact4', win(aux, Cd))
                     put('act/' + pre + '.qact2', x1.view(b, L, Cd))
-                y2 = self.buf('ln_out', rows, Cd)
-                self._ln(x1, blk.norm2, y2, rows, Cd, lnc)
-                m0 = self.buf('mlp_in', rows, Cd)
-                _cabi.check(lib.p2v_requant_eltwise(y2.data_ptr(), None, m0.data_ptr(), rows, Cd, blk.requant_in.data_ptr(),
-                                                    None, blk.requant_out.data_ptr(), 0.0, st))
-                self.launches += 1
+                m0 = self.buf('ln_out', rows, Cd)
+                self._ln(x1, blk.norm2, m0, rows, Cd, lnc)      # LN2 + qact3 + / channel scale + mlp.qact0
                 hid = self.buf('hidden', rows, blk.fc1.n)
                 self._gemm(m0, blk.fc1, hid, rows)
                 xn = self.buf('stream%d' % ((bi + 1) % 2), rows, Cd)
                 self._gemm(hid, blk.fc2, xn, rows, residual=x1, aux=aux)
                 if dump is not None:
                     put('ln/' + pre + '.norm2', lnc.view(b, L, Cd))
-                    put('act/' + pre + '.qact3', y2.view(b, L, Cd))
+                    put('act/' + pre + '.qact3', lnc.view(b, L, Cd).clamp(-128, 127))
                     put('act/' + pre + '.mlp.qact0', m0.view(b, L, Cd))
                     put('act/' + pre + '.mlp.qact1', hid.view(b, L, blk.fc1.n))
                     put('act/' + pre + '.mlp.qact2', aux.view(b, L, Cd))

@@ -124,6 +124,8 @@ typedef struct p2v_layernorm {
   float post_zp;
   float in_scale1;             /* min over channels of the input scale */
   int pot;
+  int pre_clamp;               /* non-zero: the LN code passes an int8 QAct of its own grid (clamp to [-128, 127]) before
+                                  the re-gridding - Swin's block.qact3 in front of Mlp's qact0 (swin_quant.py:392-394) */
 } p2v_layernorm;
 int p2v_layernorm_int(const int8_t* in, int64_t in_row_stride, int8_t* out, int32_t* ln_codes, int rows,
                       int d, const p2v_layernorm* p, void* stream);
@@ -180,11 +182,15 @@ typedef struct p2v_window_attention {
   const uint8_t* region;   /* [windows * n] region id of the shift mask (swin_quant.py:317-340); NULL without a shift   */
   const float* bias;       /* [heads][n (key)][n (row)] dequantized qact_table entry of the pair's relative position    */
   const float* exp_lut;    /* [lut_n] integer exp of d = rowmax - x (layers.py:334-358); d >= lut_n reads the last one  */
+  const float* r3;         /* [lut_n][2] fl32((1 -+ 2^-20) / (3 exp_lut[d])): brackets of the fast log2 code            */
+  const float* qerr;       /* [256] |fl32(code * qscale) - code * qscale| rounded up, indexed by the code's BYTE        */
   int32_t lut_n;
   int32_t n, heads, windows, tokens, channels;   /* tokens = windows * n per image, channels = heads * 32              */
   int32_t qshift;          /* fl32(code * qscale) * 2^qshift is an integer below 2^31 for every int8 code              */
   float qscale;            /* head_dim^-1/2 as fp32 (swin_quant.py:83,190)                                             */
   double acc_scale;        /* s_qkv^2 * 2^-qshift                                                                      */
+  float qk_scale;          /* qscale * s_qkv^2 (exact in fp32): the fast score is (sum_c q_c k_c) * qk_scale           */
+  float err_mul;           /* 128 * s_qkv^2 / s_a1: turns a row's summed qerr into a bound in units of the a1 grid     */
   float a1_scale, a1_rscale;   /* qact_attn1 grid and its exact reciprocal                                             */
   float a2_rscale;         /* 1 / s of qact2                                                                           */
   int32_t mask_int;        /* 100 / s of qact2 (an integer)                                                            */

@@ -51,6 +51,16 @@ def gemm_epilogue(a, lp, residual=None, want_f32=False):
 
 
 def layernorm(x, row_stride, rows, d, p):
+    if getattr(p, 'pre_clamp', 0):
+        # an int8 QAct on the LayerNorm's own grid in front of the re-gridding (Swin): LN to its clamped codes, then
+        # the reference's two divisions (/ channel scale, / consumer scale)
+        import copy
+        q = copy.copy(p)
+        q.pre_clamp, q.post_mul, q.post_div1, q.post_div2 = 0, np.ones(d, np.float32), _f(p.ln_out_scale), 1.0
+        clamped, codes = layernorm(x, row_stride, rows, d, q)
+        v = (clamped.astype(np.float32) * _f(p.ln_out_scale)[None, :]).astype(np.float32)
+        v = ((v / _f(p.post_div1)[None, :]).astype(np.float32) / np.float32(p.post_div2)).astype(np.float32)
+        return np.clip(np.rint(v), -128, 127).astype(np.int8), codes
     out = np.empty((rows, d), np.int8)
     codes = np.empty((rows, d), np.int32)
     keep = [_f(p.in_mask), _f(p.gamma), _f(p.beta), _f(p.ln_out_scale), _f(p.ln_out_rscale), _f(p.post_mul), _f(p.post_div1)]
@@ -155,12 +165,6 @@ def window_attention(qkv, images, p):
         kk.astype(np.uint8).reshape(shape)
 
 
-def requant(a, a_scale, out_scale):
-    f32 = np.float32
-    v = (a.astype(f32) * _f(a_scale)[None, :]).astype(f32)
-    return np.clip(np.rint((v / _f(out_scale)[None, :]).astype(f32)), -128, 127).astype(np.int8)
-
-
 def run_swin_plan(plan, x):
     """x: float32 numpy [b, c, h, w].  Returns (logits fp32, {golden-style key: codes}) - the launch sequence of
     diff_vit_b200.swin_engine.SwinIntegerEngine._run on the host."""
@@ -198,9 +202,8 @@ def run_swin_plan(plan, x):
             codes['act/' + pre + '.attn.qact3'] = win(att, Cd)
             x1, aux, _ = gemm_epilogue(att, blk.proj, residual=xs)
             codes['act/' + pre + '.attn.qact4'], codes['act/' + pre + '.qact2'] = win(aux, Cd), x1
-            y2, ln = layernorm(x1, Cd, rows, Cd, blk.norm2)
-            codes['ln/' + pre + '.norm2'], codes['act/' + pre + '.qact3'] = ln, y2
-            m0 = requant(y2, blk.requant_in, blk.requant_out)
+            m0, ln = layernorm(x1, Cd, rows, Cd, blk.norm2)
+            codes['ln/' + pre + '.norm2'], codes['act/' + pre + '.qact3'] = ln, np.clip(ln, -128, 127)
             codes['act/' + pre + '.mlp.qact0'] = m0
             hid, _, _ = gemm_epilogue(m0, blk.fc1)
             codes['act/' + pre + '.mlp.qact1'] = hid
