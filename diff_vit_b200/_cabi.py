@@ -35,7 +35,7 @@ class Attention(C.Structure):
 
 
 class WindowAttention(C.Structure):
-    _fields_ = [('perm', _vp), ('region', _vp), ('bias', _vp), ('exp_lut', _vp), ('r3', _vp), ('qerr', _vp),
+    _fields_ = [('perm', _vp), ('region', _vp), ('bias', _vp), ('exp_lut', _vp), ('r3', _vp), ('exp_lut64', _vp),
                 ('lut_n', C.c_int32),
                 ('n', C.c_int32), ('heads', C.c_int32), ('windows', C.c_int32), ('tokens', C.c_int32),
                 ('channels', C.c_int32), ('qshift', C.c_int32), ('qscale', C.c_float), ('acc_scale', C.c_double),

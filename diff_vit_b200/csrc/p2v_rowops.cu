@@ -245,13 +245,18 @@ __device__ __forceinline__ int sext_byte(uint32_t w, int j) {
 // G = 4-channel groups per lane.  FULL: d == 128 * G (no partial group).  DUMP: also write the unclamped LN codes.
 // SM: the per-channel constants live in shared memory (4 x 128 G floats, dynamic) instead of registers - for
 // d > 384 (DeiT-B / ViT-B: 768), where 16 G constant registers per lane no longer fit beside the row.
-template <int G, bool FULL, bool DUMP, bool SM = false>
+// LPR = lanes per row: narrow rows (Swin's d = 96 / 192 = 4 * 3 * LPR) put 32 / LPR rows side by side in a warp, so the
+// per-row chain (statistics, three IEEE divisions, the square root) serves that many rows per issue slot; the row sums
+// are then reduced by shuffles inside each LPR-lane segment.  LPR = 32 is the one-row-per-warp kernel.
+template <int G, bool FULL, bool DUMP, bool SM = false, int LPR = 32>
 __global__ void __launch_bounds__(256, 2)
 layernorm_int_pot_kernel(const int8_t* __restrict__ in, int64_t in_row_stride, int8_t* __restrict__ out,
                          int32_t* __restrict__ ln_codes, int rows, int d, const p2v_layernorm p) {
   pdl_launch_dependents();
-  const int lane = threadIdx.x & 31;
-  const int warps_total = gridDim.x * (blockDim.x >> 5);
+  constexpr int RPW = 32 / LPR;                         // rows per warp and step
+  const int lane = LPR == 32 ? (threadIdx.x & 31) : (threadIdx.x & (LPR - 1));   // lane within its row
+  const int rsel = LPR == 32 ? 0 : ((threadIdx.x & 31) / LPR);
+  const int warps_total = gridDim.x * (blockDim.x >> 5) * RPW;
   const int groups = d >> 2;
   constexpr int GR = SM ? 1 : G;     // register copies only without SM
   float go[GR][4], bo[GR][4], pm[GR][4];
@@ -270,7 +275,7 @@ layernorm_int_pot_kernel(const int8_t* __restrict__ in, int64_t in_row_stride, i
   }
 #pragma unroll
   for (int g = 0; g < GR; ++g) {
-    const int grp = g * 32 + lane;
+    const int grp = g * LPR + lane;
     if (SM) {
     } else if (FULL || grp < groups) {
       const int c0 = grp * 4;
@@ -292,18 +297,19 @@ layernorm_int_pot_kernel(const int8_t* __restrict__ in, int64_t in_row_stride, i
   pdl_wait();   // everything above is static; the rows are the previous kernel's output
   // software pipeline: the next row's codes are in flight while this row is normalised
   uint32_t next_w[G];
-  int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  int wrow = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW;   // first row of this warp's step (uniform)
+  int row = wrow + rsel;
 #pragma unroll
   for (int g = 0; g < G; ++g) {
-    const int grp = g * 32 + lane;
+    const int grp = g * LPR + lane;
     next_w[g] = (row < rows && (FULL || grp < groups)) ? ld_act_u32(in + (int64_t)row * in_row_stride + grp * 4) : 0u;
   }
-  for (; row < rows; row += warps_total) {
+  for (; wrow < rows; wrow += warps_total, row += warps_total) {
     uint32_t cur_w[G];
     const int nrow = row + warps_total;
 #pragma unroll
     for (int g = 0; g < G; ++g) {
-      const int grp = g * 32 + lane;
+      const int grp = g * LPR + lane;
       cur_w[g] = next_w[g];
       next_w[g] = (nrow < rows && (FULL || grp < groups)) ? ld_act_u32(in + (int64_t)nrow * in_row_stride + grp * 4) : 0u;
     }
@@ -313,7 +319,7 @@ layernorm_int_pot_kernel(const int8_t* __restrict__ in, int64_t in_row_stride, i
     for (int g = 0; g < G; ++g) {
       int mg[4];
       if (SM) {
-        const float4 m4 = *reinterpret_cast<const float4*>(ln_const + 3 * 128 * G + (g * 32 + lane) * 4);
+        const float4 m4 = *reinterpret_cast<const float4*>(ln_const + 3 * 128 * G + (g * LPR + lane) * 4);
         mg[0] = (int)m4.x; mg[1] = (int)m4.y; mg[2] = (int)m4.z; mg[3] = (int)m4.w;
       } else {
 #pragma unroll
@@ -330,15 +336,25 @@ layernorm_int_pot_kernel(const int8_t* __restrict__ in, int64_t in_row_stride, i
     }
     // warp totals with the REDUX unit (one instruction per 32-bit value instead of five shuffle / add rounds); the
     // sum of squares can pass 2^32 for large masks, so its two 16-bit halves are reduced separately
-    sum = __reduce_add_sync(0xffffffffu, sum);
-    const unsigned sq_lo = __reduce_add_sync(0xffffffffu, (unsigned)sumsq & 0xffffu);
-    const unsigned sq_hi = __reduce_add_sync(0xffffffffu, (unsigned)sumsq >> 16);
-    const long long sumsq64 = ((long long)sq_hi << 16) + (long long)sq_lo;
+    long long sumsq64;
+    if (LPR == 32) {
+      sum = __reduce_add_sync(0xffffffffu, sum);
+      const unsigned sq_lo = __reduce_add_sync(0xffffffffu, (unsigned)sumsq & 0xffffu);
+      const unsigned sq_hi = __reduce_add_sync(0xffffffffu, (unsigned)sumsq >> 16);
+      sumsq64 = ((long long)sq_hi << 16) + (long long)sq_lo;
+    } else {
+      sumsq64 = (long long)(unsigned)sumsq;
+#pragma unroll
+      for (int o = LPR / 2; o > 0; o >>= 1) {   // xor offsets below LPR stay inside the row's lane segment
+        sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        sumsq64 += __shfl_xor_sync(0xffffffffu, sumsq64, o);
+      }
+    }
     const LnRow st = ln_row_stats((long long)sum, sumsq64, d, p.in_scale1, scale_over_c);
 #pragma unroll
     for (int g = 0; g < G; ++g) {
-      const int grp = g * 32 + lane;
-      if (FULL || grp < groups) {
+      const int grp = g * LPR + lane;
+      if ((FULL || grp < groups) && (LPR == 32 || row < rows)) {
         float v[4], code[4], gg[4], bb[4], pp[4];
         if (SM) {
           const float4 g4 = *reinterpret_cast<const float4*>(ln_const + grp * 4);
@@ -569,6 +585,15 @@ extern "C" int p2v_layernorm_int(const int8_t* in, int64_t in_row_stride, int8_t
     if (ln_codes) P2V_CHECK_CUDA(launch_pdl(2, layernorm_int_pot_kernel<G_, false, true, true>, dim3(pgrid), dim3(warps * 32), smem, st, in, in_row_stride, out, ln_codes, rows, d, *p)); \
     else P2V_CHECK_CUDA(launch_pdl(2, layernorm_int_pot_kernel<G_, false, false, true>, dim3(pgrid), dim3(warps * 32), smem, st, in, in_row_stride, out, ln_codes, rows, d, *p));        \
   } while (0)
+    // rows of 96 / 192 channels (Swin stages 1 and 2): four / two rows per warp
+    if (d == 96 || d == 192) {
+      const int lpr = d / 12, rgrid = (rows + warps * (32 / lpr) - 1) / (warps * (32 / lpr));
+      const int ngrid = rgrid < kNumSMs * 2 ? rgrid : kNumSMs * 2;
+      if (lpr == 8 && ln_codes) P2V_CHECK_CUDA(launch_pdl(2, layernorm_int_pot_kernel<3, true, true, false, 8>, dim3(ngrid), dim3(warps * 32), 0, st, in, in_row_stride, out, ln_codes, rows, d, *p));
+      else if (lpr == 8) P2V_CHECK_CUDA(launch_pdl(2, layernorm_int_pot_kernel<3, true, false, false, 8>, dim3(ngrid), dim3(warps * 32), 0, st, in, in_row_stride, out, ln_codes, rows, d, *p));
+      else if (ln_codes) P2V_CHECK_CUDA(launch_pdl(2, layernorm_int_pot_kernel<3, true, true, false, 16>, dim3(ngrid), dim3(warps * 32), 0, st, in, in_row_stride, out, ln_codes, rows, d, *p));
+      else P2V_CHECK_CUDA(launch_pdl(2, layernorm_int_pot_kernel<3, true, false, false, 16>, dim3(ngrid), dim3(warps * 32), 0, st, in, in_row_stride, out, ln_codes, rows, d, *p));
+    } else
     if (groups == 1) P2V_LN_LAUNCH(1);
     else if (groups == 2) P2V_LN_LAUNCH(2);
     else if (groups == 3) P2V_LN_LAUNCH(3);

@@ -68,13 +68,17 @@ __device__ __noinline__ int wa_exact_code(float fsum, float e, int levels) { ret
 
 // Fast paths with exact fall-backs (both return the reference's codes; tests/test_gpu_swin.py compares every code of
 // every layer with the oracle):
-//   * score: S' = (sum_c q_c k_c) * (qscale * s^2) with the integer product from eight dp4a.  It differs from the exact
-//     S by at most sum_c |fl32(q_c qscale) - q_c qscale| * 128 * s^2 - a per-row bound taken from the 256-entry table
-//     `qerr` in the prologue -, so RNE(S' / s_a1) is the exact code unless S' / s_a1 lies within that bound (plus the
-//     fp32 rounding of S' itself) of a half-integer; those pairs (~1e-4) are redone by wa_exact_score.
+//   * score: S' = (sum_c q_c k_c) * (qscale * s^2) with the integer product from eight dp4a.  fl32 rounds within
+//     2^-24 relative, so S' differs from the exact S by at most 2^-24 qscale sum_c |q_c| * 128 * s^2 - a per-row bound
+//     from the prologue -, and RNE(S' / s_a1) is the exact code unless S' / s_a1 lies within that bound (plus the fp32
+//     rounding of S' itself) of a half-integer; those pairs (~1e-4) are redone by wa_exact_score.
+//   * both re-quantisations round with the 1.5 * 2^23 constant on the FMA pipe after the clamp (clamp and RNE commute
+//     for integer bounds); the int8 code is the low byte of the biased sum: no FRND / F2I (conversion unit, quarter
+//     rate) in the loop.
 //   * log2 code: k = exponent(fma(sum, 1 / (3e), 1/6)) + 2 evaluated for a low and a high bracket of 1 / (3e)
 //     (+-2^-20, table `r3`); where the two exponents differ, or k <= 1 (the irregular first step of the code
 //     function), the pair takes softmax_log_code's IEEE division (see p2v_attention_tc.cu for the argument).
+template <bool kDump>
 __global__ void __launch_bounds__(kWaMaxN)
 window_attention_kernel(const int8_t* __restrict__ qkv, int8_t* __restrict__ out, const p2v_window_attention a) {
   __shared__ __align__(16) uint32_t kp[kWaMaxN][8];             // K rows, packed int8
@@ -82,6 +86,7 @@ window_attention_kernel(const int8_t* __restrict__ qkv, int8_t* __restrict__ out
   __shared__ int8_t xs[kWaMaxN][kWaMaxN];                        // [key][row] qact2 codes: thread `row` owns its column
   __shared__ uint16_t ds[kWaMaxN][kWaMaxN];                      // [key][row] distance to the row maximum (clamped)
   __shared__ uint8_t rid[kWaMaxN];
+  constexpr float kMagic = 12582912.0f;   // 1.5 * 2^23
   const int n = a.n, C = a.channels;
   const int head = blockIdx.x % a.heads;
   const int wg = blockIdx.x / a.heads;            // window over the whole batch
@@ -94,7 +99,7 @@ window_attention_kernel(const int8_t* __restrict__ qkv, int8_t* __restrict__ out
   if (valid) {
     src_row = (int64_t)img * a.tokens + a.perm[w * n + i];
     const int8_t* base = qkv + src_row * (3 * (int64_t)C) + head * kWaHeadDim;
-    float err = 0.f;
+    uint32_t qabs = 0;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const uint4 q4 = *reinterpret_cast<const uint4*>(base + 16 * h);
@@ -105,16 +110,15 @@ window_attention_kernel(const int8_t* __restrict__ qkv, int8_t* __restrict__ out
       *reinterpret_cast<uint4*>(&kp[i][4 * h]) = k4;
 #pragma unroll
       for (int x = 0; x < 4; ++x) {
+        qabs = __dp4a(__vabsss4(qw[4 * h + x]), 0x01010101u, qabs);   // sum |q_c| (|-128| counted as 127: + 32 below)
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int c = 16 * h + 4 * x + e;
-          reinterpret_cast<uint8_t*>(&vt[i >> 2][c])[i & 3] = (uint8_t)((vw[x] >> (8 * e)) & 0xffu);
-          err += __ldg(a.qerr + ((qw[4 * h + x] >> (8 * e)) & 0xffu));     // indexed by the code's byte pattern
-        }
+        for (int e = 0; e < 4; ++e)
+          reinterpret_cast<uint8_t*>(&vt[i >> 2][16 * h + 4 * x + e])[i & 3] = (uint8_t)(vw[x] >> (8 * e));
       }
     }
-    // |S' - S| / s_a1 <= err * 128 * s^2 / s_a1 (= err * err_mul); + 2^-14 for the roundings of S' itself (|t| < 2^9)
-    guard = fadd(fmul(err, a.err_mul), 6.103515625e-05f);
+    // |S' - S| / s_a1 <= 2^-24 qscale sum|q_c| * 128 s^2 / s_a1 = sum|q_c| * err_mul; + 2^-14 for the roundings of S'
+    // itself (|t| < 2^9 wherever the code is not saturated)
+    guard = fadd(fmul((float)(qabs + 32u), a.err_mul), 6.103515625e-05f);
     rid[i] = a.region != nullptr ? a.region[w * n + i] : (uint8_t)0;
   } else {
     // keys beyond n: zero rows, so the dp4a groups of the P V loop can run over whole groups of four
@@ -128,8 +132,10 @@ window_attention_kernel(const int8_t* __restrict__ qkv, int8_t* __restrict__ out
   if (!valid) return;
 
   const int64_t dump_row = ((int64_t)(wg * a.heads + head) * n + i) * n;
-  const float* bias_h = a.bias + (int64_t)head * n * n;
+  const float* bias_p = a.bias + (int64_t)head * n * n + i;
   const int my_rid = rid[i];
+  const int mask_int = a.mask_int;
+  const float qk_scale = a.qk_scale, a1_rscale = a.a1_rscale, a1_scale = a.a1_scale, a2_rscale = a.a2_rscale;
   // ---- scores: integer product, the two re-quantisations, row maximum of the masked codes ----
   int mx = INT_MIN;
 #pragma unroll 2
@@ -144,52 +150,56 @@ window_attention_kernel(const int8_t* __restrict__ qkv, int8_t* __restrict__ out
     acc = __dp4a((int)qw[5], (int)k1.y, acc);
     acc = __dp4a((int)qw[6], (int)k1.z, acc);
     acc = __dp4a((int)qw[7], (int)k1.w, acc);
-    float t = fmul(fmul((float)acc, a.qk_scale), a.a1_rscale);
-    float r = rintf(t);
-    if (fabsf(fsub(fabsf(fsub(t, r)), 0.5f)) < guard)       // next to a rounding tie: the exact product decides
-      r = rintf(fmul(wa_exact_score(make_uint4(qw[0], qw[1], qw[2], qw[3]), make_uint4(qw[4], qw[5], qw[6], qw[7]), &kp[j][0], a.qscale, a.qshift, a.acc_scale), a.a1_rscale));
-    const float c1 = fminf(fmaxf(r, -128.f), 127.f);                                      // qact_attn1
-    const float tb = fadd(fmul(c1, a.a1_scale), __ldg(bias_h + j * n + i));                // + bias (dequantized table entry)
-    const int x = (int)fminf(fmaxf(rintf(fmul(tb, a.a2_rscale)), -128.f), 127.f);         // qact2
+    const float bias = __ldg(bias_p + j * n);
+    const float t = fminf(fmaxf(fmul(fmul((float)acc, qk_scale), a1_rscale), -128.f), 127.f);
+    float c1 = fsub(fadd(t, kMagic), kMagic);                  // qact_attn1: RNE of the clamped value
+    if (fabsf(fsub(fabsf(fsub(t, c1)), 0.5f)) < guard) {       // next to a rounding tie: the exact product decides
+      const float te = fmul(wa_exact_score(make_uint4(qw[0], qw[1], qw[2], qw[3]), make_uint4(qw[4], qw[5], qw[6], qw[7]),
+                                           &kp[j][0], a.qscale, a.qshift, a.acc_scale), a1_rscale);
+      c1 = fsub(fadd(fminf(fmaxf(te, -128.f), 127.f), kMagic), kMagic);
+    }
+    const float tb = fminf(fmaxf(fmul(fadd(fmul(c1, a1_scale), bias), a2_rscale), -128.f), 127.f);   // + bias, qact2
+    const int x = (int)(int8_t)(__float_as_uint(fadd(tb, kMagic)) & 0xffu);   // low byte of 1.5 * 2^23 + RNE(tb)
     xs[j][i] = (int8_t)x;
-    if (a.dump_a1 != nullptr) a.dump_a1[dump_row + j] = (int8_t)c1;
-    if (a.dump_a2 != nullptr) a.dump_a2[dump_row + j] = (int8_t)x;
-    mx = max(mx, x - (rid[j] != my_rid ? a.mask_int : 0));
+    if (kDump) {
+      a.dump_a1[dump_row + j] = (int8_t)c1;
+      a.dump_a2[dump_row + j] = (int8_t)x;
+    }
+    mx = max(mx, x - (rid[j] != my_rid ? mask_int : 0));
   }
   // ---- row sum of the integer exp; the distances are kept for the last pass ----
   const int dmax = a.lut_n - 1;
   double sum = 0.0;
 #pragma unroll 4
   for (int j = 0; j < n; ++j) {
-    const int xm = (int)xs[j][i] - (rid[j] != my_rid ? a.mask_int : 0);
+    const int xm = (int)xs[j][i] - (rid[j] != my_rid ? mask_int : 0);
     const int d = min(mx - xm, dmax);
     ds[j][i] = (uint16_t)d;
-    sum += (double)__ldg(a.exp_lut + d);
+    sum += __ldg(a.exp_lut64 + d);
   }
+  for (int j = n; j < ((n + 3) & ~3); ++j) ds[j][i] = (uint16_t)dmax;   // padding keys: probability 0 (and V rows of 0)
   const float fsum = __double2float_rn(sum);
   // ---- log2 codes -> probabilities 2^(15-k) as two byte planes, four keys to a word; P V by dp4a against V^T ----
   int oh[kWaHeadDim], ol[kWaHeadDim];
 #pragma unroll
   for (int c = 0; c < kWaHeadDim; ++c) oh[c] = ol[c] = 0;
   const int levels = a.softmax_levels;
+  const float2* r3p = reinterpret_cast<const float2*>(a.r3);
   for (int g = 0; 4 * g < n; ++g) {
     uint32_t ph = 0, pl = 0;
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       const int j = 4 * g + e;
-      if (j < n) {
-        const int d = ds[j][i];
-        const float2 r3 = __ldg(reinterpret_cast<const float2*>(a.r3) + d);
-        const float ulo = ffma(fsum, r3.x, 0.16666667f), uhi = ffma(fsum, r3.y, 0.16666667f);
-        int k = (int)((__float_as_uint(ulo) >> 23) & 0xffu) - 125;
-        const int khi = (int)((__float_as_uint(uhi) >> 23) & 0xffu) - 125;
-        if (k != khi || k <= 1) k = wa_exact_code(fsum, __ldg(a.exp_lut + d), levels);
-        k = min(k, levels);
-        if (a.dump_softmax != nullptr) a.dump_softmax[dump_row + j] = (uint8_t)k;
-        const uint32_t p = k >= levels ? 0u : (0x8000u >> k);
-        ph |= (p >> 8) << (8 * e);
-        pl |= (p & 0xffu) << (8 * e);
-      }
+      const int d = ds[j][i];
+      const float2 r3 = __ldg(r3p + d);
+      const uint32_t ulo = __float_as_uint(ffma(fsum, r3.x, 0.16666667f)), uhi = __float_as_uint(ffma(fsum, r3.y, 0.16666667f));
+      int k = (int)(ulo >> 23) - 125;                      // u > 0: the sign bit is clear
+      if (((ulo ^ uhi) >> 23) != 0u || ulo < 0x3f800000u)  // brackets disagree, or k <= 1
+        k = wa_exact_code(fsum, a.exp_lut[d], levels);
+      if (kDump && j < n) a.dump_softmax[dump_row + j] = (uint8_t)min(k, levels);
+      const uint32_t p = k >= levels ? 0u : (0x8000u >> k);
+      ph = __byte_perm(ph, p, e == 0 ? 0x3215 : (e == 1 ? 0x3250 : (e == 2 ? 0x3510 : 0x5210)));   // byte 1 of p -> byte e
+      pl = __byte_perm(pl, p, e == 0 ? 0x3214 : (e == 1 ? 0x3240 : (e == 2 ? 0x3410 : 0x4210)));   // byte 0 of p -> byte e
     }
 #pragma unroll
     for (int c = 0; c < kWaHeadDim; c += 4) {
@@ -294,8 +304,10 @@ using namespace p2v;
 
 extern "C" int p2v_window_attention_int(const int8_t* qkv, int8_t* out, int images, const p2v_window_attention* p,
                                         void* stream) {
-  P2V_REQUIRE(qkv && out && p && p->perm && p->bias && p->exp_lut && p->r3 && p->qerr,
+  P2V_REQUIRE(qkv && out && p && p->perm && p->bias && p->exp_lut && p->exp_lut64 && p->r3,
               "p2v_window_attention_int: null pointer");
+  const bool dump = p->dump_a1 != nullptr || p->dump_a2 != nullptr || p->dump_softmax != nullptr;
+  P2V_REQUIRE(!dump || (p->dump_a1 && p->dump_a2 && p->dump_softmax), "p2v_window_attention_int: the three dumps go together");
   P2V_REQUIRE(images > 0 && p->n > 0 && p->n <= kWaMaxN && p->heads > 0 && p->windows > 0,
               "p2v_window_attention_int: bad shape images=%d n=%d heads=%d windows=%d", images, p->n, p->heads, p->windows);
   P2V_REQUIRE(p->channels == p->heads * kWaHeadDim, "p2v_window_attention_int: channels=%d is not heads * 32", p->channels);
@@ -307,7 +319,8 @@ extern "C" int p2v_window_attention_int(const int8_t* qkv, int8_t* out, int imag
               "p2v_window_attention_int: qkv and out must be 16-byte aligned");
   const int64_t items = (int64_t)images * p->windows * p->heads;
   P2V_REQUIRE(items < (1ll << 31), "p2v_window_attention_int: too many (window, head) items");
-  window_attention_kernel<<<(unsigned)items, kWaMaxN, 0, (cudaStream_t)stream>>>(qkv, out, *p);
+  if (dump) window_attention_kernel<true><<<(unsigned)items, kWaMaxN, 0, (cudaStream_t)stream>>>(qkv, out, *p);
+  else window_attention_kernel<false><<<(unsigned)items, kWaMaxN, 0, (cudaStream_t)stream>>>(qkv, out, *p);
   P2V_CHECK_CUDA(cudaGetLastError());
   return P2V_OK;
 }

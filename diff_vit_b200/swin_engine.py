@@ -139,13 +139,6 @@ class _SwinBuilder(_Builder):
         m = (codes * np.float32(qscale)).astype(np.float32).astype(np.float64) * 2.0 ** qshift
         if not (np.all(m == np.rint(m)) and np.abs(m).max() < 2.0 ** 31):
             raise NotImplementedError('q scaling %g does not fit the fixed-point product' % qscale)
-        # the fast score path's error table: |fl32(code * qscale) - code * qscale| per code BYTE, rounded up
-        cb = np.arange(256)
-        cv = np.where(cb < 128, cb, cb - 256).astype(np.float64)
-        exact = cv * float(np.float32(qscale))
-        t32 = (cv.astype(np.float32) * np.float32(qscale)).astype(np.float32).astype(np.float64)
-        qerr = torch.from_numpy(np.nextafter(np.abs(t32 - exact).astype(np.float32), np.float32(np.inf)) *
-                                (np.abs(t32 - exact) > 0))
         lut = swin_exp_lut(torch.tensor(s2))
         r = 1.0 / (3.0 * lut.double())
         r3 = torch.stack([(r * (1.0 - 2.0 ** -20)).float(), (r * (1.0 + 2.0 ** -20)).float()], -1).contiguous()
@@ -154,8 +147,8 @@ class _SwinBuilder(_Builder):
             raise NotImplementedError('%s: 100 / qact2 scale is not an integer' % pre)
         return NS(perm=window_permutation(res, ws, shift), region=shift_regions(res, ws, shift),
                   bias=bias.permute(2, 1, 0).contiguous(),               # [head][key][row]
-                  table_codes=tq.to(torch.int32), exp_lut=lut, r3=r3, qerr=qerr.float().contiguous(),
-                  qk_scale=qscale * s1 * s1, err_mul=128.0 * s1 * s1 / sa,
+                  table_codes=tq.to(torch.int32), exp_lut=lut, exp_lut64=lut.double().contiguous(), r3=r3,
+                  qk_scale=qscale * s1 * s1, err_mul=float(np.nextafter(np.float32(2.0 ** -24 * qscale * 128.0 * s1 * s1 / sa), np.float32(np.inf))),
                   n=n, heads=heads, windows=(res[0] // ws) * (res[1] // ws), tokens=res[0] * res[1], channels=dim,
                   qshift=qshift, qscale=qscale, acc_scale=s1 * s1 * 2.0 ** -qshift, a1_scale=sa, a1_rscale=1.0 / sa,
                   a2_rscale=1.0 / s2, mask_int=int(mask), out_unit=2.0 ** -15 * s1, out_rscale=1.0 / s3,
@@ -291,7 +284,7 @@ class _Bound:
     def attn(self, a):
         d = _cabi.WindowAttention()
         d.perm, d.region, d.bias, d.exp_lut = self.p(a.perm), self.p(a.region), self.p(a.bias), self.p(a.exp_lut)
-        d.r3, d.qerr, d.qk_scale, d.err_mul = self.p(a.r3), self.p(a.qerr), a.qk_scale, a.err_mul
+        d.r3, d.exp_lut64, d.qk_scale, d.err_mul = self.p(a.r3), self.p(a.exp_lut64), a.qk_scale, a.err_mul
         d.lut_n = a.exp_lut.numel()
         d.n, d.heads, d.windows, d.tokens, d.channels = a.n, a.heads, a.windows, a.tokens, a.channels
         d.qshift, d.qscale, d.acc_scale = a.qshift, a.qscale, a.acc_scale

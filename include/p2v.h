@@ -183,21 +183,22 @@ typedef struct p2v_window_attention {
   const float* bias;       /* [heads][n (key)][n (row)] dequantized qact_table entry of the pair's relative position    */
   const float* exp_lut;    /* [lut_n] integer exp of d = rowmax - x (layers.py:334-358); d >= lut_n reads the last one  */
   const float* r3;         /* [lut_n][2] fl32((1 -+ 2^-20) / (3 exp_lut[d])): brackets of the fast log2 code            */
-  const float* qerr;       /* [256] |fl32(code * qscale) - code * qscale| rounded up, indexed by the code's BYTE        */
+  const double* exp_lut64; /* [lut_n] the same table as doubles (the exact row sum adds them without a conversion)      */
   int32_t lut_n;
   int32_t n, heads, windows, tokens, channels;   /* tokens = windows * n per image, channels = heads * 32              */
   int32_t qshift;          /* fl32(code * qscale) * 2^qshift is an integer below 2^31 for every int8 code              */
   float qscale;            /* head_dim^-1/2 as fp32 (swin_quant.py:83,190)                                             */
   double acc_scale;        /* s_qkv^2 * 2^-qshift                                                                      */
   float qk_scale;          /* qscale * s_qkv^2 (exact in fp32): the fast score is (sum_c q_c k_c) * qk_scale           */
-  float err_mul;           /* 128 * s_qkv^2 / s_a1: turns a row's summed qerr into a bound in units of the a1 grid     */
+  float err_mul;           /* 2^-24 qscale * 128 s_qkv^2 / s_a1 (rounded up): times sum_c |q_c| it bounds the fast
+                              score's distance from the exact one in units of the a1 grid                              */
   float a1_scale, a1_rscale;   /* qact_attn1 grid and its exact reciprocal                                             */
   float a2_rscale;         /* 1 / s of qact2                                                                           */
   int32_t mask_int;        /* 100 / s of qact2 (an integer)                                                            */
   float out_unit;          /* 2^-15 * s_qkv: the value of one unit of sum_j 2^(15 - k_j) v_j                           */
   float out_rscale;        /* 1 / s of qact3                                                                           */
   int32_t softmax_levels;  /* 2^bits = 16                                                                              */
-  int8_t* dump_a1;         /* optional [images * windows][heads][n][n]: qact_attn1 codes                               */
+  int8_t* dump_a1;         /* optional (all three or none) [images * windows][heads][n][n]: qact_attn1 codes           */
   int8_t* dump_a2;         /* optional, same shape: qact2 codes (before the mask)                                      */
   uint8_t* dump_softmax;   /* optional, same shape: log2 codes (softmax_levels = probability 0)                        */
 } p2v_window_attention;

@@ -170,12 +170,19 @@ def _ln_plan(rng, d, pot):
 
 
 @pytest.mark.parametrize('rows,d,stride_rows', [(197 * 3, 384, 1), (64, 192, 1), (33, 128, 1), (5, 768, 1), (4, 384, 197),
-                                                (700, 768, 1), (300, 1024, 1), (90, 512, 1), (75, 640, 1), (3, 768, 197)])
+                                                (700, 768, 1), (300, 1024, 1), (90, 512, 1), (75, 640, 1), (3, 768, 197),
+                                                # Swin: four / two rows per warp (d = 96 / 192) with ragged row counts, the
+                                                # 4C LayerNorm of the last PatchMerging (d = 1536, general kernel)
+                                                (1001, 96, 1), (3, 96, 1), (4099, 96, 1), (333, 192, 1), (1, 192, 1),
+                                                (50, 1536, 1)])
 @pytest.mark.parametrize('pot', [True, False])
-@pytest.mark.parametrize('big_masks', [False, True], ids=['masks_le_8', 'masks_to_64'])
+@pytest.mark.parametrize('big_masks', [False, True, 'pre_clamp'], ids=['masks_le_8', 'masks_to_64', 'pre_clamp'])
 def test_layernorm_int_matches_host_arithmetic(cabi, rows, d, stride_rows, pot, big_masks):
     rng = np.random.default_rng(rows + d + pot)
     p = _ln_plan(rng, d, pot)
+    if big_masks == 'pre_clamp':   # an int8 QAct on the LayerNorm's own grid before the re-gridding (Swin's qact3)
+        p.pre_clamp, big_masks = 1, False
+        p.gamma = p.gamma * 3.0    # enough codes beyond +-127 for the clamp to matter
     if big_masks:   # beyond the PTF range {1, 2, 4, 8}: the kernel must fall back from fp32 to integer row statistics
         p.in_mask = p.in_mask * torch.from_numpy((2.0 ** rng.integers(0, 4, size=d)).astype(np.float32))
     x = _rand_i8(rng, rows * stride_rows, d)
@@ -187,6 +194,9 @@ def test_layernorm_int_matches_host_arithmetic(cabi, rows, d, stride_rows, pot, 
     for k, v in keep.items():
         setattr(c, k, v.data_ptr())
     c.post_div2, c.post_zp, c.in_scale1, c.pot = p.post_div2, p.post_zp, p.in_scale1, p.pot
+    c.pre_clamp = int(getattr(p, 'pre_clamp', 0))
+    if c.pre_clamp:
+        assert (np.abs(want_codes) > 127).mean() > 1e-3
     xd = torch.from_numpy(x).cuda()
     out = torch.zeros(rows, d, dtype=torch.int8, device='cuda')
     codes = torch.zeros(rows, d, dtype=torch.int32, device='cuda')
