@@ -39,6 +39,7 @@ def parse():
     ap.add_argument('--e2e-steps', type=int, default=40, help='batches of the host-buffer serving loop (its un-overlapped first upload is inside the timed region)')
     ap.add_argument('--cpu-sample', type=int, default=32, help='images in the CPU-baseline sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-swin', action='store_true', help='skip the config-5 (swin_tiny b128) side measurement at N = 1')
     return ap.parse_args()
 
 
@@ -238,6 +239,37 @@ def time_layernorm(lib_mod, bound, rows, d, iters, stream_obj):
         t1.record(stream_obj)
     stream_obj.synchronize()
     return t0.elapsed_time(t1) / iters
+
+
+def swin_side_measurement(device, iters=20):
+    """BASELINE config 5 beside the headline (N = 1 only; not part of the timed region above): swin_tiny, W8A8 PoT,
+    batch 128 synthetic images, random-init weights, on the Swin integer engine (diff_vit_b200/swin_engine.py) -
+    CUDA-graph replay of its launch sequence, device-resident fp32 input, CUDA events."""
+    import diff_vit_b200 as dv
+    torch.manual_seed(0)
+    m = dv.swin_tiny_patch4_window7_224(cfg=dv.Config(True, True, 'minmax')).eval().to(device)
+    g = torch.Generator(device=device).manual_seed(1)
+    dv.calibrate_model(m, [torch.randn(8, 3, 224, 224, device=device, generator=g)])
+    x = torch.randn(128, 3, 224, 224, device=device, generator=g)
+    with torch.no_grad():
+        for _ in range(3):
+            m(x)
+        if m._engine_off is not None:
+            return {'unavailable': m._engine_off}
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(device)
+        e0.record()
+        for _ in range(iters):
+            m(x)
+        e1.record()
+        torch.cuda.synchronize(device)
+    ms = e0.elapsed_time(e1) / iters
+    gop = 2.0 * sum(m.flops()) / 1e9
+    return {'metric': 'images/sec W8A8 PoT swin_tiny b128 (BASELINE config 5)', 'value': round(128 / ms * 1e3, 1),
+            'unit': 'images/s', 'ms_per_step': round(ms, 4), 'steps': iters, 'launches_per_step': m.integer_engine().launches,
+            'gop_per_image_linears': round(gop, 3), 'achieved_tops': round(128 / ms * gop, 1),
+            'note': 'SwinTransformer.forward on the integer engine: graph replay incl. the device-side copy of the input '
+                    'into the graph buffer and of the logits out of it; calibration (8 images) excluded'}
 
 
 def bind_to_gpu_numa_node(local):
@@ -480,6 +512,13 @@ def run_ours(args):
              'frac_of_nominal_int8': round(model_tops / INT8_NOMINAL_TOPS, 4), 'gop_per_image': GOP_PER_IMAGE,
              'note': 'per GPU'}
 
+    swin = None
+    if world == 1 and not args.no_swin:
+        try:
+            swin = swin_side_measurement(device)
+        except Exception as e:      # the headline line must not depend on the side measurement
+            swin = {'unavailable': '%s: %s' % (type(e).__name__, e)}
+
     cpu = None
     if not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
@@ -512,7 +551,7 @@ def run_ours(args):
         'launches_per_step': launches,
         'roofline': roofline, 'roofline_fc1_gemm': roofline_gemm, 'roofline_layernorm': roofline_ln,
         'tensor_pipe_util_pct': tensor_pipe, 'whole_model': whole, 'weak': weak, 'cpu_baseline': cpu,
-        'clocks': clocks,
+        'clocks': clocks, 'config5_swin_tiny': swin,
     }
     print(json.dumps(line))
     if world > 1:

@@ -66,3 +66,27 @@ def test_swin_micro_plan_on_the_host_vs_reference_golden_and_oracle(swin_model, 
             assert d.max() <= 1 and (d != 0).mean() <= 1e-3, k
         lsb = float(state['act']['act_out'][0])
         assert np.abs(logits - z['w8/logits']).max() <= 2 * lsb
+
+
+def test_swin_flops_list_and_engine_dispatch_rules(swin_golden):
+    """`flops()` (what the engine path returns) equals the list a per-module forward accumulates; the engine is only
+    considered for CUDA tensors of a quantized model, and is dropped by everything that can change its plan."""
+    import diff_vit_b200 as dv
+    from test_swin_golden import build_swin_micro
+    model = build_swin_micro(swin_golden)
+    x = torch.from_numpy(swin_golden['x_eval'])
+    n = model.num_linear_layers()
+    with torch.no_grad():
+        _, flops, _ = model(x, [8] * n, False)                 # float graph
+    assert flops == model.flops() and len(flops) == n
+    assert model._integer_forward(x, [8] * n) is None          # not quantized, CPU tensor
+    model._engine = object()
+    model.model_quant()
+    assert model._engine is None and model._int_active
+    assert model._integer_forward(x, [8] * n) is None          # CPU tensor: never the engine
+    model._engine = object()
+    model.model_dequant()
+    assert model._engine is None and not model._int_active
+    model._engine = object()
+    model.load_state_dict(model.state_dict())
+    assert model._engine is None
