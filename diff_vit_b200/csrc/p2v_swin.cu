@@ -5,7 +5,7 @@
 //   p2v_gather_row_segments    the 2 x 2 neighbourhood concat of PatchMerging   (models/swin_quant.py:445-457)
 //   p2v_avgpool_requant        token average + qact3                            (models/swin_quant.py:810-813)
 //
-// Window attention, per (window, head): one thread owns one of the n = ws^2 <= 64 query rows.
+// Window attention, per (window, head): one thread owns one of the n = ws^2 <= 64 query rows (five items per CTA).
 //   q' = fl32(q * head_dim^-1/2)   - the reference scales the DEQUANTIZED q in fp32 before the product, so q' is not on
 //                                    an integer grid.  fl32(code * s * c) = s * fl32(code * c) for a power-of-two s, and
 //                                    every fl32(code * c), |code| <= 128, is a multiple of 2^-qshift below 2^31 in that
@@ -78,21 +78,44 @@ __device__ __noinline__ int wa_exact_code(float fsum, float e, int levels) { ret
 //   * log2 code: k = exponent(fma(sum, 1 / (3e), 1/6)) + 2 evaluated for a low and a high bracket of 1 / (3e)
 //     (+-2^-20, table `r3`); where the two exponents differ, or k <= 1 (the irregular first step of the code
 //     function), the pair takes softmax_log_code's IEEE division (see p2v_attention_tc.cu for the argument).
+// Several (window, head) items share a CTA of 256 threads: thread tid holds row tid % n of the CTA's item tid / n, so 5 items
+// of 49 rows fill 245 of the 256 lanes (one item per 64-thread CTA left 15 of 64 idle).  Each item has its own K / V^T
+// tiles; the score / distance columns are per thread.
+constexpr int kWaThreads = 256;
+constexpr int kWaMaxItems = 5;
+struct WaSmem {
+  alignas(16) uint32_t kp[kWaMaxItems][kWaMaxN][8];                 // K rows, packed int8
+  alignas(16) uint32_t vt[kWaMaxItems][kWaMaxN / 4][kWaVtStride];   // V^T: word [g][c] = v[4g .. 4g + 3][c]
+  int8_t xs[kWaMaxN][kWaThreads];                                   // [key][thread] qact2 codes
+  uint16_t ds[kWaMaxN][kWaThreads];                                 // [key][thread] distance to the row maximum (clamped)
+  uint8_t rid[kWaMaxItems][kWaMaxN];
+};
+
 template <bool kDump>
-__global__ void __launch_bounds__(kWaMaxN)
-window_attention_kernel(const int8_t* __restrict__ qkv, int8_t* __restrict__ out, const p2v_window_attention a) {
-  __shared__ __align__(16) uint32_t kp[kWaMaxN][8];             // K rows, packed int8
-  __shared__ __align__(16) uint32_t vt[kWaMaxN / 4][kWaVtStride];   // V^T: word [g][c] = v[4g .. 4g + 3][c]
-  __shared__ int8_t xs[kWaMaxN][kWaMaxN];                        // [key][row] qact2 codes: thread `row` owns its column
-  __shared__ uint16_t ds[kWaMaxN][kWaMaxN];                      // [key][row] distance to the row maximum (clamped)
-  __shared__ uint8_t rid[kWaMaxN];
+__global__ void __launch_bounds__(kWaThreads, 3)
+window_attention_kernel(const int8_t* __restrict__ qkv, int8_t* __restrict__ out, const p2v_window_attention a,
+                        int items_total, int items_per_cta) {
+  extern __shared__ __align__(16) uint8_t wa_smem_raw[];
+  WaSmem& sm = *reinterpret_cast<WaSmem*>(wa_smem_raw);
   constexpr float kMagic = 12582912.0f;   // 1.5 * 2^23
   const int n = a.n, C = a.channels;
-  const int head = blockIdx.x % a.heads;
-  const int wg = blockIdx.x / a.heads;            // window over the whole batch
+  const int tid = threadIdx.x;
+  const int it = tid / n, i = tid - it * n;           // item within the CTA, row within the item
+  const int item = blockIdx.x * items_per_cta + it;
+  const bool valid = it < items_per_cta && item < items_total;
+  const int head = valid ? item % a.heads : 0;
+  const int wg = valid ? item / a.heads : 0;      // window over the whole batch
   const int img = wg / a.windows, w = wg % a.windows;
-  const int i = threadIdx.x;
-  const bool valid = i < n;
+  uint32_t (*kp)[8] = sm.kp[valid ? it : 0];
+  uint32_t (*vt)[kWaVtStride] = sm.vt[valid ? it : 0];
+  const uint8_t* rid = sm.rid[valid ? it : 0];
+  // keys n .. 63 of every item: zero K rows and V columns, so the loops below can run over whole groups of four keys
+  for (int z = tid; z < kWaMaxItems * (kWaMaxN - n); z += kWaThreads) {
+    const int zi = z / (kWaMaxN - n), zr = n + z % (kWaMaxN - n);
+    *reinterpret_cast<uint4*>(&sm.kp[zi][zr][0]) = make_uint4(0, 0, 0, 0);
+    *reinterpret_cast<uint4*>(&sm.kp[zi][zr][4]) = make_uint4(0, 0, 0, 0);
+    for (int c = 0; c < kWaHeadDim; ++c) reinterpret_cast<uint8_t*>(&sm.vt[zi][zr >> 2][c])[zr & 3] = 0;
+  }
   int64_t src_row = 0;
   uint32_t qw[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   float guard = 0.f;
@@ -119,19 +142,12 @@ window_attention_kernel(const int8_t* __restrict__ qkv, int8_t* __restrict__ out
     // |S' - S| / s_a1 <= 2^-24 qscale sum|q_c| * 128 s^2 / s_a1 = sum|q_c| * err_mul; + 2^-14 for the roundings of S'
     // itself (|t| < 2^9 wherever the code is not saturated)
     guard = fadd(fmul((float)(qabs + 32u), a.err_mul), 6.103515625e-05f);
-    rid[i] = a.region != nullptr ? a.region[w * n + i] : (uint8_t)0;
-  } else {
-    // keys beyond n: zero rows, so the dp4a groups of the P V loop can run over whole groups of four
-    *reinterpret_cast<uint4*>(&kp[i][0]) = make_uint4(0, 0, 0, 0);
-    *reinterpret_cast<uint4*>(&kp[i][4]) = make_uint4(0, 0, 0, 0);
-#pragma unroll
-    for (int c = 0; c < kWaHeadDim; ++c) reinterpret_cast<uint8_t*>(&vt[i >> 2][c])[i & 3] = 0;
-    rid[i] = 0;
+    sm.rid[it][i] = a.region != nullptr ? a.region[w * n + i] : (uint8_t)0;
   }
   __syncthreads();
   if (!valid) return;
 
-  const int64_t dump_row = ((int64_t)(wg * a.heads + head) * n + i) * n;
+  const int64_t dump_row = ((int64_t)item * n + i) * n;
   const float* bias_p = a.bias + (int64_t)head * n * n + i;
   const int my_rid = rid[i];
   const int mask_int = a.mask_int;
@@ -160,7 +176,7 @@ window_attention_kernel(const int8_t* __restrict__ qkv, int8_t* __restrict__ out
     }
     const float tb = fminf(fmaxf(fmul(fadd(fmul(c1, a1_scale), bias), a2_rscale), -128.f), 127.f);   // + bias, qact2
     const int x = (int)(int8_t)(__float_as_uint(fadd(tb, kMagic)) & 0xffu);   // low byte of 1.5 * 2^23 + RNE(tb)
-    xs[j][i] = (int8_t)x;
+    sm.xs[j][tid] = (int8_t)x;
     if (kDump) {
       a.dump_a1[dump_row + j] = (int8_t)c1;
       a.dump_a2[dump_row + j] = (int8_t)x;
@@ -172,12 +188,12 @@ window_attention_kernel(const int8_t* __restrict__ qkv, int8_t* __restrict__ out
   double sum = 0.0;
 #pragma unroll 4
   for (int j = 0; j < n; ++j) {
-    const int xm = (int)xs[j][i] - (rid[j] != my_rid ? mask_int : 0);
+    const int xm = (int)sm.xs[j][tid] - (rid[j] != my_rid ? mask_int : 0);
     const int d = min(mx - xm, dmax);
-    ds[j][i] = (uint16_t)d;
+    sm.ds[j][tid] = (uint16_t)d;
     sum += __ldg(a.exp_lut64 + d);
   }
-  for (int j = n; j < ((n + 3) & ~3); ++j) ds[j][i] = (uint16_t)dmax;   // padding keys: probability 0 (and V rows of 0)
+  for (int j = n; j < ((n + 3) & ~3); ++j) sm.ds[j][tid] = (uint16_t)dmax;   // padding keys: probability 0 (and V rows of 0)
   const float fsum = __double2float_rn(sum);
   // ---- log2 codes -> probabilities 2^(15-k) as two byte planes, four keys to a word; P V by dp4a against V^T ----
   int oh[kWaHeadDim], ol[kWaHeadDim];
@@ -190,7 +206,7 @@ window_attention_kernel(const int8_t* __restrict__ qkv, int8_t* __restrict__ out
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       const int j = 4 * g + e;
-      const int d = ds[j][i];
+      const int d = sm.ds[j][tid];
       const float2 r3 = __ldg(r3p + d);
       const uint32_t ulo = __float_as_uint(ffma(fsum, r3.x, 0.16666667f)), uhi = __float_as_uint(ffma(fsum, r3.y, 0.16666667f));
       int k = (int)(ulo >> 23) - 125;                      // u > 0: the sign bit is clear
@@ -319,8 +335,17 @@ extern "C" int p2v_window_attention_int(const int8_t* qkv, int8_t* out, int imag
               "p2v_window_attention_int: qkv and out must be 16-byte aligned");
   const int64_t items = (int64_t)images * p->windows * p->heads;
   P2V_REQUIRE(items < (1ll << 31), "p2v_window_attention_int: too many (window, head) items");
-  if (dump) window_attention_kernel<true><<<(unsigned)items, kWaMaxN, 0, (cudaStream_t)stream>>>(qkv, out, *p);
-  else window_attention_kernel<false><<<(unsigned)items, kWaMaxN, 0, (cudaStream_t)stream>>>(qkv, out, *p);
+  static unsigned long long configured = 0;
+  int dev = 0;
+  if (needs_configure(configured, &dev)) {
+    P2V_CHECK_CUDA(cudaFuncSetAttribute(window_attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WaSmem)));
+    P2V_CHECK_CUDA(cudaFuncSetAttribute(window_attention_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WaSmem)));
+    mark_configured(configured, dev);
+  }
+  const int per_cta = kWaThreads / p->n < kWaMaxItems ? kWaThreads / p->n : kWaMaxItems;
+  const unsigned grid = (unsigned)((items + per_cta - 1) / per_cta);
+  if (dump) window_attention_kernel<true><<<grid, kWaThreads, sizeof(WaSmem), (cudaStream_t)stream>>>(qkv, out, *p, (int)items, per_cta);
+  else window_attention_kernel<false><<<grid, kWaThreads, sizeof(WaSmem), (cudaStream_t)stream>>>(qkv, out, *p, (int)items, per_cta);
   P2V_CHECK_CUDA(cudaGetLastError());
   return P2V_OK;
 }
