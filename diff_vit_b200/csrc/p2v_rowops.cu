@@ -160,7 +160,8 @@ embed_assemble_kernel(const int8_t* __restrict__ pe, int8_t* __restrict__ out, i
 // of the warp.  Power-of-two output grids (every minmax-calibrated model) fold 1/s_out into gamma and
 // beta: fl(t*gamma) * 2^-e == fl(t * (gamma * 2^-e)), so the folded form rounds exactly like the
 // reference's (t * gamma) / s_out and (beta - u * gamma) / s_out.
-constexpr int kLnMaxGroups = 12;  // d <= 1536 (general kernel; the register-resident power-of-two kernel serves d <= 1024)
+constexpr int kLnMaxGroups = 16;  // d <= 2048 (general kernel: the 4C LayerNorm of the last PatchMerging is 1536 wide in
+                                  // swin_tiny / small, 2048 in swin_base); the register-resident power-of-two kernel serves d <= 1024
 
 __device__ __forceinline__ uint32_t pack_sat4f(float v0, float v1, float v2, float v3) {
   uint32_t hi, r;

@@ -109,6 +109,8 @@ class _SwinBuilder(_Builder):
 
     def ln_plan(self, in_scale, gamma, beta, out_act):
         d = gamma.numel()
+        if d % 4 or d > 2048:
+            raise NotImplementedError('LayerNorm over %d channels (p2v_layernorm_int: multiples of 4 up to 2048)' % d)
         in_scale = _expand(in_scale, d)
         in_scale1 = in_scale.min()
         out_s = _expand(self.act(out_act)[0], d)

@@ -174,7 +174,7 @@ def _ln_plan(rng, d, pot):
                                                 # Swin: four / two rows per warp (d = 96 / 192) with ragged row counts, the
                                                 # 4C LayerNorm of the last PatchMerging (d = 1536, general kernel)
                                                 (1001, 96, 1), (3, 96, 1), (4099, 96, 1), (333, 192, 1), (1, 192, 1),
-                                                (50, 1536, 1)])
+                                                (50, 1536, 1), (9, 2048, 1)])
 @pytest.mark.parametrize('pot', [True, False])
 @pytest.mark.parametrize('big_masks', [False, True, 'pre_clamp'], ids=['masks_le_8', 'masks_to_64', 'pre_clamp'])
 def test_layernorm_int_matches_host_arithmetic(cabi, rows, d, stride_rows, pot, big_masks):

@@ -200,3 +200,21 @@ def test_swin_tiny_engine_batch128_config5_vs_oracle():
     assert torch.equal(logits, full[:2])
     assert total > 3e7
     print('swin_tiny config 5 on the integer engine: %d codes compared on identical inputs, %d differ' % (total, bad))
+
+
+def test_swin_base_engine_vs_oracle():
+    """swin_base (C = 128, heads 4 / 8 / 16 / 32, 24 blocks, the 2048-wide LayerNorm of the last PatchMerging) through
+    the same engine: 2 images, every quantizer's codes against the oracle on identical inputs."""
+    import diff_vit_b200 as dv
+    torch.manual_seed(0)
+    model = dv.swin_base_patch4_window7_224(cfg=dv.Config(True, True, 'minmax')).eval().cuda()
+    g = torch.Generator(device='cuda').manual_seed(0)
+    dv.calibrate_model(model, [torch.randn(4, 3, 224, 224, device='cuda', generator=g)])
+    x = torch.randn(2, 3, 224, 224, device='cuda', generator=g)
+    with torch.no_grad():
+        full = model(x)
+    assert model._engine_off is None, model._engine_off
+    logits, codes, total, bad = _engine_vs_oracle(model, x)
+    assert torch.equal(logits, full)
+    assert total > 5e7
+    print('swin_base on the integer engine: %d codes compared on identical inputs, %d differ' % (total, bad))
