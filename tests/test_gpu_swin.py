@@ -218,3 +218,71 @@ def test_swin_base_engine_vs_oracle():
     assert torch.equal(logits, full)
     assert total > 5e7
     print('swin_base on the integer engine: %d codes compared on identical inputs, %d differ' % (total, bad))
+
+
+# ---- the window attention kernel on its own -----------------------------------------------------------------------------
+@pytest.fixture(scope='module')
+def cabi():
+    from diff_vit_b200 import _cabi
+    _cabi.lib()
+    return _cabi
+
+
+def _wa_plan(rng, heads, res, ws, shift, s1, sa, s2, s3, st):
+    from diff_vit_b200.swin_engine import _SwinBuilder
+    from diff_vit_b200.swin_quant import relative_position_index
+    C_ = heads * 32
+    b = _SwinBuilder.__new__(_SwinBuilder)
+    t = lambda v: torch.tensor([v], dtype=torch.float32)
+    z = torch.zeros(1)
+    b.arch = {'softmax_bits': 4}
+    b.P = {'a.qkv.weight': torch.zeros(3 * C_, C_),
+           'a.relative_position_bias_table': torch.from_numpy(rng.standard_normal(((2 * ws - 1) ** 2, heads)).astype(np.float32)) * 4 * st,
+           'a.relative_position_index': relative_position_index((ws, ws))}
+    b.s = {'act': {'a.qact1': (t(s1), z, -128, 127), 'a.qact_attn1': (t(sa), z, -128, 127), 'a.qact2': (t(s2), z, -128, 127),
+                   'a.qact3': (t(s3), z, -128, 127), 'a.qact_table': (t(st), z, -128, 127)}}
+    return b.window_attention('a', heads, res, ws, shift)
+
+
+@pytest.mark.parametrize('heads,res,ws,shift,images', [(3, (14, 14), 7, 0, 3), (3, (14, 14), 7, 3, 3), (1, (7, 7), 7, 0, 5),
+                                                       (2, (8, 8), 4, 2, 2), (4, (16, 16), 8, 4, 1), (6, (28, 28), 7, 3, 2)])
+@pytest.mark.parametrize('spread,scales', [(12, (2.0 ** -3, 2.0 ** -2, 2.0 ** -2, 2.0 ** -4)),      # flat rows
+                                            (127, (2.0 ** -3, 2.0 ** 0, 2.0 ** -1, 2.0 ** -3)),      # peaked rows, saturating scores
+                                            (40, (2.0 ** -2, 2.0 ** -4, 2.0 ** -5, 2.0 ** -5)),      # fine score grid: long exp table
+                                            (60, (2.0 ** -4, 2.0 ** -3, 2.0 ** -3, 2.0 ** -6))])
+def test_window_attention_kernel_matches_its_integer_formulation(cabi, heads, res, ws, shift, images, spread, scales):
+    """`p2v_window_attention_int` (dp4a fast paths with tie guards, five items per CTA, ragged last CTA) against the
+    exact integer formulation in numpy (tests/hostmath.window_attention, itself pinned to the reference golden by
+    tests/test_swin_plan.py): scores after both re-quantisations, log2 codes and the output, bit for bit - flat and
+    peaked rows, saturating scores, shifted windows, window sizes 4 / 7 / 8."""
+    import ctypes as C
+    import hostmath
+    from diff_vit_b200.swin_engine import _Bound
+    rng = np.random.default_rng(heads * 1000 + res[0] * 10 + shift + spread)
+    s1, sa, s2, s3 = scales
+    p = _wa_plan(rng, heads, res, ws, shift, s1, sa, s2, s3, st=2.0 ** -3)
+    L, C_ = res[0] * res[1], heads * 32
+    qkv = rng.integers(-spread, spread + 1, size=(images * L, 3 * C_)).astype(np.int8)
+    qkv[0, :C_] = -128                                       # a row of the most negative code (|q| bound, saturation)
+    want, w1, w2, wsm = hostmath.window_attention(qkv, images, p)
+    holder = _Bound.__new__(_Bound)
+    holder.device, holder.keep = torch.device('cuda'), []
+    d = holder.attn(p)
+    nw = images * p.windows
+    d1 = torch.zeros(nw, heads, p.n, p.n, dtype=torch.int8, device='cuda')
+    d2 = torch.zeros_like(d1)
+    d3 = torch.zeros(nw, heads, p.n, p.n, dtype=torch.uint8, device='cuda')
+    xq = torch.from_numpy(qkv).cuda()
+    out = torch.zeros(images * L, C_, dtype=torch.int8, device='cuda')
+    out2 = torch.zeros_like(out)
+    st = cabi.current_stream()
+    cabi.check(cabi.lib().p2v_window_attention_int(xq.data_ptr(), out2.data_ptr(), images, C.byref(d), st))   # plain kernel
+    d.dump_a1, d.dump_a2, d.dump_softmax = d1.data_ptr(), d2.data_ptr(), d3.data_ptr()
+    cabi.check(cabi.lib().p2v_window_attention_int(xq.data_ptr(), out.data_ptr(), images, C.byref(d), st))    # dump kernel
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(d1.cpu().numpy(), w1)
+    np.testing.assert_array_equal(d2.cpu().numpy(), w2)
+    np.testing.assert_array_equal(d3.cpu().numpy(), wsm)
+    np.testing.assert_array_equal(out.cpu().numpy(), want)
+    np.testing.assert_array_equal(out2.cpu().numpy(), want)
+    assert (wsm < 16).mean() > 0.02 and len(np.unique(want)) > 8
