@@ -245,6 +245,7 @@ def swin_side_measurement(device, iters=20):
     """BASELINE config 5 beside the headline (N = 1 only; not part of the timed region above): swin_tiny, W8A8 PoT,
     batch 128 synthetic images, random-init weights, on the Swin integer engine (diff_vit_b200/swin_engine.py) -
     CUDA-graph replay of its launch sequence, device-resident fp32 input, CUDA events."""
+    import torch
     import diff_vit_b200 as dv
     torch.manual_seed(0)
     m = dv.swin_tiny_patch4_window7_224(cfg=dv.Config(True, True, 'minmax')).eval().to(device)
