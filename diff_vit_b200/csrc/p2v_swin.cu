@@ -23,6 +23,7 @@
 
 #include "p2v_common.cuh"
 #include "p2v_math.cuh"
+#include "p2v_requant.cuh"
 
 namespace p2v {
 
@@ -72,9 +73,9 @@ __device__ __noinline__ int wa_exact_code(float fsum, float e, int levels) { ret
 //     2^-24 relative, so S' differs from the exact S by at most 2^-24 qscale sum_c |q_c| * 128 * s^2 - a per-row bound
 //     from the prologue -, and RNE(S' / s_a1) is the exact code unless S' / s_a1 lies within that bound (plus the fp32
 //     rounding of S' itself) of a half-integer; those pairs (~1e-4) are redone by wa_exact_score.
-//   * both re-quantisations round with the 1.5 * 2^23 constant on the FMA pipe after the clamp (clamp and RNE commute
-//     for integer bounds); the int8 code is the low byte of the biased sum: no FRND / F2I (conversion unit, quarter
-//     rate) in the loop.
+//   * both re-quantisations round with the 1.5 * 2^23 constant on the FMA pipe (clamp and RNE commute for integer
+//     bounds); the int8 code is the low byte of the biased sum: no FRND / F2I (conversion unit, quarter rate) in the
+//     loop.
 //   * log2 code: k = exponent(fma(sum, 1 / (3e), 1/6)) + 2 evaluated for a low and a high bracket of 1 / (3e)
 //     (+-2^-20, table `r3`); where the two exponents differ, or k <= 1 (the irregular first step of the code
 //     function), the pair takes softmax_log_code's IEEE division (see p2v_attention_tc.cu for the argument).
@@ -151,7 +152,8 @@ window_attention_kernel(const int8_t* __restrict__ qkv, int8_t* __restrict__ out
   const float* bias_p = a.bias + (int64_t)head * n * n + i;
   const int my_rid = rid[i];
   const int mask_int = a.mask_int;
-  const float qk_scale = a.qk_scale, a1_rscale = a.a1_rscale, a1_scale = a.a1_scale, a2_rscale = a.a2_rscale;
+  const float a1_rscale = a.a1_rscale, a1_scale = a.a1_scale, a2_rscale = a.a2_rscale;
+  const float qkrs = fmul(a.qk_scale, a1_rscale);   // exact: a1_rscale is a power of two
   // ---- scores: integer product, the two re-quantisations, row maximum of the masked codes ----
   int mx = INT_MIN;
 #pragma unroll 2
@@ -167,14 +169,18 @@ window_attention_kernel(const int8_t* __restrict__ qkv, int8_t* __restrict__ out
     acc = __dp4a((int)qw[6], (int)k1.z, acc);
     acc = __dp4a((int)qw[7], (int)k1.w, acc);
     const float bias = __ldg(bias_p + j * n);
-    const float t = fminf(fmaxf(fmul(fmul((float)acc, qk_scale), a1_rscale), -128.f), 127.f);
-    float c1 = fsub(fadd(t, kMagic), kMagic);                  // qact_attn1: RNE of the clamped value
-    if (fabsf(fsub(fabsf(fsub(t, c1)), 0.5f)) < guard) {       // next to a rounding tie: the exact product decides
+    // qact_attn1: 1.5 * 2^23 + RNE(acc * qkrs) from ONE fused multiply-add (|acc * qkrs| < 2^22, checked by the host),
+    // the distance to the rounded value from a second one; the clamp to int8 follows the rounding (they commute)
+    const float accf = (float)acc;
+    float c1 = fsub(ffma(accf, qkrs, kMagic), kMagic);
+    if (fabsf(fsub(fabsf(ffma(accf, qkrs, -c1)), 0.5f)) < guard) {   // next to a rounding tie: the exact product decides
       const float te = fmul(wa_exact_score(make_uint4(qw[0], qw[1], qw[2], qw[3]), make_uint4(qw[4], qw[5], qw[6], qw[7]),
                                            &kp[j][0], a.qscale, a.qshift, a.acc_scale), a1_rscale);
-      c1 = fsub(fadd(fminf(fmaxf(te, -128.f), 127.f), kMagic), kMagic);
+      c1 = fsub(fadd(fminf(fmaxf(te, -256.f), 256.f), kMagic), kMagic);
     }
-    const float tb = fminf(fmaxf(fmul(fadd(fmul(c1, a1_scale), bias), a2_rscale), -128.f), 127.f);   // + bias, qact2
+    c1 = fminf(fmaxf(c1, -128.f), 127.f);
+    // + bias (c1 * s_a1 is exact, so the fused form rounds like the reference's add), qact2
+    const float tb = fminf(fmaxf(fmul(ffma(c1, a1_scale, bias), a2_rscale), -128.f), 127.f);
     const int x = (int)(int8_t)(__float_as_uint(fadd(tb, kMagic)) & 0xffu);   // low byte of 1.5 * 2^23 + RNE(tb)
     sm.xs[j][tid] = (int8_t)x;
     if (kDump) {
@@ -250,6 +256,8 @@ __global__ void __launch_bounds__(256)
 quant_patchify_small_kernel(const float* __restrict__ x, int8_t* __restrict__ codes, int c, int h, int w, int p,
                             float scale, float zp, int64_t total_words) {
   const int wp = p / 4, gw = w / p, gh = h / p;
+  const float rs = __frcp_rn(scale);
+  const float s4[4] = {scale, scale, scale, scale}, rs4[4] = {rs, rs, rs, rs};
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total_words; i += (int64_t)gridDim.x * blockDim.x) {
     int64_t t = i;
     const int kw4 = (int)(t % wp); t /= wp;
@@ -259,9 +267,11 @@ quant_patchify_small_kernel(const float* __restrict__ x, int8_t* __restrict__ co
     const int py = (int)(t % gh);
     const int64_t img = t / gh;
     const float4 v = __ldg(reinterpret_cast<const float4*>(x + ((img * c + ch) * h + (py * p + kh)) * (int64_t)w + px * p + kw4 * 4));
-    reinterpret_cast<uint32_t*>(codes)[i] =
-        pack4_sat_s8(quant_div(v.x, scale, zp, -128, 127), quant_div(v.y, scale, zp, -128, 127),
-                     quant_div(v.z, scale, zp, -128, 127), quant_div(v.w, scale, zp, -128, 127));
+    // four pixels per guarded rounding (multiply by fl(1 / s), exact IEEE division only next to a rounding tie)
+    const float y4[4] = {v.x, v.y, v.z, v.w};
+    float r4[4];
+    div_round4(y4, s4, rs4, zp, r4);
+    reinterpret_cast<uint32_t*>(codes)[i] = pack_sat4(r4[0], r4[1], r4[2], r4[3]);
   }
 }
 
@@ -328,6 +338,8 @@ extern "C" int p2v_window_attention_int(const int8_t* qkv, int8_t* out, int imag
               "p2v_window_attention_int: bad shape images=%d n=%d heads=%d windows=%d", images, p->n, p->heads, p->windows);
   P2V_REQUIRE(p->channels == p->heads * kWaHeadDim, "p2v_window_attention_int: channels=%d is not heads * 32", p->channels);
   P2V_REQUIRE(p->tokens == p->windows * p->n, "p2v_window_attention_int: tokens=%d is not windows * n", p->tokens);
+  P2V_REQUIRE(p->qk_scale > 0.f && p->a1_rscale > 0.f && (double)p->qk_scale * p->a1_rscale <= 4.0,
+              "p2v_window_attention_int: qk_scale / s_a1 = %g: scores beyond 2^21 grid steps", (double)p->qk_scale * p->a1_rscale);
   P2V_REQUIRE(p->lut_n <= 65536, "p2v_window_attention_int: table of %d entries (at most 65536)", p->lut_n);
   P2V_REQUIRE(p->lut_n >= 1 && p->qshift >= 0 && p->qshift <= 60 && p->softmax_levels >= 1 && p->softmax_levels <= 16,
               "p2v_window_attention_int: bad table / shift / levels");

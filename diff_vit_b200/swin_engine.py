@@ -144,6 +144,8 @@ class _SwinBuilder(_Builder):
         lut = swin_exp_lut(torch.tensor(s2))
         r = 1.0 / (3.0 * lut.double())
         r3 = torch.stack([(r * (1.0 - 2.0 ** -20)).float(), (r * (1.0 + 2.0 ** -20)).float()], -1).contiguous()
+        if qscale * s1 * s1 / sa > 4.0:
+            raise NotImplementedError('%s: qact_attn1 grid %g is too fine for scores of scale %g' % (pre, sa, qscale * s1 * s1))
         mask = 100.0 / s2
         if mask != int(mask):
             raise NotImplementedError('%s: 100 / qact2 scale is not an integer' % pre)

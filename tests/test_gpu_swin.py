@@ -199,7 +199,13 @@ def test_swin_tiny_engine_batch128_config5_vs_oracle():
     logits, codes, total, bad = _engine_vs_oracle(model, sub)
     assert torch.equal(logits, full[:2])
     assert total > 3e7
-    print('swin_tiny config 5 on the integer engine: %d codes compared on identical inputs, %d differ' % (total, bad))
+    # the same model with 4-bit weights everywhere, and with the reference's kind of mixed assignment
+    n = model.num_linear_layers()
+    _, _, total4, bad4 = _engine_vs_oracle(model, sub, [4] * n)
+    mixed = [8 if i % 3 == 0 else 4 for i in range(n)]
+    _, _, totalm, badm = _engine_vs_oracle(model, sub, mixed)
+    print('swin_tiny config 5 on the integer engine: %d codes compared on identical inputs, %d differ; W4: %d of %d; '
+          'mixed 4 / 8: %d of %d' % (total, bad, bad4, total4, badm, totalm))
 
 
 def test_swin_base_engine_vs_oracle():
