@@ -54,6 +54,24 @@ class BlockDesc(C.Structure):
                 ('fc1', LinearDesc), ('fc2', LinearDesc), ('attn', Attention)]
 
 
+class SwinBlockDesc(C.Structure):
+    _fields_ = [('norm1', LayerNorm), ('norm2', LayerNorm), ('qkv', LinearDesc), ('proj', LinearDesc),
+                ('fc1', LinearDesc), ('fc2', LinearDesc), ('attn', WindowAttention)]
+
+
+class SwinStageDesc(C.Structure):
+    _fields_ = [('height', C.c_int32), ('width', C.c_int32), ('dim', C.c_int32), ('depth', C.c_int32),
+                ('blocks', C.POINTER(SwinBlockDesc)), ('has_merge', C.c_int32), ('merge_idx', _vp),
+                ('merge_norm', LayerNorm), ('reduction', LinearDesc)]
+
+
+class SwinDesc(C.Structure):
+    _fields_ = [('img_size', C.c_int32), ('patch_size', C.c_int32), ('in_chans', C.c_int32), ('embed_dim', C.c_int32),
+                ('num_stages', C.c_int32), ('num_classes', C.c_int32), ('input_scale', C.c_float),
+                ('patch_embed', LinearDesc), ('pe_norm', LayerNorm), ('stages', C.POINTER(SwinStageDesc)),
+                ('norm', LayerNorm), ('pool_in_scale', C.c_float), ('pool_out_scale', C.c_float), ('head', LinearDesc)]
+
+
 class VitDesc(C.Structure):
     _fields_ = [('img_size', C.c_int32), ('patch_size', C.c_int32), ('in_chans', C.c_int32),
                 ('embed_dim', C.c_int32), ('depth', C.c_int32), ('num_heads', C.c_int32),
@@ -94,6 +112,9 @@ SYMBOLS = {
     'p2v_window_attention_int': (C.c_int, [_vp, _vp, C.c_int, C.POINTER(WindowAttention), _vp]),
     'p2v_gather_row_segments': (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp]),
     'p2v_avgpool_requant': (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, _vp]),
+    'p2v_swin_workspace_bytes': (C.c_int64, [C.POINTER(SwinDesc), C.c_int]),
+    'p2v_swin_launches_per_forward': (C.c_int, [C.POINTER(SwinDesc)]),
+    'p2v_swin_forward': (C.c_int, [C.POINTER(SwinDesc), _vp, _vp, _vp, C.c_int, _vp, _vp]),
     'p2v_unpack_int4': (C.c_int, [_vp, _vp, C.c_int64, _vp]),
     'p2v_select_histogram': (C.c_int, [_vp, C.c_int64, C.c_uint32, C.c_uint32, C.c_int, _vp, _vp]),
     'p2v_observe_minmax': (C.c_int, [_vp, C.c_int64, C.c_int, C.c_int, _vp, _vp, _vp]),

@@ -389,3 +389,148 @@ extern "C" int p2v_avgpool_requant(const int8_t* in, int8_t* out, int images, in
   P2V_CHECK_CUDA(cudaGetLastError());
   return P2V_OK;
 }
+
+// ---- the whole Swin forward as one C call ---------------------------------------------------------------------------
+// Stateless: the descriptor points at the caller's device tensors (weights, per-channel vectors, permutations, tables),
+// the workspace is the caller's, every launch goes to the caller's stream - so the call can be captured into a CUDA
+// graph by the caller (diff_vit_b200/swin_engine.py does).  Same launch sequence as SwinIntegerEngine._run, which
+// stays as the code-dump path of the tests.
+namespace {
+
+inline int64_t align_up(int64_t v) { return (v + 1023) & ~(int64_t)1023; }
+
+struct SwinLayout {
+  int64_t patches, pe, stream[3], ln, qkv, att, hidden, cat, cat_ln, pooled, total;
+};
+
+// Largest extent of every buffer over the stages (rows * channels halves from stage to stage; the hidden width is
+// whatever fc1 says)
+int swin_layout(const p2v_swin_desc* d, int b, SwinLayout* L) {
+  P2V_REQUIRE(d && d->stages && d->num_stages > 0 && b > 0, "p2v_swin: bad descriptor");
+  P2V_REQUIRE(d->patch_size > 0 && d->img_size % d->patch_size == 0, "p2v_swin: image / patch size");
+  const int grid = d->img_size / d->patch_size;
+  int64_t rows0 = (int64_t)b * grid * grid, act = 0, qkv = 0, hid = 0, cat = 0;
+  for (int s = 0; s < d->num_stages; ++s) {
+    const p2v_swin_stage_desc& st = d->stages[s];
+    P2V_REQUIRE(st.blocks && st.depth > 0 && st.dim > 0 && st.height > 0 && st.width > 0, "p2v_swin: stage %d", s);
+    const int64_t rows = (int64_t)b * st.height * st.width;
+    act = act > rows * st.dim ? act : rows * st.dim;
+    qkv = qkv > rows * 3 * st.dim ? qkv : rows * 3 * st.dim;
+    for (int j = 0; j < st.depth; ++j) hid = hid > rows * st.blocks[j].fc1.n ? hid : rows * st.blocks[j].fc1.n;
+    if (st.has_merge) {
+      cat = cat > rows * st.dim ? cat : rows * st.dim;
+      act = act > rows / 4 * st.reduction.n ? act : rows / 4 * st.reduction.n;
+    }
+  }
+  act = act > rows0 * d->embed_dim ? act : rows0 * d->embed_dim;
+  int64_t off = 0;
+  auto take = [&off](int64_t bytes) { const int64_t o = off; off += align_up(bytes); return o; };
+  L->patches = take(rows0 * d->in_chans * d->patch_size * d->patch_size);
+  L->pe = take(rows0 * d->embed_dim);
+  for (int i = 0; i < 3; ++i) L->stream[i] = take(act);
+  L->ln = take(act);
+  L->qkv = take(qkv);
+  L->att = take(act);
+  L->hidden = take(hid);
+  L->cat = take(cat);
+  L->cat_ln = take(cat);
+  L->pooled = take((int64_t)b * d->stages[d->num_stages - 1].dim);
+  L->total = off;
+  return P2V_OK;
+}
+
+int swin_gemm(const int8_t* a, const p2v_linear_desc& lin, int8_t* out, int64_t m, const int8_t* residual, float* out_f32,
+              void* st) {
+  p2v_epilogue e = lin.epi;
+  e.residual = residual;
+  e.aux_codes = nullptr;
+  e.out_f32 = out_f32;
+  e.flags = (e.flags & ~(P2V_EPI_RESIDUAL | P2V_EPI_OUT_F32)) | (residual ? P2V_EPI_RESIDUAL : 0u) | (out_f32 ? P2V_EPI_OUT_F32 : 0u);
+  P2V_REQUIRE(m < (1ll << 31), "p2v_swin: %lld rows", (long long)m);
+  return p2v_gemm_i8(a, lin.k, lin.w, out, lin.n, (int)m, lin.n, lin.k, &e, st);
+}
+
+}  // namespace
+
+#define P2V_TRY(expr)              \
+  do {                             \
+    int _rc = (expr);              \
+    if (_rc != P2V_OK) return _rc; \
+  } while (0)
+
+extern "C" int64_t p2v_swin_workspace_bytes(const p2v_swin_desc* d, int b) {
+  SwinLayout L;
+  if (swin_layout(d, b, &L) != P2V_OK) return -1;
+  return L.total;
+}
+
+extern "C" int p2v_swin_launches_per_forward(const p2v_swin_desc* d) {
+  if (!d || !d->stages) return -1;
+  int n = 3 + 3;   // patchify, patch GEMM, LN | final LN, avgpool, head
+  for (int s = 0; s < d->num_stages; ++s) n += 7 * d->stages[s].depth + (d->stages[s].has_merge ? 3 : 0);
+  return n;
+}
+
+extern "C" int p2v_swin_forward(const p2v_swin_desc* d, const float* x, float* logits, int8_t* logit_codes, int b,
+                                void* workspace, void* stream) {
+  P2V_REQUIRE(x && logits && logit_codes && workspace, "p2v_swin_forward: null pointer");
+  P2V_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 1023) == 0, "p2v_swin_forward: workspace must be 1024-byte aligned");
+  SwinLayout L;
+  P2V_TRY(swin_layout(d, b, &L));
+  int8_t* ws = static_cast<int8_t*>(workspace);
+  int8_t* patches = ws + L.patches;
+  int8_t* pe = ws + L.pe;
+  int8_t* ln = ws + L.ln;
+  int8_t* qkv = ws + L.qkv;
+  int8_t* att = ws + L.att;
+  int8_t* hidden = ws + L.hidden;
+  const int grid = d->img_size / d->patch_size;
+  int64_t rows = (int64_t)b * grid * grid;
+  P2V_TRY(p2v_quant_patchify(x, patches, b, d->in_chans, d->img_size, d->img_size, d->patch_size, d->input_scale, 0.f, stream));
+  P2V_TRY(swin_gemm(patches, d->patch_embed, pe, rows, nullptr, nullptr, stream));
+  int cur = 0;                                        // which of the three stream buffers holds the residual stream
+  int8_t* xs = ws + L.stream[cur];
+  P2V_TRY(p2v_layernorm_int(pe, d->embed_dim, xs, nullptr, (int)rows, d->embed_dim, &d->pe_norm, stream));
+  for (int s = 0; s < d->num_stages; ++s) {
+    const p2v_swin_stage_desc& st = d->stages[s];
+    const int C = st.dim;
+    rows = (int64_t)b * st.height * st.width;
+    for (int j = 0; j < st.depth; ++j) {
+      const p2v_swin_block_desc& blk = st.blocks[j];
+      int8_t* x1 = ws + L.stream[(cur + 1) % 3];
+      int8_t* xn = ws + L.stream[(cur + 2) % 3];
+      P2V_TRY(p2v_layernorm_int(xs, C, ln, nullptr, (int)rows, C, &blk.norm1, stream));
+      P2V_TRY(swin_gemm(ln, blk.qkv, qkv, rows, nullptr, nullptr, stream));
+      p2v_window_attention wa = blk.attn;
+      wa.dump_a1 = wa.dump_a2 = nullptr;
+      wa.dump_softmax = nullptr;
+      P2V_TRY(p2v_window_attention_int(qkv, att, b, &wa, stream));
+      P2V_TRY(swin_gemm(att, blk.proj, x1, rows, xs, nullptr, stream));             // + shortcut, qact2
+      P2V_TRY(p2v_layernorm_int(x1, C, ln, nullptr, (int)rows, C, &blk.norm2, stream));   // LN2 .. mlp.qact0
+      P2V_TRY(swin_gemm(ln, blk.fc1, hidden, rows, nullptr, nullptr, stream));
+      P2V_TRY(swin_gemm(hidden, blk.fc2, xn, rows, x1, nullptr, stream));           // + residual, qact4
+      cur = (cur + 2) % 3;
+      xs = xn;
+    }
+    if (st.has_merge) {
+      int8_t* cat = ws + L.cat;
+      int8_t* cat_ln = ws + L.cat_ln;
+      int8_t* xn = ws + L.stream[(cur + 1) % 3];
+      const int tokens = st.height * st.width;
+      P2V_TRY(p2v_gather_row_segments(xs, cat, st.merge_idx, b, tokens, tokens / 4, 4, C, stream));
+      P2V_TRY(p2v_layernorm_int(cat, 4 * C, cat_ln, nullptr, (int)(rows / 4), 4 * C, &st.merge_norm, stream));
+      P2V_TRY(swin_gemm(cat_ln, st.reduction, xn, rows / 4, nullptr, nullptr, stream));
+      cur = (cur + 1) % 3;
+      xs = xn;
+    }
+  }
+  const p2v_swin_stage_desc& last = d->stages[d->num_stages - 1];
+  const int C = last.has_merge ? last.reduction.n : last.dim;
+  const int tokens = last.has_merge ? last.height * last.width / 4 : last.height * last.width;
+  rows = (int64_t)b * tokens;
+  int8_t* pooled = ws + L.pooled;
+  P2V_TRY(p2v_layernorm_int(xs, C, ln, nullptr, (int)rows, C, &d->norm, stream));
+  P2V_TRY(p2v_avgpool_requant(ln, pooled, b, tokens, C, d->pool_in_scale, d->pool_out_scale, 0.f, stream));
+  P2V_TRY(swin_gemm(pooled, d->head, logit_codes, b, nullptr, logits, stream));
+  return P2V_OK;
+}

@@ -3,9 +3,11 @@
 ``build_swin_plan`` turns the calibrated state (``swin_quant.extract_swin_state``) into integer weight codes plus the
 per-channel vectors of every fused epilogue, the window permutations / shift-mask regions / relative-position bias of
 every attention layer and the 2 x 2 gather of every PatchMerging - plain CPU tensors, executable on the host by
-tests/hostmath for the CPU test-suite.  ``SwinIntegerEngine`` uploads a plan and runs it through the kernel-level C
-ABI (include/p2v.h): tcgen05 GEMMs with fused re-quantisation / GELU / residual epilogues, the integer LayerNorm, the
-window attention kernel (csrc/p2v_swin.cu).  Activations are int8 codes in token order from the patch embedding to
+tests/hostmath for the CPU test-suite.  ``SwinIntegerEngine`` uploads a plan, describes it as a ``p2v_swin_desc`` and
+runs it with ONE C call per forward (``p2v_swin_forward``, include/p2v.h; captured into a CUDA graph per batch size):
+tcgen05 GEMMs with fused re-quantisation / GELU / residual epilogues, the integer LayerNorm, the window attention
+kernel (csrc/p2v_swin.cu).  ``forward_dump`` issues the same launches one by one from Python (``_run``) with every
+intermediate code tensor copied out - the path the parity tests compare with the oracle, and with ``forward``.  Activations are int8 codes in token order from the patch embedding to
 the head; the cyclic shift and the window partition are index permutations inside the attention kernel.
 
 Per block (models/swin_quant.py:345-399, WindowAttention.forward :177-221, Mlp models/layers_quant.py:304-346):
@@ -255,6 +257,36 @@ class _Bound:
             self.stages.append(NS(res=st.res, dim=st.dim, heads=st.heads, blocks=blocks, merge=merge))
         self.norm = self.ln(plan.norm)
         self.head = self.linear(plan.head)
+        self.desc = self._descriptor()
+
+    def _descriptor(self):
+        """The plan as a p2v_swin_desc (include/p2v.h): what p2v_swin_forward walks."""
+        a = self.plan.arch
+        ld = lambda lin: _cabi.LinearDesc(w=lin.w.data_ptr(), n=lin.n, k=lin.k, epi=lin.epi)
+        self._c_blocks, stages = [], (_cabi.SwinStageDesc * len(self.stages))()
+        for i, st in enumerate(self.stages):
+            blocks = (_cabi.SwinBlockDesc * len(st.blocks))()
+            for j, b in enumerate(st.blocks):
+                blocks[j].norm1, blocks[j].norm2 = b.norm1, b.norm2
+                blocks[j].qkv, blocks[j].proj, blocks[j].fc1, blocks[j].fc2 = ld(b.qkv), ld(b.proj), ld(b.fc1), ld(b.fc2)
+                blocks[j].attn = b.attn
+            self._c_blocks.append(blocks)
+            s = stages[i]
+            s.height, s.width, s.dim, s.depth = st.res[0], st.res[1], st.dim, len(st.blocks)
+            s.blocks = C.cast(blocks, C.POINTER(_cabi.SwinBlockDesc))
+            s.has_merge = int(st.merge is not None)
+            if st.merge is not None:
+                s.merge_idx, s.merge_norm, s.reduction = st.merge.idx.data_ptr(), st.merge.norm, ld(st.merge.reduction)
+        self._c_stages = stages
+        d = _cabi.SwinDesc()
+        d.img_size, d.patch_size, d.in_chans = a['img_size'], a['patch_size'], a['in_chans']
+        d.embed_dim, d.num_stages, d.num_classes = a['embed_dim'], len(self.stages), a['num_classes']
+        d.input_scale = self.plan.input_scale
+        d.patch_embed, d.pe_norm = ld(self.patch_embed), self.pe_norm
+        d.stages = C.cast(stages, C.POINTER(_cabi.SwinStageDesc))
+        d.norm, d.head = self.norm, ld(self.head)
+        d.pool_in_scale, d.pool_out_scale = self.plan.pool_in_scale, self.plan.pool_out_scale
+        return d
 
     def up(self, t):
         if t is None:
@@ -497,16 +529,29 @@ class SwinIntegerEngine:
                 return logits.clone()
             logits = torch.empty(b, nc, dtype=torch.float32, device=self.device)
             codes = self.buf('logit_codes', b, nc)
-            self._run(b, x, logits, codes)
+            self._c_forward(bound, b, x, logits, codes)
             if graph:
                 xs = x.clone()
                 out = torch.empty_like(logits)
                 torch.cuda.current_stream(self.device).synchronize()
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):
-                    self._run(b, xs, out, codes)
+                    self._c_forward(bound, b, xs, out, codes)
                 self._graphs[gk] = (g, xs, out)
             return logits
+
+    def _c_forward(self, bound, b, x, logits, codes):
+        """One p2v_swin_forward call (csrc/p2v_swin.cu): the launch sequence of `_run` without the dumps, on the
+        current stream, over one workspace per batch size."""
+        lib = _cabi.lib()
+        nbytes = lib.p2v_swin_workspace_bytes(C.byref(bound.desc), b)
+        if nbytes < 0:
+            _cabi.check(-1)
+        ws = self.buf('workspace', nbytes + 1024, dtype=torch.uint8)
+        ptr = ws.data_ptr() + (-ws.data_ptr()) % 1024
+        _cabi.check(lib.p2v_swin_forward(C.byref(bound.desc), x.data_ptr(), logits.data_ptr(), codes.data_ptr(), b, ptr,
+                                         _cabi.current_stream(self.device)))
+        self.launches = lib.p2v_swin_launches_per_forward(C.byref(bound.desc))
 
     def forward_dump(self, x, bit_config=None):
         """(logits, {golden-style key: integer codes on the CPU}) - every quantizer's codes in the layout of

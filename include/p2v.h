@@ -212,6 +212,20 @@ int p2v_gather_row_segments(const int8_t* in, int8_t* out, const int32_t* idx, i
 int p2v_avgpool_requant(const int8_t* in, int8_t* out, int images, int tokens, int channels, float in_scale,
                         float out_scale, float out_zp, void* stream);
 
+/* The whole quantized Swin forward as one call.  Replaces SwinTransformer.forward in quantized mode
+ * (models/swin_quant.py:790-817) with everything below it (PatchEmbed, BasicLayer, SwinTransformerBlock :345-399,
+ * WindowAttention :177-221, Mlp, PatchMerging :445-467).  Stateless: the descriptor and the HOST arrays it points at
+ * (stages, blocks) are read during the call, every device buffer belongs to the caller, all launches go to `stream`
+ * - so a caller may capture the call into a CUDA graph.  workspace: p2v_swin_workspace_bytes(desc, b) bytes,
+ * 1024-byte aligned.  x fp32 [b, in_chans, img, img]; logits fp32 [b, classes]; logit_codes int8 [b, classes]. */
+typedef struct p2v_swin_block_desc p2v_swin_block_desc;
+typedef struct p2v_swin_stage_desc p2v_swin_stage_desc;
+typedef struct p2v_swin_desc p2v_swin_desc;
+int64_t p2v_swin_workspace_bytes(const p2v_swin_desc* desc, int b);
+int p2v_swin_launches_per_forward(const p2v_swin_desc* desc);
+int p2v_swin_forward(const p2v_swin_desc* desc, const float* x, float* logits, int8_t* logit_codes, int b,
+                     void* workspace, void* stream);
+
 /* ---- the operators on their own, fp32 in / fp32 out (module-level use) -------------------------------- */
 /* QIntLayerNorm.forward in mode 'int' (models/ptq/layers.py:255-289) on dequantized fp32 rows x [rows, d]:
  * x_q = RNE(x / in_scale[c]) * in_mask[c] with in_mask = RNE(in_scale / in_scale1), in_scale1 = min(in_scale);
@@ -280,6 +294,30 @@ typedef struct p2v_vit_desc {
   p2v_layernorm norm;                      /* final norm (CLS rows) -> qact2 */
   p2v_linear_desc head;                    /* epilogue = act_out, OUT_F32 */
 } p2v_vit_desc;
+
+struct p2v_swin_block_desc {
+  p2v_layernorm norm1, norm2;               /* norm2: LN2 + qact3 + / channel scale + mlp.qact0 (pre_clamp) */
+  p2v_linear_desc qkv, proj, fc1, fc2;      /* proj / fc2 run with the residual epilogue */
+  p2v_window_attention attn;
+};
+struct p2v_swin_stage_desc {
+  int32_t height, width, dim, depth;        /* token grid, channels and blocks of the stage */
+  const p2v_swin_block_desc* blocks;        /* HOST array [depth] */
+  int32_t has_merge;                        /* PatchMerging behind the blocks */
+  const int32_t* merge_idx;                 /* device [height / 2 * width / 2 * 4]: x0 / x1 / x2 / x3 source tokens */
+  p2v_layernorm merge_norm;                 /* over 4 * dim channels */
+  p2v_linear_desc reduction;                /* 4 * dim -> 2 * dim, epilogue = downsample.qact2 */
+};
+struct p2v_swin_desc {
+  int32_t img_size, patch_size, in_chans, embed_dim, num_stages, num_classes;
+  float input_scale;                        /* qact_input (symmetric) */
+  p2v_linear_desc patch_embed;              /* 4 x 4 conv as GEMM, epilogue = patch_embed.qact_before_norm */
+  p2v_layernorm pe_norm;                    /* patch_embed.norm + patch_embed.qact */
+  const p2v_swin_stage_desc* stages;        /* HOST array [num_stages] */
+  p2v_layernorm norm;                       /* final norm + qact2 */
+  float pool_in_scale, pool_out_scale;      /* qact2 / qact3 around the token average */
+  p2v_linear_desc head;                     /* epilogue = act_out, fp32 logits */
+};
 
 typedef struct p2v_vit p2v_vit;
 
