@@ -292,3 +292,26 @@ def test_window_attention_kernel_matches_its_integer_formulation(cabi, heads, re
     np.testing.assert_array_equal(out.cpu().numpy(), want)
     np.testing.assert_array_equal(out2.cpu().numpy(), want)
     assert (wsm < 16).mean() > 0.02 and len(np.unique(want)) > 8
+
+
+def test_swin_engine_scope_float_scale_grids_keep_the_per_module_path():
+    """The engine covers symmetric power-of-two activation grids (the minmax observer of config 5).  A model
+    calibrated with a float-scale observer is refused once (NotImplementedError inside, recorded on the model) and its
+    forward keeps running on the per-module operators - same logits as with `per_module` forced."""
+    import diff_vit_b200 as dv
+    z = np.load(os.path.join(GOLDEN, 'swin_micro.npz'))
+    a = [int(v) for v in z['arch']]
+    model = dv.SwinTransformer(img_size=a[0], patch_size=a[1], num_classes=a[2], embed_dim=a[3], window_size=a[4],
+                               depths=tuple(a[5:7]), num_heads=tuple(a[7:9]), norm_layer=dv.QIntLayerNorm,
+                               input_quant=True, cfg=dv.Config(True, True, 'percentile')).eval()
+    model.load_state_dict({k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith('sd/')}, strict=True)
+    model = model.cuda()
+    dv.calibrate_model(model, [torch.from_numpy(z['x_calib']).cuda()])
+    x = torch.from_numpy(z['x_eval']).cuda()
+    with torch.no_grad():
+        got = model(x)
+    assert model._engine_off, 'a percentile-calibrated model must be outside the integer engine'
+    model.per_module = True
+    with torch.no_grad():
+        want = model(x)
+    assert torch.equal(got, want) and got.std() > 0
