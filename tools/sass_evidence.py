@@ -1,6 +1,6 @@
 """Which Blackwell-native instructions each hot kernel of libp2vit_b200.so contains (cuobjdump -sass):
 UTCIMMA = tcgen05.mma kind::i8, LDTM / STTM = tcgen05.ld / .st, UTMALDG / UTMASTG = TMA loads / stores, UTCBAR =
-tcgen05.commit, IMMA = the legacy mma.sync path.
+tcgen05.commit, IMMA = the legacy mma.sync path, IDP.4A = dp4a (the Swin window attention kernel's products).
 
     python tools/sass_evidence.py > profiles/r2_sass_evidence.txt
 """
@@ -10,7 +10,7 @@ import re
 import subprocess
 
 LIB = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'diff_vit_b200', 'libp2vit_b200.so')
-PAT = re.compile(r'\b(UTCIMMA|LDTM|STTM|UTMALDG|UTMASTG|UTCBAR|IMMA|UBLKCP|SYNCS)[A-Z0-9_.x]*')
+PAT = re.compile(r'\b(UTCIMMA|LDTM|STTM|UTMALDG|UTMASTG|UTCBAR|IMMA|IDP|UBLKCP|SYNCS)[A-Z0-9_.x]*')
 out = subprocess.run(['cuobjdump', '-sass', LIB], capture_output=True, text=True).stdout
 kernels = collections.OrderedDict()
 name = None
