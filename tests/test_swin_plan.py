@@ -90,3 +90,30 @@ def test_swin_flops_list_and_engine_dispatch_rules(swin_golden):
     model._engine = object()
     model.load_state_dict(model.state_dict())
     assert model._engine is None
+
+
+def test_swin_plan_scope_is_enforced(swin_model):
+    """What the Swin integer plan refuses (the model then keeps its per-module path): asymmetric quantizers, float
+    activation grids where a power of two is assumed, a qact2 grid that makes the shift mask's -100 a non-integer."""
+    import copy
+    state = extract_swin_state(swin_model)
+    n = num_linear_layers(state['arch'])
+    build_swin_plan(state, [8] * n)                                        # the calibrated state itself is inside
+    with pytest.raises(IndexError):
+        build_swin_plan(state, [8] * 3)
+    with pytest.raises(KeyError):
+        build_swin_plan(state, [6] * n)                                    # the reference: BIT_TYPE_DICT['int6']
+    pre = 'layers.0.blocks.1.attn'
+    s = copy.deepcopy(state)
+    sc, zp, lo, hi = s['act'][pre + '.qact2']
+    s['act'][pre + '.qact2'] = (sc, zp + 3.0, lo, hi)
+    with pytest.raises(NotImplementedError, match='symmetric'):
+        build_swin_plan(s, [8] * n)
+    s = copy.deepcopy(state)
+    s['act'][pre + '.qact_attn1'] = (sc * 0.3, zp, lo, hi)
+    with pytest.raises(NotImplementedError, match='power of two'):
+        build_swin_plan(s, [8] * n)
+    s = copy.deepcopy(state)
+    s['act'][pre + '.qact2'] = (torch.full_like(sc, 8.0), zp, lo, hi)      # 100 / 8 = 12.5
+    with pytest.raises(NotImplementedError):                               # (the integer exp or the mask check trips)
+        build_swin_plan(s, [8] * n)
