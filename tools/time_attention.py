@@ -42,7 +42,7 @@ def main():
         _cabi.check(_cabi.lib().p2v_attention_tc_set_skew(int(os.environ['P2V_ATT_SKEW'])))
     b = int(sys.argv[1]) if len(sys.argv) > 1 else 256
     mode = sys.argv[2] if len(sys.argv) > 2 else '60'
-    n, heads = 197, 6
+    n, heads = int(os.environ.get('P2V_ATT_N', '197')), 6      # P2V_ATT_N: token count (what the ragged 197 = 6 x 32 + 5 costs)
     torch.manual_seed(0)
     if mode != 'real':
         spread = int(mode)
@@ -53,7 +53,7 @@ def main():
         c = _cabi.Attention()
         c.score_mul, c.score_zp, c.out_mul, c.out_zp, c.softmax_levels = p.score_mul, p.score_zp, p.out_mul, p.out_zp, 16
         c.in_zp, c.exp_lut, c.lut_sig_bits = 0.0, lut.data_ptr(), p.lut_sig_bits
-        time_both(qkv, b, n, heads, c, 'random +-%d, b=%d' % (spread, b))
+        time_both(qkv, b, n, heads, c, 'random +-%d, b=%d, n=%d' % (spread, b, n))
         return
     import diff_vit_b200 as dv
     model = dv.deit_small_patch16_224(pretrained=False, cfg=dv.Config(True, True, 'minmax')).eval().cuda()
