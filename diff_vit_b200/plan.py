@@ -358,17 +358,29 @@ def build_plan(state, bit_config):
 _PLAN_CLASSES = {c.__name__: c for c in (LinearPlan, LayerNormPlan, AttentionPlan, BlockPlan, VitPlan)}
 
 
+def _is_record(obj):
+    from types import SimpleNamespace
+    return hasattr(obj, '__dataclass_fields__') or isinstance(obj, SimpleNamespace)
+
+
 def _flatten(obj, prefix, out):
+    from types import SimpleNamespace
     if isinstance(obj, torch.Tensor):
         out[prefix] = obj.detach().cpu().numpy()
     elif hasattr(obj, '__dataclass_fields__'):
         out[prefix + '/__class__'] = type(obj).__name__
         for f in obj.__dataclass_fields__:
             _flatten(getattr(obj, f), prefix + '/' + f, out)
-    elif isinstance(obj, (list, tuple)) and obj and hasattr(obj[0], '__dataclass_fields__'):
+    elif isinstance(obj, SimpleNamespace):           # the Swin plans (swin_engine.py) are namespaces of the same leaves
+        out[prefix + '/__ns__'] = ','.join(vars(obj))
+        for f, v in vars(obj).items():
+            _flatten(v, prefix + '/' + f, out)
+    elif isinstance(obj, (list, tuple)) and obj and _is_record(obj[0]):
         out[prefix + '/__len__'] = len(obj)
         for i, o in enumerate(obj):
             _flatten(o, '%s/%d' % (prefix, i), out)
+    elif isinstance(obj, (list, tuple)):             # plain tuples (bit_config, a stage's resolution): keep the type
+        out[prefix + '/__tuple__'] = repr(tuple(obj))
     elif isinstance(obj, dict):
         out[prefix + '/__dict__'] = repr(sorted(obj.items()))
     elif obj is None:
@@ -408,6 +420,12 @@ def _unflatten(z, prefix):
         return dict(ast.literal_eval(str(z[prefix + '/__dict__'])))
     if prefix + '/__len__' in z:
         return [_unflatten(z, '%s/%d' % (prefix, i)) for i in range(int(z[prefix + '/__len__']))]
+    if prefix + '/__tuple__' in z:
+        return tuple(ast.literal_eval(str(z[prefix + '/__tuple__'])))
+    if prefix + '/__ns__' in z:
+        from types import SimpleNamespace
+        names = [f for f in str(z[prefix + '/__ns__']).split(',') if f]
+        return SimpleNamespace(**{f: _unflatten(z, prefix + '/' + f) for f in names})
     if prefix + '/__class__' in z:
         cls = _PLAN_CLASSES[str(z[prefix + '/__class__'])]
         import dataclasses

@@ -238,6 +238,39 @@ def build_swin_plan(state, bit_config=None):
     return _SwinBuilder(state, bit_config).build()
 
 
+# ---- serialised plans (SURVEY section 5 "checkpoint / resume": the reference keeps calibrated scales only as Python
+# attributes; an integer plan is self-contained and runs without the float model) ------------------------------------
+def _plan_linears(plan):
+    yield plan, 'patch_embed'
+    for st in plan.stages:
+        for b in st.blocks:
+            for f in ('qkv', 'proj', 'fc1', 'fc2'):
+                yield b, f
+        if st.merge is not None:
+            yield st.merge, 'reduction'
+    yield plan, 'head'
+
+
+def save_swin_plan(plan, path, pack4=True):
+    """Write a Swin plan to a compressed .npz file (same format as plan.save_plan); 4-bit layers int4-packed."""
+    import copy
+    from .plan import _flatten
+    if pack4:
+        plan = copy.deepcopy(plan)
+        for owner, f in _plan_linears(plan):
+            setattr(owner, f, getattr(owner, f).pack())
+    flat = {}
+    _flatten(plan, 'plan', flat)
+    np.savez_compressed(path, **{k: np.asarray(v) for k, v in flat.items()})
+
+
+def load_swin_plan(path):
+    """Read a plan written by `save_swin_plan`."""
+    from .plan import _unflatten
+    with np.load(path) as z:
+        return _unflatten({k: z[k] for k in z.files}, 'plan')
+
+
 # ---- execution ----------------------------------------------------------------------------------------------------
 class _Bound:
     """A plan's tensors on one device plus the C descriptors that point at them."""
@@ -332,10 +365,14 @@ class _Bound:
 class SwinIntegerEngine:
     """Quantized forward of one calibrated SwinTransformer on one CUDA device."""
 
-    def __init__(self, model=None, state=None, device=None, max_plans=4):
-        if state is None:
+    def __init__(self, model=None, state=None, device=None, max_plans=4, plans=()):
+        """`plans`: ready-made plans (`load_swin_plan`), served for their bit_config without the float model."""
+        plans = list(plans)
+        if state is None and model is not None:
             from .swin_quant import extract_swin_state
             state = extract_swin_state(model)
+        if state is None and not plans:
+            raise ValueError('SwinIntegerEngine needs a calibrated model, its state, or serialised plans')
         if device is None:
             device = next(model.parameters()).device if model is not None else torch.device('cuda')
         self.device = torch.device(device)
@@ -345,8 +382,9 @@ class SwinIntegerEngine:
             self.device = torch.device('cuda', torch.cuda.current_device())
         _cabi.lib()          # fails loudly when the library is missing: there is no other implementation
         self.state = state
-        self.arch = state['arch']
-        self.max_plans = max_plans
+        self.arch = state['arch'] if state is not None else plans[0].arch
+        self.max_plans = max(max_plans, len(plans))
+        self._ready = {tuple(int(b) for b in p.bit_config): p for p in plans}
         self._bound = {}      # bit_config tuple -> _Bound
         self._buf = {}        # (name, shape) -> tensor
         self._graphs = {}     # (bit_config, batch) -> (graph, x_static, logits_static)
@@ -361,7 +399,13 @@ class SwinIntegerEngine:
                 old = next(iter(self._bound))
                 del self._bound[old]
                 self._graphs = {k: v for k, v in self._graphs.items() if k[0] != old}
-            self._bound[key] = _Bound(build_swin_plan(self.state, key), self.device)
+            if key in self._ready:
+                plan = self._ready[key]
+            elif self.state is not None:
+                plan = build_swin_plan(self.state, key)
+            else:
+                raise KeyError('no serialised plan for bit_config %s and no calibrated state to build one from' % (key,))
+            self._bound[key] = _Bound(plan, self.device)
         return key, self._bound[key]
 
     def buf(self, name, *shape, dtype=torch.int8):

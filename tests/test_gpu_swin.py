@@ -315,3 +315,27 @@ def test_swin_engine_scope_float_scale_grids_keep_the_per_module_path():
     with torch.no_grad():
         want = model(x)
     assert torch.equal(got, want) and got.std() > 0
+
+
+def test_swin_engine_from_a_serialised_plan(tmp_path):
+    """A plan written by save_swin_plan runs on a fresh engine without the float model: same logits as the model's
+    own engine, for the 8-bit and for a mixed 4 / 8-bit assignment (int4-packed layers in the file)."""
+    import diff_vit_b200 as dv
+    from diff_vit_b200.swin_engine import SwinIntegerEngine, load_swin_plan, save_swin_plan
+    z = np.load(os.path.join(GOLDEN, 'swin_micro.npz'))
+    model = build_swin_micro(z).cuda()
+    dv.calibrate_model(model, [torch.from_numpy(z['x_calib']).cuda()])
+    x = torch.from_numpy(z['x_eval']).cuda()
+    n = model.num_linear_layers()
+    eng = model.integer_engine()
+    plans = []
+    for i, bits in enumerate(([8] * n, [4 if j % 2 else 8 for j in range(n)])):
+        _, bound = eng.bound(bits)
+        path = str(tmp_path / ('plan%d.npz' % i))
+        save_swin_plan(bound.plan, path)
+        plans.append(load_swin_plan(path))
+    fresh = SwinIntegerEngine(device='cuda', plans=plans)
+    for bits in ([8] * n, [4 if j % 2 else 8 for j in range(n)]):
+        assert torch.equal(fresh.forward(x, bits), eng.forward(x, bits))
+    with pytest.raises(KeyError):
+        fresh.forward(x, [4] * n)              # no such plan in the files and no calibrated state to build it from

@@ -117,3 +117,25 @@ def test_swin_plan_scope_is_enforced(swin_model):
     s['act'][pre + '.qact2'] = (torch.full_like(sc, 8.0), zp, lo, hi)      # 100 / 8 = 12.5
     with pytest.raises(NotImplementedError):                               # (the integer exp or the mask check trips)
         build_swin_plan(s, [8] * n)
+
+
+def test_swin_plan_round_trips_through_a_file(swin_model, swin_golden, tmp_path):
+    """save_swin_plan / load_swin_plan: the integer plan on disk (4-bit layers int4-packed) executes to the same codes."""
+    from diff_vit_b200.swin_engine import load_swin_plan, save_swin_plan
+    state = extract_swin_state(swin_model)
+    n = num_linear_layers(state['arch'])
+    bits = [4 if i % 2 else 8 for i in range(n)]
+    plan = build_swin_plan(state, bits)
+    path = str(tmp_path / 'swin_plan.npz')
+    save_swin_plan(plan, path)
+    back = load_swin_plan(path)
+    assert back.bit_config == tuple(bits) and back.stages[0].res == plan.stages[0].res
+    assert back.stages[0].blocks[0].qkv.w is None and back.stages[0].blocks[0].qkv.w4 is not None     # 4-bit: packed nibbles
+    assert back.patch_embed.w is not None and back.patch_embed.w4 is None                             # 8-bit: int8 codes
+    x = swin_golden['x_eval']
+    want_logits, want = hostmath.run_swin_plan(plan, x)
+    got_logits, got = hostmath.run_swin_plan(back, x)
+    assert set(got) == set(want)
+    for k in want:
+        np.testing.assert_array_equal(got[k], want[k], err_msg=k)
+    np.testing.assert_array_equal(got_logits, want_logits)
