@@ -115,6 +115,7 @@ SYMBOLS = {
     'p2v_swin_workspace_bytes': (C.c_int64, [C.POINTER(SwinDesc), C.c_int]),
     'p2v_swin_launches_per_forward': (C.c_int, [C.POINTER(SwinDesc)]),
     'p2v_swin_forward': (C.c_int, [C.POINTER(SwinDesc), _vp, _vp, _vp, C.c_int, _vp, _vp]),
+    'p2v_swin_forward_u8': (C.c_int, [C.POINTER(SwinDesc), _vp, _vp, _vp, _vp, _vp, C.c_int, _vp, _vp]),
     'p2v_unpack_int4': (C.c_int, [_vp, _vp, C.c_int64, _vp]),
     'p2v_select_histogram': (C.c_int, [_vp, C.c_int64, C.c_uint32, C.c_uint32, C.c_int, _vp, _vp]),
     'p2v_observe_minmax': (C.c_int, [_vp, C.c_int64, C.c_int, C.c_int, _vp, _vp, _vp]),

@@ -493,6 +493,8 @@ __global__ void fake_quant_f32_kernel(const float* __restrict__ x, float* __rest
 
 int quant_patchify_small_launch(const float* x, int8_t* codes, int b, int c, int h, int w, int p, float scale,
                                 float zero_point, cudaStream_t st);   // p2v_swin.cu
+int quant_patchify_small_u8_launch(const uint8_t* x, int8_t* codes, int b, int c, int h, int w, int p, float scale,
+                                   float zero_point, const float* mean, const float* stdv, cudaStream_t st);
 
 static int grid_for(int64_t work, int block) {
   int64_t g = (work + block - 1) / block;
@@ -524,7 +526,8 @@ extern "C" int p2v_quant_patchify_u8(const uint8_t* x, int8_t* codes, int b, int
   P2V_REQUIRE(x && codes && mean && stdv, "p2v_quant_patchify_u8: null pointer");
   P2V_REQUIRE(b > 0 && c > 0 && c <= 4 && p > 0 && h % p == 0 && w % p == 0,
               "p2v_quant_patchify_u8: bad shape %dx%dx%dx%d p=%d (at most 4 channels)", b, c, h, w, p);
-  P2V_REQUIRE(p % 16 == 0 && w % 16 == 0, "p2v_quant_patchify_u8: patch size and width must be multiples of 16");
+  if (p % 16 != 0 || w % 16 != 0)   // small patches (Swin: 4 x 4): four pixels per thread, csrc/p2v_swin.cu
+    return quant_patchify_small_u8_launch(x, codes, b, c, h, w, p, scale, zero_point, mean, stdv, (cudaStream_t)stream);
   P2V_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0, "p2v_quant_patchify_u8: x must be 16-byte aligned");
   U8Norm nm = {};
   for (int i = 0; i < c; ++i) {

@@ -324,6 +324,53 @@ int quant_patchify_small_launch(const float* x, int8_t* codes, int b, int c, int
   return P2V_OK;
 }
 
+// The same from 8-bit pixels (see quant_patchify_u8_kernel in p2v_rowops.cu): the loader's (p / 255 - mean[c]) / std[c]
+// and the input quantizer are evaluated once per (channel, pixel value) into a shared-memory table of codes per block,
+// and the image becomes a byte gather, four pixels per thread.
+struct U8NormSmall {
+  float mean[4], stdv[4];
+};
+__global__ void __launch_bounds__(256)
+quant_patchify_small_u8_kernel(const uint8_t* __restrict__ x, int8_t* __restrict__ codes, int c, int h, int w, int p,
+                               float scale, float zp, U8NormSmall nm, int64_t total_words) {
+  __shared__ uint8_t lut[4][256];
+  for (int i = threadIdx.x; i < c * 256; i += blockDim.x) {
+    const int ch = i >> 8, v = i & 255;
+    const float xn = fdiv(fsub(fdiv((float)v, 255.0f), nm.mean[ch]), nm.stdv[ch]);
+    lut[ch][v] = (uint8_t)(int8_t)quant_div(xn, scale, zp, -128, 127);
+  }
+  __syncthreads();
+  const int wp = p / 4, gw = w / p, gh = h / p;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total_words; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t t = i;
+    const int kw4 = (int)(t % wp); t /= wp;
+    const int kh = (int)(t % p); t /= p;
+    const int ch = (int)(t % c); t /= c;
+    const int px = (int)(t % gw); t /= gw;
+    const int py = (int)(t % gh);
+    const int64_t img = t / gh;
+    const uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(x + ((img * c + ch) * h + (py * p + kh)) * (int64_t)w + px * p + kw4 * 4));
+    reinterpret_cast<uint32_t*>(codes)[i] = (uint32_t)lut[ch][v & 0xff] | ((uint32_t)lut[ch][(v >> 8) & 0xff] << 8) |
+                                            ((uint32_t)lut[ch][(v >> 16) & 0xff] << 16) | ((uint32_t)lut[ch][v >> 24] << 24);
+  }
+}
+
+int quant_patchify_small_u8_launch(const uint8_t* x, int8_t* codes, int b, int c, int h, int w, int p, float scale,
+                                   float zero_point, const float* mean, const float* stdv, cudaStream_t st) {
+  P2V_REQUIRE(p % 4 == 0 && w % 4 == 0, "p2v_quant_patchify_u8: patch size and width must be multiples of 4");
+  P2V_REQUIRE((reinterpret_cast<uintptr_t>(x) & 3) == 0 && (reinterpret_cast<uintptr_t>(codes) & 3) == 0,
+              "p2v_quant_patchify_u8: x must be 4-byte aligned");
+  U8NormSmall nm = {};
+  for (int i = 0; i < c; ++i) {
+    nm.mean[i] = mean[i];
+    nm.stdv[i] = stdv[i];
+  }
+  const int64_t total = (int64_t)b * c * h * (w / 4);
+  quant_patchify_small_u8_kernel<<<grid_for_work(total, 256), 256, 0, st>>>(x, codes, c, h, w, p, scale, zero_point, nm, total);
+  P2V_CHECK_CUDA(cudaGetLastError());
+  return P2V_OK;
+}
+
 }  // namespace p2v
 
 using namespace p2v;
@@ -471,9 +518,9 @@ extern "C" int p2v_swin_launches_per_forward(const p2v_swin_desc* d) {
   return n;
 }
 
-extern "C" int p2v_swin_forward(const p2v_swin_desc* d, const float* x, float* logits, int8_t* logit_codes, int b,
-                                void* workspace, void* stream) {
-  P2V_REQUIRE(x && logits && logit_codes && workspace, "p2v_swin_forward: null pointer");
+static int swin_forward_impl(const p2v_swin_desc* d, const float* x, const uint8_t* x8, const float* mean, const float* stdv,
+                             float* logits, int8_t* logit_codes, int b, void* workspace, void* stream) {
+  P2V_REQUIRE((x || x8) && logits && logit_codes && workspace, "p2v_swin_forward: null pointer");
   P2V_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 1023) == 0, "p2v_swin_forward: workspace must be 1024-byte aligned");
   SwinLayout L;
   P2V_TRY(swin_layout(d, b, &L));
@@ -486,7 +533,11 @@ extern "C" int p2v_swin_forward(const p2v_swin_desc* d, const float* x, float* l
   int8_t* hidden = ws + L.hidden;
   const int grid = d->img_size / d->patch_size;
   int64_t rows = (int64_t)b * grid * grid;
-  P2V_TRY(p2v_quant_patchify(x, patches, b, d->in_chans, d->img_size, d->img_size, d->patch_size, d->input_scale, 0.f, stream));
+  if (x8 != nullptr)
+    P2V_TRY(p2v_quant_patchify_u8(x8, patches, b, d->in_chans, d->img_size, d->img_size, d->patch_size, d->input_scale, 0.f,
+                                  mean, stdv, stream));
+  else
+    P2V_TRY(p2v_quant_patchify(x, patches, b, d->in_chans, d->img_size, d->img_size, d->patch_size, d->input_scale, 0.f, stream));
   P2V_TRY(swin_gemm(patches, d->patch_embed, pe, rows, nullptr, nullptr, stream));
   int cur = 0;                                        // which of the three stream buffers holds the residual stream
   int8_t* xs = ws + L.stream[cur];
@@ -533,4 +584,16 @@ extern "C" int p2v_swin_forward(const p2v_swin_desc* d, const float* x, float* l
   P2V_TRY(p2v_avgpool_requant(ln, pooled, b, tokens, C, d->pool_in_scale, d->pool_out_scale, 0.f, stream));
   P2V_TRY(swin_gemm(pooled, d->head, logit_codes, b, nullptr, logits, stream));
   return P2V_OK;
+}
+
+extern "C" int p2v_swin_forward(const p2v_swin_desc* d, const float* x, float* logits, int8_t* logit_codes, int b,
+                                void* workspace, void* stream) {
+  P2V_REQUIRE(x != nullptr, "p2v_swin_forward: null pointer");
+  return swin_forward_impl(d, x, nullptr, nullptr, nullptr, logits, logit_codes, b, workspace, stream);
+}
+
+extern "C" int p2v_swin_forward_u8(const p2v_swin_desc* d, const uint8_t* x, const float* mean, const float* stdv,
+                                   float* logits, int8_t* logit_codes, int b, void* workspace, void* stream) {
+  P2V_REQUIRE(x && mean && stdv, "p2v_swin_forward_u8: null pointer");
+  return swin_forward_impl(d, nullptr, x, mean, stdv, logits, logit_codes, b, workspace, stream);
 }

@@ -584,7 +584,42 @@ class SwinIntegerEngine:
                 self._graphs[gk] = (g, xs, out)
             return logits
 
-    def _c_forward(self, bound, b, x, logits, codes):
+    def forward_u8(self, x_u8, mean, std, bit_config=None, graph=True):
+        """The forward from 8-bit pixels [b, c, h, w] (CUDA uint8) with the loader's normalisation constants: the device
+        evaluates (pixel / 255 - mean[c]) / std[c] op for op (p2v_swin_forward_u8), so the logits equal `forward` on the
+        normalised fp32 tensor, for a quarter of the input traffic."""
+        a = self.arch
+        if not (torch.is_tensor(x_u8) and x_u8.is_cuda and x_u8.dtype == torch.uint8):
+            raise _cabi.P2VError('SwinIntegerEngine.forward_u8 expects a CUDA uint8 tensor')
+        if tuple(x_u8.shape[1:]) != (a['in_chans'], a['img_size'], a['img_size']):
+            raise ValueError('expected [b, %d, %d, %d] images, got %s' % (a['in_chans'], a['img_size'], a['img_size'],
+                                                                          tuple(x_u8.shape)))
+        x_u8 = x_u8.to(self.device).contiguous()
+        b, c = x_u8.shape[0], x_u8.shape[1]
+        key, bound = self.bound(bit_config)
+        norm = ((C.c_float * c)(*[float(v) for v in mean]), (C.c_float * c)(*[float(v) for v in std]))
+        nc = a['num_classes']
+        with torch.cuda.device(self.device):
+            gk = (key, b, 'u8', tuple(float(v) for v in mean), tuple(float(v) for v in std))
+            if graph and gk in self._graphs:
+                g, xs, logits = self._graphs[gk]
+                xs.copy_(x_u8)
+                g.replay()
+                return logits.clone()
+            logits = torch.empty(b, nc, dtype=torch.float32, device=self.device)
+            codes = self.buf('logit_codes', b, nc)
+            self._c_forward(bound, b, x_u8, logits, codes, norm)
+            if graph:
+                xs = x_u8.clone()
+                out = torch.empty_like(logits)
+                torch.cuda.current_stream(self.device).synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._c_forward(bound, b, xs, out, codes, norm)
+                self._graphs[gk] = (g, xs, out)
+            return logits
+
+    def _c_forward(self, bound, b, x, logits, codes, norm=None):
         """One p2v_swin_forward call (csrc/p2v_swin.cu): the launch sequence of `_run` without the dumps, on the
         current stream, over one workspace per batch size."""
         lib = _cabi.lib()
@@ -593,8 +628,12 @@ class SwinIntegerEngine:
             _cabi.check(-1)
         ws = self.buf('workspace', nbytes + 1024, dtype=torch.uint8)
         ptr = ws.data_ptr() + (-ws.data_ptr()) % 1024
-        _cabi.check(lib.p2v_swin_forward(C.byref(bound.desc), x.data_ptr(), logits.data_ptr(), codes.data_ptr(), b, ptr,
-                                         _cabi.current_stream(self.device)))
+        st = _cabi.current_stream(self.device)
+        if norm is not None:       # 8-bit pixels + (mean, std) as host float arrays
+            _cabi.check(lib.p2v_swin_forward_u8(C.byref(bound.desc), x.data_ptr(), norm[0], norm[1], logits.data_ptr(),
+                                                codes.data_ptr(), b, ptr, st))
+        else:
+            _cabi.check(lib.p2v_swin_forward(C.byref(bound.desc), x.data_ptr(), logits.data_ptr(), codes.data_ptr(), b, ptr, st))
         self.launches = lib.p2v_swin_launches_per_forward(C.byref(bound.desc))
 
     def forward_dump(self, x, bit_config=None):

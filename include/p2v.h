@@ -91,7 +91,8 @@ int p2v_quant_patchify(const float* x, int8_t* codes, int b, int c, int h, int w
                        float zero_point, void* stream);
 /* The same from 8-bit pixels x [b, c, h, w] (device): the fp32 preprocessing of the reference's loaders,
  * (pixel / 255 - mean[c]) / std[c] (torchvision ToTensor + Normalize, test_quant.py:96-110), is evaluated on the
- * device op for op, so the codes equal those of the fp32 entry on the normalised tensor.  mean / std: HOST arrays [c]. */
+ * device op for op, so the codes equal those of the fp32 entry on the normalised tensor.  mean / std: HOST arrays [c].
+ * p: a multiple of 4 (16-pixel vector path when p and w are multiples of 16, 4-pixel path otherwise). */
 int p2v_quant_patchify_u8(const uint8_t* x, int8_t* codes, int b, int c, int h, int w, int p, float scale,
                           float zero_point, const float* mean, const float* stdv, void* stream);
 
@@ -225,6 +226,10 @@ int64_t p2v_swin_workspace_bytes(const p2v_swin_desc* desc, int b);
 int p2v_swin_launches_per_forward(const p2v_swin_desc* desc);
 int p2v_swin_forward(const p2v_swin_desc* desc, const float* x, float* logits, int8_t* logit_codes, int b,
                      void* workspace, void* stream);
+/* The same from 8-bit pixels x [b, in_chans, img, img] (device) with the loader's normalisation constants (HOST arrays
+ * [in_chans]): (pixel / 255 - mean[c]) / std[c] is evaluated on the device op for op (as p2v_vit_forward_u8). */
+int p2v_swin_forward_u8(const p2v_swin_desc* desc, const uint8_t* x, const float* mean, const float* stdv, float* logits,
+                        int8_t* logit_codes, int b, void* workspace, void* stream);
 
 /* ---- the operators on their own, fp32 in / fp32 out (module-level use) -------------------------------- */
 /* QIntLayerNorm.forward in mode 'int' (models/ptq/layers.py:255-289) on dequantized fp32 rows x [rows, d]:

@@ -339,3 +339,24 @@ def test_swin_engine_from_a_serialised_plan(tmp_path):
         assert torch.equal(fresh.forward(x, bits), eng.forward(x, bits))
     with pytest.raises(KeyError):
         fresh.forward(x, [4] * n)              # no such plan in the files and no calibrated state to build it from
+
+
+def test_swin_uint8_pixel_entry_equals_fp32_entry_on_normalised_images():
+    """p2v_swin_forward_u8 / SwinIntegerEngine.forward_u8: 8-bit pixels plus the loader's mean / std give the logits of
+    the fp32 entry on torchvision's ToTensor + Normalize of the same pixels, bit for bit (all 256 pixel values occur in
+    every channel), eager and through the replayed graph."""
+    import diff_vit_b200 as dv
+    z = np.load(os.path.join(GOLDEN, 'swin_micro.npz'))
+    model = build_swin_micro(z).cuda()
+    dv.calibrate_model(model, [torch.from_numpy(z['x_calib']).cuda()])
+    eng = model.integer_engine()
+    g = torch.Generator().manual_seed(11)
+    img = torch.randint(0, 256, (5, 3, 56, 56), dtype=torch.uint8, generator=g)
+    img[1].reshape(3, -1)[:, :256].copy_(torch.arange(256, dtype=torch.uint8).expand(3, 256))
+    mean, std = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
+    x = img.float().div(255)
+    x = (x - torch.tensor(mean).reshape(1, 3, 1, 1)) / torch.tensor(std).reshape(1, 3, 1, 1)     # ToTensor + Normalize
+    want = eng.forward(x.cuda())
+    got = eng.forward_u8(img.cuda(), mean, std)
+    again = eng.forward_u8(img.cuda(), mean, std)
+    assert torch.equal(got, want) and torch.equal(again, want) and want.std() > 0
