@@ -283,6 +283,29 @@ def swin_side_measurement(device, iters=20):
                     'into the graph buffer and of the logits out of it; calibration (8 images) excluded'}
 
 
+def int8_library_peak(device, n=8192, iters=10):
+    """SURVEY 8d asks for three int8 denominators: nominal 4.5 POP/s, 2 x the measured bf16 burst, and - when the box
+    offers it - the library's own int8 GEMM measured in the same run: torch._int_mm (cuBLASLt) on n^3.  A measurement
+    of the denominator only; nothing on the product path calls it."""
+    import torch
+    try:
+        a = torch.randint(-128, 128, (n, n), dtype=torch.int8, device=device)
+        b = torch.randint(-128, 128, (n, n), dtype=torch.int8, device=device).t()      # column-major second operand
+        for _ in range(3):
+            torch._int_mm(a, b)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(device)
+        e0.record()
+        for _ in range(iters):
+            torch._int_mm(a, b)
+        e1.record()
+        torch.cuda.synchronize(device)
+        ms = e0.elapsed_time(e1) / iters
+        return {'tops': round(2.0 * n ** 3 / (ms * 1e-3) / 1e12, 1), 'source': 'torch._int_mm %d^3 (cuBLASLt int8, s32 out), %d launches' % (n, iters)}
+    except Exception as e:
+        return {'tops': None, 'source': 'torch._int_mm unavailable: %s' % type(e).__name__}
+
+
 def bind_to_gpu_numa_node(local):
     """One process per GPU: run (and first-touch the pinned staging buffers) on the CPUs NVML reports as local to
     this GPU, so that eight ranks do not pull their 154 MB batches across the socket interconnect.  Best effort."""
@@ -522,6 +545,11 @@ def run_ours(args):
     whole = {'achieved_tops': round(model_tops, 2), 'frac_of_peak': round(model_tops / peak, 4),
              'frac_of_nominal_int8': round(model_tops / INT8_NOMINAL_TOPS, 4), 'gop_per_image': GOP_PER_IMAGE,
              'note': 'per GPU'}
+    if world == 1:
+        lib_peak = int8_library_peak(device)
+        whole['int8_library_peak'] = lib_peak
+        if lib_peak['tops']:
+            whole['frac_of_int8_library_peak'] = round(model_tops / lib_peak['tops'], 4)
 
     swin = None
     if world == 1 and not args.no_swin:
