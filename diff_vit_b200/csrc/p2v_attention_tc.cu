@@ -497,9 +497,22 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_co
           // ---- pass 1 (the only read of the raw scores): codes, four to a word, parked in the first four columns of their
           // own 16-column piece; row extrema of this warp's chunks, then of both halves ----
           int mx = (int)0x80000000, mn = 0x7fffffff;
+          // whole 32-key chunks first (no masks, no branches in the loop), then the ragged last chunk in the warp that
+          // owns it (n = 197: 5 keys; with the masked variants inside the loop n = 197 ran slower than n = 208)
+          const int full_chunks = n >> 5;
 #pragma unroll 1
-          for (int c = hf; c < nchunks; c += 2) {
-            const int cnt0 = n - 32 * c;               // > 0
+          for (int c = hf; c < full_chunks; c += 2) {
+            uint32_t v0[16], v1[16], w[4];
+            tmem_ld_32x16(tile + 32 * c, v0);
+            tmem_ld_32x16(tile + 32 * c + 16, v1);
+            tmem_ld_wait();
+            code_piece<false>(v0, 16, mul, c0, w, mx, mn);
+            tmem_st_32x4(tile + 32 * c, w);
+            code_piece<false>(v1, 16, mul, c0, w, mx, mn);
+            tmem_st_32x4(tile + 32 * c + 16, w);
+          }
+          if ((n & 31) != 0 && hf == (full_chunks & 1)) {
+            const int c = full_chunks, cnt0 = n & 31;
             uint32_t v0[16], v1[16], w[4];
             tmem_ld_32x16(tile + 32 * c, v0);
             if (cnt0 > 16) tmem_ld_32x16(tile + 32 * c + 16, v1);
@@ -508,8 +521,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_co
             else code_piece<true>(v0, cnt0, mul, c0, w, mx, mn);
             tmem_st_32x4(tile + 32 * c, w);
             if (cnt0 > 16) {
-              if (cnt0 >= 32) code_piece<false>(v1, 16, mul, c0, w, mx, mn);
-              else code_piece<true>(v1, cnt0 - 16, mul, c0, w, mx, mn);
+              code_piece<true>(v1, cnt0 - 16, mul, c0, w, mx, mn);
               tmem_st_32x4(tile + 32 * c + 16, w);
             }
           }
@@ -533,16 +545,23 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_co
           // ---- pass 2: exact row sum of the integer exp ----
           double acc[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll 1
-          for (int c = hf; c < nchunks; c += 2) {
-            const int cnt0 = n - 32 * c;
+          for (int c = hf; c < full_chunks; c += 2) {
+            uint32_t w0[4], w1[4];
+            tmem_ld_32x4(tile + 32 * c, w0);
+            tmem_ld_32x4(tile + 32 * c + 16, w1);
+            tmem_ld_wait();
+            sum_piece<false>(w0, 16, bias, base_e, acc);
+            sum_piece<false>(w1, 16, bias, base_e, acc);
+          }
+          if ((n & 31) != 0 && hf == (full_chunks & 1)) {
+            const int c = full_chunks, cnt0 = n & 31;
             uint32_t w0[4], w1[4];
             tmem_ld_32x4(tile + 32 * c, w0);
             if (cnt0 > 16) tmem_ld_32x4(tile + 32 * c + 16, w1);
             tmem_ld_wait();
             if (cnt0 >= 16) sum_piece<false>(w0, 16, bias, base_e, acc);
             else sum_piece<true>(w0, cnt0, bias, base_e, acc);
-            if (cnt0 >= 32) sum_piece<false>(w1, 16, bias, base_e, acc);
-            else if (cnt0 > 16) sum_piece<true>(w1, cnt0 - 16, bias, base_e, acc);
+            if (cnt0 > 16) sum_piece<true>(w1, cnt0 - 16, bias, base_e, acc);
           }
           const double part = (acc[0] + acc[1]) + (acc[2] + acc[3]);     // integers < 2^53: exact in any order
           s.x_sum[pair][hf][lane] = part;
