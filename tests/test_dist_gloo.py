@@ -71,8 +71,22 @@ def _worker(rank, world, port, ret):
             part.update(dvd.shard(act))
         ok_pct = (float(part.max_val) == float(whole.max_val) and float(part.min_val) == float(whole.min_val)
                   and float(whole.max_val) == float(torch.quantile(act.reshape(-1), 0.99999)))
+        # the Swin family (BASELINE config 5) through the same distributed calibration: sharded batch, all-reduced
+        # statistics, single-process (= the reference's) scales
+        from test_swin_golden import build_swin_micro
+        zs = np.load(os.path.join(GOLDEN, 'swin_micro.npz'))
+        swin = build_swin_micro(zs)
+        dvd.calibrate_model_distributed(swin, [dvd.shard(torch.from_numpy(zs['x_calib']))])
+        bad_swin, n_swin = [], 0
+        for name, m in swin.named_modules():
+            if isinstance(m, dv.QAct) and m.quantizer.scale is not None and 'mlp.qact0' not in name:
+                n_swin += 1
+                if not np.array_equal(zs['scale/' + name].reshape(-1), m.quantizer.scale.numpy().reshape(-1)):
+                    bad_swin.append(name)
+            if isinstance(m, dv.Mlp) and not np.array_equal(zs['cs/' + name], m.best_scale[-1].numpy()):
+                bad_swin.append(name + '/cs')
         ret[rank] = (len(scales), bad, ok_gather, abs(top1 - float(ref1)) < 1e-9 and abs(top5 - float(ref5)) < 1e-9, n,
-                     ok_pct)
+                     ok_pct, n_swin, bad_swin)
     finally:
         dist.destroy_process_group()
 
@@ -84,7 +98,8 @@ def test_two_rank_calibration_matches_single_process_and_reference():
     ret = mgr.dict()
     mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
     for rank in range(world):
-        count, bad, ok_gather, ok_acc, n, ok_pct = ret[rank]
+        count, bad, ok_gather, ok_acc, n, ok_pct, n_swin, bad_swin = ret[rank]
+        assert n_swin >= 50 and bad_swin == [], 'rank %d: Swin scales differ from the reference calibration: %s' % (rank, bad_swin[:5])
         assert ok_pct, 'sharded percentile calibration differs from the single-process quantile'
         assert count == 71
         assert bad == [], 'rank %d: parameters differ from the single-process reference calibration: %s' % (rank, bad[:5])
