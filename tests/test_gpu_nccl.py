@@ -54,7 +54,23 @@ def _worker(rank, world, port, ret):
         p5, _, _ = model(dvd.shard(odd).contiguous(), bc, False)
         same = same and bool(torch.equal(dvd.gather_logits(p5), full[:5]))
         top1, top5, n = dvd.validate(model, [(dvd.shard(xe).contiguous(), dvd.shard(torch.from_numpy(z['w8/logits']).argmax(1)))], bc)
-        ret[rank] = (bad, same, golden, top1, n)
+        # the Swin family on the same plumbing: NCCL-reduced calibration == the reference's scales, sharded forward on
+        # the Swin integer engine + gather == the unsharded forward == the reference's golden logits
+        from test_swin_golden import build_swin_micro
+        zs = np.load(os.path.join(GOLDEN, 'swin_micro.npz'))
+        swin = build_swin_micro(zs).to(dev)
+        dvd.calibrate_model_distributed(swin, [dvd.shard(torch.from_numpy(zs['x_calib']).to(dev))])
+        bad_swin = [name for name, m in swin.named_modules()
+                    if isinstance(m, dv.QAct) and m.quantizer.scale is not None and 'mlp.qact0' not in name
+                    and m.quantizer.scale.numel() == 1
+                    and not np.array_equal(zs['scale/' + name].reshape(-1), m.quantizer.scale.cpu().numpy().reshape(-1))]
+        xs = torch.from_numpy(zs['x_eval']).to(dev)
+        with torch.no_grad():
+            sfull = swin(xs)
+            spart = swin(dvd.shard(xs).contiguous())
+        swin_ok = (swin._engine_off is None and bool(torch.equal(dvd.gather_logits(spart), sfull))
+                   and float(np.abs(sfull.cpu().numpy() - zs['w8/logits']).max()) <= 2 * float(swin.act_out.quantizer.scale))
+        ret[rank] = (bad, same, golden, top1, n, bad_swin, swin_ok)
     finally:
         dist.destroy_process_group()
 
@@ -67,7 +83,8 @@ def test_two_gpus_nccl_calibration_and_logits_gather():
     ret = mp.Manager().dict()
     mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
     for rank in range(world):
-        bad, same, golden, top1, n = ret[rank]
+        bad, same, golden, top1, n, bad_swin, swin_ok = ret[rank]
         assert bad == [], bad
+        assert bad_swin == [] and swin_ok, bad_swin
         assert same and golden
         assert n == 6 and top1 >= 99.0       # all six eval images, labels = the reference's own argmax
